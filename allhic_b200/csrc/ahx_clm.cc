@@ -1,0 +1,372 @@
+// ahx_clm.cc -- host-side CLM ingestion for libahx (no CUDA in this file).
+//
+// Product code: implements NewCLM/readRE/readClmLines/readClm of the reference
+// (clm.go:121-240) plus GoldenArray/SumLog (base.go:130-167) with the same map
+// semantics, then freezes the two Go maps (`contacts`, `orientedContacts`)
+// into the flat pair table documented in include/ahx.h, which is what gets
+// uploaded to the GPU.  Parsing is multi-threaded: lines are tokenised and
+// histogrammed in parallel, then applied to the maps in file order so that
+// "last line wins" / "smallest SumLog wins" behave exactly like the
+// single-threaded Go loop.
+#include "ahx_internal.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace ahx {
+
+static thread_local std::string g_err;
+void set_global_error(const std::string &s) { g_err = s; }
+const char *global_error() { return g_err.c_str(); }
+
+// Go's math.Log (FDLIBM e_log algorithm).  Used instead of libm so that SumLog
+// ties (clm.go:230 `meanDist < p.meanDist`) resolve as they do in the Go
+// binary on amd64, where the compiler never fuses multiply-adds.
+#pragma GCC push_options
+#pragma GCC optimize("fp-contract=off")
+double go_log(double x) {
+  constexpr double kLn2Hi = 6.93147180369123816490e-01, kLn2Lo = 1.90821492927058770002e-10;
+  constexpr double kL[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                            2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                            1.479819860511658591e-01};
+  if (std::isnan(x) || (std::isinf(x) && x > 0)) return x;
+  if (x < 0) return std::nan("");
+  if (x == 0) return -INFINITY;
+  int e;
+  double m = std::frexp(x, &e);
+  if (m < M_SQRT1_2) { m *= 2; --e; }
+  const double f = m - 1, k = static_cast<double>(e);
+  const double s = f / (2 + f), z = s * s, w = z * z;
+  const double odd = z * (kL[0] + w * (kL[2] + w * (kL[4] + w * kL[6])));
+  const double even = w * (kL[1] + w * (kL[3] + w * kL[5]));
+  const double r = odd + even, hfsq = 0.5 * f * f;
+  return k * kLn2Hi - ((hfsq - (s * (hfsq + r) + k * kLn2Lo)) - f);
+}
+
+// base.go:156-167 GoldenArray + base.go:138-144 SumLog in one pass.
+void golden_and_sumlog(const int64_t *d, int64_t n, int32_t *bins, double *sumlog) {
+  for (int k = 0; k < AHX_BB; ++k) bins[k] = 0;
+  double sum = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double lg = go_log(static_cast<double>(d[i]));
+    sum += lg;
+    const double q = lg / 0.4812118250596684;                              // PHI, base.go:36
+    const double r = q < 0 ? std::ceil(q - 0.5) : std::floor(q + 0.5);      // Round, base.go:130
+    int c = 18;                                                            // LB; also Go's int(NaN/-Inf)
+    if (r >= 29.0) c = 29; else if (r > 18.0) c = static_cast<int>(r);
+    bins[c - 18]++;
+  }
+  *sumlog = sum;
+}
+#pragma GCC pop_options
+
+static inline uint8_t rr(uint8_t b) { return b == '-' ? '+' : '-'; }  // clm.go:160
+static inline uint64_t pair_key(int32_t a, int32_t b) { return (static_cast<uint64_t>(static_cast<uint32_t>(a)) << 32) | static_cast<uint32_t>(b); }
+static inline uint64_t okey(int32_t a, int32_t b, uint8_t ao, uint8_t bo) {
+  return (static_cast<uint64_t>(static_cast<uint32_t>(a)) << 40) | (static_cast<uint64_t>(static_cast<uint32_t>(b)) << 16) | (static_cast<uint64_t>(ao) << 8) | bo;
+}
+
+}  // namespace ahx
+
+using namespace ahx;
+
+struct ahx_clm {
+  int32_t n = 0;
+  std::vector<std::string> names;
+  std::vector<int64_t> sizes;
+  std::unordered_map<std::string, int32_t> tig2idx;
+  struct Contact { int32_t ai, bi; int32_t strand; int64_t nlinks; double mean_dist; };
+  struct Oriented { int32_t ai, bi; uint8_t ao, bo; std::array<int32_t, AHX_BB> g; };
+  std::vector<Contact> contacts;                       // insertion order
+  std::unordered_map<uint64_t, int64_t> cmap;
+  std::vector<Oriented> oriented;                      // insertion order
+  std::unordered_map<uint64_t, int64_t> omap;
+  bool finalized = false;
+  std::vector<int32_t> pa, pb, nl, slots, hist;
+  std::vector<int8_t> strand;
+
+  void apply_line(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g,
+                  double mean_dist, int64_t nlinks) {
+    finalized = false;
+    const int32_t st = (ao != bo) ? -1 : 1;                                 // clm.go:224-227
+    auto it = cmap.find(pair_key(ai, bi));
+    if (it != cmap.end()) {
+      Contact &c = contacts[it->second];
+      if (mean_dist < c.mean_dist) { c.strand = st; c.nlinks = nlinks; c.mean_dist = mean_dist; }
+    } else {
+      cmap.emplace(pair_key(ai, bi), static_cast<int64_t>(contacts.size()));
+      contacts.push_back({ai, bi, st, nlinks, mean_dist});
+    }
+    put_oriented(ai, bi, ao, bo, g);
+    put_oriented(bi, ai, rr(bo), rr(ao), g);                                // clm.go:238
+  }
+  void put_oriented(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g) {
+    auto it = omap.find(okey(ai, bi, ao, bo));
+    if (it != omap.end()) { oriented[it->second].g = g; return; }
+    omap.emplace(okey(ai, bi, ao, bo), static_cast<int64_t>(oriented.size()));
+    oriented.push_back({ai, bi, ao, bo, g});
+  }
+};
+
+namespace {
+
+struct Mapped {
+  const char *p = nullptr; size_t n = 0; int fd = -1;
+  bool open(const char *path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) return false;
+    n = static_cast<size_t>(st.st_size);
+    if (n == 0) { p = ""; return true; }
+    void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) return false;
+    p = static_cast<const char *>(m);
+    return true;
+  }
+  ~Mapped() { if (p && n) munmap(const_cast<char *>(p), n); if (fd >= 0) close(fd); }
+};
+
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+// strconv.Atoi with the error dropped (clm.go:152,186,190): invalid -> 0.
+inline int64_t atoi_or_zero(const char *s, size_t n) {
+  if (n == 0) return 0;
+  size_t i = 0; bool neg = false;
+  if (s[0] == '+' || s[0] == '-') { neg = s[0] == '-'; i = 1; if (n == 1) return 0; }
+  int64_t v = 0;
+  for (; i < n; ++i) { const unsigned d = static_cast<unsigned>(s[i] - '0'); if (d > 9) return 0; v = v * 10 + d; }
+  return neg ? -v : v;
+}
+
+struct ParsedLine { int32_t ai, bi; uint8_t ao, bo; std::array<int32_t, AHX_BB> g; double sumlog; int64_t nlinks; };
+
+// Parses lines of [beg,end) (beg at a line start).  Returns false on a line the
+// reference would panic on.
+bool parse_chunk(const ahx_clm &clm, const char *buf, size_t beg, size_t end, size_t total,
+                 std::vector<ParsedLine> *out, std::string *err) {
+  std::vector<int64_t> dists;
+  size_t p = beg;
+  while (p < end) {
+    size_t e = p;
+    while (e < total && buf[e] != '\n') ++e;
+    const size_t next = e + 1;
+    size_t a = p, b = e;
+    while (a < b && is_space(buf[a])) ++a;                                  // strings.TrimSpace
+    while (b > a && is_space(buf[b - 1])) --b;
+    if (a == b) {
+      if (next >= total) break;                                            // trailing blank at EOF
+      *err = "empty line in CLM file (the reference panics on it)"; return false;
+    }
+    size_t t1 = a; while (t1 < b && buf[t1] != '\t') ++t1;
+    size_t s1 = a; while (s1 < t1 && buf[s1] != ' ') ++s1;
+    if (s1 == a || s1 + 1 >= t1 || t1 >= b) { *err = "malformed CLM line: expected `a± b±\\tN\\td1 d2 ...`"; return false; }
+    size_t s2 = s1 + 1; while (s2 < t1 && buf[s2] != ' ') ++s2;
+    size_t t2 = t1 + 1; while (t2 < b && buf[t2] != '\t') ++t2;
+    if (t2 >= b) { *err = "malformed CLM line: no distance column"; return false; }
+    ParsedLine pl;
+    pl.ao = static_cast<uint8_t>(buf[s1 - 1]);
+    pl.bo = static_cast<uint8_t>(buf[s2 - 1]);
+    auto ia = clm.tig2idx.find(std::string(buf + a, s1 - 1 - a));
+    auto ib = clm.tig2idx.find(std::string(buf + s1 + 1, s2 - 1 - (s1 + 1)));
+    if (ia != clm.tig2idx.end() && ib != clm.tig2idx.end()) {              // clm.go:211-218
+      pl.ai = ia->second; pl.bi = ib->second;
+      size_t q = t2 + 1, wend = q;
+      while (wend < b && buf[wend] != '\t') ++wend;
+      dists.clear();
+      for (;;) {                                                           // Split(words[2], " ")
+        const size_t w = q;
+        while (q < wend && buf[q] != ' ') ++q;
+        dists.push_back(atoi_or_zero(buf + w, q - w));
+        if (q >= wend) break;
+        ++q;
+      }
+      pl.nlinks = static_cast<int64_t>(dists.size());                      // len(line.links), clm.go:228
+      golden_and_sumlog(dists.data(), pl.nlinks, pl.g.data(), &pl.sumlog);
+      out->push_back(pl);
+    }
+    p = next;
+  }
+  return true;
+}
+
+int read_re(ahx_clm *clm, const char *refile) {                           // clm.go:141-157
+  Mapped m;
+  if (!m.open(refile)) { set_global_error(std::string("cannot open REfile `") + refile + "`"); return AHX_ERR_IO; }
+  size_t p = 0;
+  while (p < m.n) {
+    size_t e = p;
+    while (e < m.n && m.p[e] != '\n') ++e;
+    size_t q = p; std::string_view first, last;
+    while (q < e) {                                                        // strings.Fields
+      while (q < e && is_space(m.p[q])) ++q;
+      if (q >= e) break;
+      const size_t w = q;
+      while (q < e && !is_space(m.p[q])) ++q;
+      if (first.empty()) first = std::string_view(m.p + w, q - w);
+      last = std::string_view(m.p + w, q - w);
+    }
+    if (!first.empty() && first[0] != '#') {
+      clm->names.emplace_back(first);
+      clm->sizes.push_back(atoi_or_zero(last.data(), last.size()));
+      clm->tig2idx[clm->names.back()] = static_cast<int32_t>(clm->names.size() - 1);
+    }
+    p = e + 1;
+  }
+  clm->n = static_cast<int32_t>(clm->names.size());
+  return AHX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm **out) {
+  if (!clmfile || !refile || !out) { set_global_error("ahx_clm_parse: null argument"); return AHX_ERR_ARG; }
+  auto *clm = new ahx_clm();
+  int rc = read_re(clm, refile);
+  if (rc != AHX_OK) { delete clm; return rc; }
+  Mapped m;
+  if (!m.open(clmfile)) { set_global_error(std::string("cannot open clmfile `") + clmfile + "`"); delete clm; return AHX_ERR_IO; }
+  if (nthreads <= 0) nthreads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+  nthreads = static_cast<int>(std::min<size_t>(static_cast<size_t>(nthreads), m.n / (1 << 16) + 1));
+  std::vector<size_t> cut(nthreads + 1);
+  cut[0] = 0; cut[nthreads] = m.n;
+  for (int t = 1; t < nthreads; ++t) {
+    size_t c = m.n / nthreads * t;
+    while (c < m.n && m.p[c] != '\n') ++c;
+    cut[t] = std::min(m.n, c + 1);
+  }
+  std::vector<std::vector<ParsedLine>> parts(nthreads);
+  std::vector<std::string> errs(nthreads);
+  std::vector<char> ok(nthreads, 1);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t] { ok[t] = parse_chunk(*clm, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t]); });
+  for (auto &x : th) x.join();
+  for (int t = 0; t < nthreads; ++t)
+    if (!ok[t]) { set_global_error(errs[t]); delete clm; return AHX_ERR_IO; }
+  for (auto &part : parts)
+    for (auto &pl : part) clm->apply_line(pl.ai, pl.bi, pl.ao, pl.bo, pl.g, pl.sumlog, pl.nlinks);
+  rc = ahx_clm_finalize(clm);
+  if (rc != AHX_OK) { delete clm; return rc; }
+  *out = clm;
+  return AHX_OK;
+}
+
+int ahx_clm_new(int32_t n_tigs, const int64_t *sizes, ahx_clm **out) {
+  if (n_tigs < 0 || (n_tigs > 0 && !sizes) || !out) { set_global_error("ahx_clm_new: bad argument"); return AHX_ERR_ARG; }
+  auto *clm = new ahx_clm();
+  clm->n = n_tigs;
+  clm->sizes.assign(sizes, sizes + n_tigs);
+  clm->names.assign(n_tigs, std::string());
+  *out = clm;
+  return AHX_OK;
+}
+
+int ahx_clm_add_line(ahx_clm *clm, int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const int64_t *dists, int64_t n) {
+  if (!clm || ai < 0 || bi < 0 || ai >= clm->n || bi >= clm->n || n < 0 || (n > 0 && !dists)) {
+    set_global_error("ahx_clm_add_line: bad argument"); return AHX_ERR_ARG;
+  }
+  std::array<int32_t, AHX_BB> g; double sl;
+  golden_and_sumlog(dists, n, g.data(), &sl);
+  clm->apply_line(ai, bi, ao, bo, g, sl, n);
+  return AHX_OK;
+}
+
+int ahx_clm_finalize(ahx_clm *clm) {
+  if (!clm) { set_global_error("ahx_clm_finalize: null"); return AHX_ERR_ARG; }
+  if (clm->finalized) return AHX_OK;
+  // rows = unordered pairs {a<b}, sorted by (a,b) so that consecutive rows share `a`
+  std::vector<uint64_t> keys;
+  keys.reserve(clm->contacts.size());
+  for (auto &c : clm->contacts) if (c.ai != c.bi) keys.push_back(pair_key(std::min(c.ai, c.bi), std::max(c.ai, c.bi)));
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  const size_t E = keys.size();
+  auto row_of = [&](int32_t a, int32_t b) -> int64_t {
+    const uint64_t k = pair_key(std::min(a, b), std::max(a, b));
+    auto it = std::lower_bound(keys.begin(), keys.end(), k);
+    return (it != keys.end() && *it == k) ? static_cast<int64_t>(it - keys.begin()) : -1;
+  };
+  clm->pa.resize(E); clm->pb.resize(E); clm->nl.assign(E, 0); clm->strand.assign(E, 0);
+  clm->slots.assign(E * 8, -1); clm->hist.clear();
+  for (size_t e = 0; e < E; ++e) { clm->pa[e] = static_cast<int32_t>(keys[e] >> 32); clm->pb[e] = static_cast<int32_t>(keys[e] & 0xffffffffu); }
+  // M(): P[ai][bi] = P[bi][ai] = nlinks per map entry (clm.go:440-445).  Go's map
+  // order is random; when both (a,b) and (b,a) keys exist (never written by
+  // `extract`, extract.go:477-481) the later-inserted key wins here.
+  for (auto &c : clm->contacts) {
+    if (c.ai == c.bi) continue;
+    const int64_t e = row_of(c.ai, c.bi);
+    if (c.nlinks > INT32_MAX) { set_global_error("nlinks exceeds int32"); return AHX_ERR_ARG; }
+    clm->nl[e] = static_cast<int32_t>(c.nlinks);
+    clm->strand[e] = static_cast<int8_t>(c.strand);
+  }
+  for (auto &o : clm->oriented) {
+    if (o.ai == o.bi) continue;                       // Q[a][a] is never read (i<j are distinct contigs)
+    const bool sa = o.ao == '-', sb = o.bo == '-';
+    if ((!sa && o.ao != '+') || (!sb && o.bo != '+')) continue;  // can never equal a Signs byte
+    const int64_t e = row_of(o.ai, o.bi);
+    if (e < 0) continue;
+    const int dir = o.ai < o.bi ? 0 : 1;
+    const int32_t h = static_cast<int32_t>(clm->hist.size() / AHX_BB);
+    clm->hist.insert(clm->hist.end(), o.g.begin(), o.g.end());
+    clm->slots[e * 8 + dir * 4 + 2 * (sa ? 1 : 0) + (sb ? 1 : 0)] = h;
+  }
+  clm->finalized = true;
+  return AHX_OK;
+}
+
+void ahx_clm_free(ahx_clm *clm) { delete clm; }
+int32_t ahx_clm_ntigs(const ahx_clm *clm) { return clm ? clm->n : 0; }
+const char *ahx_clm_tig_name(const ahx_clm *clm, int32_t i) { return (clm && i >= 0 && i < clm->n) ? clm->names[i].c_str() : ""; }
+int64_t ahx_clm_tig_size(const ahx_clm *clm, int32_t i) { return (clm && i >= 0 && i < clm->n) ? clm->sizes[i] : 0; }
+int32_t ahx_clm_tig_index(const ahx_clm *clm, const char *name) {
+  if (!clm || !name) return -1;
+  auto it = clm->tig2idx.find(name);
+  return it == clm->tig2idx.end() ? -1 : it->second;
+}
+int64_t ahx_clm_npairs(const ahx_clm *clm) { return (clm && clm->finalized) ? static_cast<int64_t>(clm->pa.size()) : -1; }
+int64_t ahx_clm_nhists(const ahx_clm *clm) { return (clm && clm->finalized) ? static_cast<int64_t>(clm->hist.size() / AHX_BB) : -1; }
+int ahx_clm_get_pairs(const ahx_clm *clm, int32_t *pa, int32_t *pb, int32_t *nl, int8_t *strand, int32_t *slots) {
+  if (!clm || !clm->finalized) { set_global_error("ahx_clm_get_pairs: not finalized"); return AHX_ERR_STATE; }
+  const size_t E = clm->pa.size();
+  if (pa) std::memcpy(pa, clm->pa.data(), E * 4);
+  if (pb) std::memcpy(pb, clm->pb.data(), E * 4);
+  if (nl) std::memcpy(nl, clm->nl.data(), E * 4);
+  if (strand) std::memcpy(strand, clm->strand.data(), E);
+  if (slots) std::memcpy(slots, clm->slots.data(), E * 8 * 4);
+  return AHX_OK;
+}
+int ahx_clm_get_hists(const ahx_clm *clm, int32_t *hist) {
+  if (!clm || !clm->finalized) { set_global_error("ahx_clm_get_hists: not finalized"); return AHX_ERR_STATE; }
+  if (hist) std::memcpy(hist, clm->hist.data(), clm->hist.size() * 4);
+  return AHX_OK;
+}
+
+}  // extern "C"
+
+// Internal accessors for ahx_load_clm (ahx_core.cu).
+namespace ahx {
+ClmView view_of(const ahx_clm *clm) {
+  ClmView v{};
+  v.n = clm->n; v.sizes = clm->sizes.data(); v.E = static_cast<int64_t>(clm->pa.size());
+  v.pa = clm->pa.data(); v.pb = clm->pb.data(); v.nl = clm->nl.data(); v.strand = clm->strand.data();
+  v.slots = clm->slots.data(); v.H = static_cast<int64_t>(clm->hist.size() / AHX_BB); v.hist = clm->hist.data();
+  v.finalized = clm->finalized;
+  return v;
+}
+}  // namespace ahx

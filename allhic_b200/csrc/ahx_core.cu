@@ -1,0 +1,743 @@
+// ahx_core.cu -- context, upload, and the batched Tour.Evaluate / EvaluateQ kernels.
+//
+// Kernels in this file (all sm_100a, no tensor cores: the path is gather +
+// fp64 divide/log + reduction):
+//   eval_m_sparse_kernel  Tour.Evaluate (evaluate.go:116-143) in contig space:
+//                         one CTA scores T tours against the nonzero pairs of M
+//   eval_m_dense_kernel   the same score in position space, gathering dense M
+//                         (north_star's literal formulation; one CTA per tour)
+//   eval_q_kernel         CLM.EvaluateQ (orientation.go:159-193), one CTA per
+//                         (tour, signs) individual
+//   build_dense_kernel    scatters the pair table into the dense N x N int32 M
+//   probe_* kernels       DFMA / fp64-divide / L2 read peaks for the roofline
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "ahx_ctx.h"
+#include "ahx_device.cuh"
+
+namespace ahx {
+
+int fail(ahx_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  set_global_error(msg);
+  return code;
+}
+int cuda_fail(ahx_ctx *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, AHX_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+int enter(ahx_ctx *ctx, bool need_loaded) {
+  if (!ctx) return fail(nullptr, AHX_ERR_ARG, "null context");
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaSetDevice");
+  if (need_loaded && !ctx->loaded) return fail(ctx, AHX_ERR_STATE, "no linkage group loaded (call ahx_load first)");
+  return AHX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Tour.Evaluate, contig-space kernel.
+//   grid = ceil(P / T) CTAs, kBlock threads.  Dynamic shared memory:
+//     x    double[N*T]   mid-point of contig c in tour t at x[c*T+t] (NaN = inactive)
+//     tig  int[L]        staging of one tour
+//   XGLOBAL: x lives in a per-CTA slice of global memory instead (N too large
+//   for shared memory); T must be 1.
+// ---------------------------------------------------------------------------
+template <int T, typename Coo, typename IdxT, bool XGLOBAL>
+__global__ void __launch_bounds__(kBlock)
+eval_m_sparse_kernel(const IdxT *__restrict__ tours, const int *__restrict__ rows, int P, int L, int N,
+                     const long long *__restrict__ sizes, const typename Coo::Elem *__restrict__ coo, int E,
+                     double *__restrict__ xglobal, double *__restrict__ out, int *__restrict__ errflag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long scan_scratch[kWarps];
+  __shared__ double red_scratch[kWarps];
+  const int tid = threadIdx.x;
+  double *x; int *tig;
+  if constexpr (XGLOBAL) {
+    x = xglobal + static_cast<size_t>(blockIdx.x) * N * T;
+    tig = reinterpret_cast<int *>(smem_raw);
+  } else {
+    x = reinterpret_cast<double *>(smem_raw);
+    tig = reinterpret_cast<int *>(smem_raw + sizeof(double) * static_cast<size_t>(N) * T);
+  }
+  const int p0 = blockIdx.x * T;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int i = tid; i < N * T; i += kBlock) x[i] = qnan;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (p0 + t >= P) break;
+    const int row = rows ? rows[p0 + t] : p0 + t;
+    const IdxT *src = tours + static_cast<size_t>(row) * L;
+    for (int i = tid; i < L; i += kBlock) {
+      int v = static_cast<int>(src[i]);
+      if (static_cast<unsigned>(v) >= static_cast<unsigned>(N)) { *errflag = 1; v = 0; }  // reported by the host wrapper
+      tig[i] = v;
+    }
+    __syncthreads();
+    scatter_mids<T>(tig, L, sizes, x, t, scan_scratch, tid);
+    __syncthreads();
+  }
+  double acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = 0.0;
+  accumulate_pairs<T, Coo>(x, coo, E, acc, tid);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const double s = block_sum(acc[t], red_scratch, tid);
+    if (tid == 0 && p0 + t < P) {
+      const int row = rows ? rows[p0 + t] : p0 + t;
+      out[row] = 0.0 - s;  // score starts at +0.0 and only subtracts (evaluate.go:128,140)
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Tour.Evaluate, position-space kernel over the dense int32 M (literal loop of
+// evaluate.go:129-141).  One CTA per tour; warp w owns rows i = w, w+8, ...;
+// lanes sweep j = i+1.. and stop at the first j beyond LIMIT.
+// Shared memory: tig int[L], mid double[L].
+// ---------------------------------------------------------------------------
+template <typename IdxT>
+__global__ void __launch_bounds__(kBlock)
+eval_m_dense_kernel(const IdxT *__restrict__ tours, int P, int L, int N, const long long *__restrict__ sizes,
+                    const int *__restrict__ M, double *__restrict__ out, int *__restrict__ errflag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long scan_scratch[kWarps];
+  __shared__ double red_scratch[kWarps];
+  double *mid = reinterpret_cast<double *>(smem_raw);
+  int *tig = reinterpret_cast<int *>(smem_raw + sizeof(double) * static_cast<size_t>(L));
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const IdxT *src = tours + static_cast<size_t>(blockIdx.x) * L;
+  for (int i = tid; i < L; i += kBlock) {
+    int v = static_cast<int>(src[i]);
+    if (static_cast<unsigned>(v) >= static_cast<unsigned>(N)) { *errflag = 1; v = 0; }
+    tig[i] = v;
+  }
+  __syncthreads();
+  {
+    const int per = (L + kBlock - 1) / kBlock;
+    const int beg = min(L, tid * per), end = min(L, beg + per);
+    long long local = 0;
+    for (int i = beg; i < end; ++i) local += __ldg(sizes + tig[i]);
+    long long cum = block_excl_scan(local, scan_scratch, tid);
+    for (int i = beg; i < end; ++i) {
+      const long long s = __ldg(sizes + tig[i]);
+      mid[i] = static_cast<double>(2 * cum + s) * 0.5;
+      cum += s;
+    }
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = wid; i < L - 1; i += kWarps) {
+    const int *row = M + static_cast<size_t>(tig[i]) * N;
+    const double mi = mid[i];
+    for (int j = i + 1 + lane; j < L; j += 32) {
+      const double d = mid[j] - mi;
+      if (d > kLimit) break;
+      const int n = __ldg(row + tig[j]);
+      if (n != 0) acc += static_cast<double>(n) / d;
+    }
+  }
+  const double s = block_sum(acc, red_scratch, tid);
+  if (tid == 0) out[blockIdx.x] = 0.0 - s;
+}
+
+__global__ void build_dense_kernel(const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ nl,
+                                   long long E, int N, int *__restrict__ M) {
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < E;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int a = pa[e], b = pb[e], n = nl[e];
+    M[static_cast<size_t>(a) * N + b] = n;   // clm.go:443-444
+    M[static_cast<size_t>(b) * N + a] = n;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CLM.EvaluateQ (orientation.go:159-193).  One CTA per individual.
+// Shared memory: cum long long[L] | pos int[N] | tig int[L] | sg uint8[N].
+// For a stored pair {a<b}: (i,j) = sorted tour positions; the contig at i is the
+// row index of Q and the one at j the column, so the GArray looked up is
+// orientedContacts[(first, second, Signs[first], Signs[second])]
+// (orientation.go:145-150) = slots[e][dir][2*[sf=='-'] + [ss=='-']].
+// The sentinel `continue` and the LIMIT `break` of the reference reduce to
+// per-pair masks because dist is monotone in j for fixed i.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+eval_q_kernel(const int *__restrict__ tours, int shared_tour, int P, int L, int N, const long long *__restrict__ sizes,
+              const unsigned char *__restrict__ signs, const int *__restrict__ pa, const int *__restrict__ pb,
+              const int *__restrict__ slots, const int *__restrict__ hist, int E, double *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long scan_scratch[kWarps];
+  __shared__ double red_scratch[kWarps];
+  long long *cum = reinterpret_cast<long long *>(smem_raw);
+  int *pos = reinterpret_cast<int *>(smem_raw + sizeof(long long) * static_cast<size_t>(L));
+  int *tig = pos + N;
+  unsigned char *sg = reinterpret_cast<unsigned char *>(tig + L);
+  const int tid = threadIdx.x, p = blockIdx.x;
+  const int *src = tours + (shared_tour ? 0 : static_cast<size_t>(p) * L);
+  const unsigned char *sgsrc = signs + static_cast<size_t>(p) * N;
+  for (int i = tid; i < N; i += kBlock) { pos[i] = -1; sg[i] = sgsrc[i]; }
+  for (int i = tid; i < L; i += kBlock) tig[i] = src[i];
+  __syncthreads();
+  {
+    const int per = (L + kBlock - 1) / kBlock;
+    const int beg = min(L, tid * per), end = min(L, beg + per);
+    long long local = 0;
+    for (int i = beg; i < end; ++i) local += __ldg(sizes + tig[i]);
+    long long c = block_excl_scan(local, scan_scratch, tid);
+    for (int i = beg; i < end; ++i) {
+      cum[i] = c;                                  // cumsize[i], orientation.go:167-170
+      pos[tig[i]] = i;
+      c += __ldg(sizes + tig[i]);
+    }
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int e = tid; e < E; e += kBlock) {
+    const int a = __ldg(pa + e), b = __ldg(pb + e);
+    const int px = pos[a], py = pos[b];
+    if (px < 0 || py < 0) continue;
+    const int i = min(px, py), j = max(px, py);
+    const long long dist = cum[j - 1] - cum[i];    // orientation.go:181 (sic)
+    if (dist > kLimitI) continue;
+    const int dir = px < py ? 0 : 1;
+    const unsigned char sf = sg[dir ? b : a], ss = sg[dir ? a : b];
+    if ((sf != '+' && sf != '-') || (ss != '+' && ss != '-')) continue;
+    const int h = __ldg(slots + static_cast<size_t>(e) * 8 + dir * 4 + 2 * (sf == '-') + (ss == '-'));
+    if (h < 0) continue;                           // Q[a][b][0] == -1
+    const int4 *hp = reinterpret_cast<const int4 *>(hist + static_cast<size_t>(h) * 12);
+    const int4 q0 = __ldg(hp), q1 = __ldg(hp + 1), q2 = __ldg(hp + 2);
+    const int q[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      if (q[k] != 0) acc += static_cast<double>(q[k]) * log(static_cast<double>(c_GR[k] + dist));
+  }
+  const double s = block_sum(acc, red_scratch, tid);
+  if (tid == 0) out[p] = 0.0 - s;
+}
+
+// ---------------------------------------------------------------------------
+// Roofline probes.
+// ---------------------------------------------------------------------------
+__global__ void probe_dfma_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void probe_ddiv_kernel(double *out, int iters) {
+  double d0 = 3.0 + threadIdx.x, d1 = d0 + 0.5, d2 = d0 + 0.25, d3 = d0 + 0.125;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int i = 0; i < iters; ++i) {
+    s0 += 7.0 / d0; s1 += 7.0 / d1; s2 += 7.0 / d2; s3 += 7.0 / d3;
+    d0 += 1.0; d1 += 1.0; d2 += 1.0; d3 += 1.0;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s0 + s1 + s2 + s3;
+}
+__global__ void probe_read_kernel(const int4 *__restrict__ in, size_t n, int reps, int4 *out) {
+  int4 acc = make_int4(0, 0, 0, 0);
+  for (int r = 0; r < reps; ++r)
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const int4 v = __ldcg(in + i);
+      acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+    }
+  if (acc.x == 0x7fffffff) out[0] = acc;
+}
+__global__ void fill_kernel(int4 *p, size_t n, int v) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = make_int4(v, v, v, v);
+}
+
+// ---------------------------------------------------------------------------
+// Launch helpers.
+// ---------------------------------------------------------------------------
+size_t eval_m_smem_bytes(int T, int32_t N, int32_t L) {
+  return sizeof(double) * static_cast<size_t>(N) * T + sizeof(int) * static_cast<size_t>(L);
+}
+
+static int pick_T(const ahx_ctx *ctx, int32_t P, int32_t L) {
+  if (const char *env = getenv("AHX_EVAL_T")) {
+    const int t = atoi(env);
+    if ((t == 1 || t == 2 || t == 4) && eval_m_smem_bytes(t, ctx->N, L) <= ctx->smem_optin - 1024) return t;
+  }
+  // Amortise the COO stream over several tours while keeping >= 2 CTAs per SM
+  // and enough CTAs to fill the machine.
+  for (int t : {4, 2}) {
+    const size_t bytes = eval_m_smem_bytes(t, ctx->N, L);
+    if (bytes * 2 + 4096 <= ctx->smem_optin && (P + t - 1) / t >= 4 * ctx->sm_count) return t;
+  }
+  return 1;
+}
+
+template <int T, typename Coo, typename IdxT, bool XG>
+static cudaError_t launch_sparse_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L,
+                                   double *out, cudaStream_t s) {
+  auto kern = eval_m_sparse_kernel<T, Coo, IdxT, XG>;
+  const size_t smem = XG ? sizeof(int) * static_cast<size_t>(L) : eval_m_smem_bytes(T, ctx->N, L);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const typename Coo::Elem *coo;
+  if constexpr (sizeof(typename Coo::Elem) == 8) coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo16.p);
+  else coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo32.p);
+  const int grid = (P + T - 1) / T;
+  double *xg = nullptr;
+  if (XG) {
+    e = ctx->d_xglobal.reserve(static_cast<size_t>(grid) * ctx->N * T);
+    if (e != cudaSuccess) return e;
+    xg = ctx->d_xglobal.p;
+  }
+  kern<<<grid, kBlock, smem, s>>>(tours, rows, P, L, ctx->N, ctx->d_sizes.p, coo, static_cast<int>(ctx->E), xg, out, ctx->d_errflag.p);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+template <typename Coo, typename IdxT>
+static cudaError_t launch_sparse_c(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L,
+                                   double *out, cudaStream_t s) {
+  if (eval_m_smem_bytes(1, ctx->N, L) + 1024 > ctx->smem_optin)
+    return launch_sparse_t<1, Coo, IdxT, true>(ctx, tours, rows, P, L, out, s);
+  switch (pick_T(ctx, P, L)) {
+    case 4: return launch_sparse_t<4, Coo, IdxT, false>(ctx, tours, rows, P, L, out, s);
+    case 2: return launch_sparse_t<2, Coo, IdxT, false>(ctx, tours, rows, P, L, out, s);
+    default: return launch_sparse_t<1, Coo, IdxT, false>(ctx, tours, rows, P, L, out, s);
+  }
+}
+
+int launch_eval_m_sparse(ahx_ctx *ctx, const int32_t *d_tours, const uint16_t *d_tours16, const int32_t *d_rows,
+                         int32_t P, int32_t L, double *d_out, cudaStream_t s) {
+  if (P == 0) return AHX_OK;
+  cudaError_t e;
+  if (d_tours16) {
+    e = ctx->coo16 ? launch_sparse_c<Coo16, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s)
+                   : launch_sparse_c<Coo32, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s);
+  } else {
+    e = ctx->coo16 ? launch_sparse_c<Coo16, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s)
+                   : launch_sparse_c<Coo32, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s);
+  }
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "eval_m_sparse_kernel launch");
+  return AHX_OK;
+}
+
+static int ensure_dense(ahx_ctx *ctx) {
+  if (ctx->dense_ready) return AHX_OK;
+  const size_t nn = static_cast<size_t>(ctx->N) * ctx->N;
+  AHX_CUDA(ctx, ctx->d_M.reserve(nn));
+  AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_M.p, 0, nn * sizeof(int32_t), ctx->stream));  // Make2DSlice zeros, base.go:279
+  if (ctx->E > 0) {
+    ahx::DevBuf<int32_t> d_nl;
+    AHX_CUDA(ctx, d_nl.reserve(ctx->E));
+    AHX_CUDA(ctx, cudaMemcpyAsync(d_nl.p, ctx->h_nl.data(), ctx->E * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = static_cast<int>(std::min<int64_t>((ctx->E + 255) / 256, 4096));
+    build_dense_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_pa.p, ctx->d_pb.p, d_nl.p, ctx->E, ctx->N, ctx->d_M.p);
+    ctx->launches++;
+    AHX_CUDA(ctx, cudaGetLastError());
+    AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    d_nl.release();
+  }
+  ctx->dense_ready = true;
+  return AHX_OK;
+}
+
+int launch_eval_m_dense(ahx_ctx *ctx, const int32_t *d_tours, int32_t P, int32_t L, double *d_out, cudaStream_t s) {
+  if (P == 0) return AHX_OK;
+  int rc = ensure_dense(ctx);
+  if (rc != AHX_OK) return rc;
+  const size_t smem = (sizeof(double) + sizeof(int)) * static_cast<size_t>(L);
+  if (smem + 1024 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_eval_m_dense: tour too long for the dense kernel's shared memory");
+  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_m_dense_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  eval_m_dense_kernel<int32_t><<<P, kBlock, smem, s>>>(d_tours, P, L, ctx->N, ctx->d_sizes.p, ctx->d_M.p, d_out, ctx->d_errflag.p);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  return AHX_OK;
+}
+
+int launch_eval_q(ahx_ctx *ctx, const int32_t *d_tours, int shared_tour, const uint8_t *d_signs, int32_t P, int32_t L,
+                  double *d_out, cudaStream_t s) {
+  if (P == 0) return AHX_OK;
+  const size_t smem = sizeof(long long) * static_cast<size_t>(L) + sizeof(int) * (static_cast<size_t>(ctx->N) + L) + ctx->N;
+  if (smem + 1024 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_eval_q: group too large for shared memory");
+  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  eval_q_kernel<<<P, kBlock, smem, s>>>(d_tours, shared_tour, P, L, ctx->N, ctx->d_sizes.p, d_signs, ctx->d_pa.p, ctx->d_pb.p,
+                                        ctx->d_slots.p, ctx->d_hist.p, static_cast<int>(ctx->E), d_out);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  return AHX_OK;
+}
+
+// Waits for the context stream and turns the device-side range-check flag into an error.
+int finish_checked(ahx_ctx *ctx, const char *who) {
+  int flag = 0;
+  AHX_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_errflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_errflag.p, 0, sizeof(int), ctx->stream));
+    return fail(ctx, AHX_ERR_ARG, std::string(who) + ": contig index out of range in a tour");
+  }
+  return AHX_OK;
+}
+
+// Tour.Tigs must hold distinct contig indices (they come from tigToIdx).
+int validate_tour(ahx_ctx *ctx, int32_t L, const int32_t *tour, const char *who) {
+  if (L < 0 || L > ctx->N || (L > 0 && !tour)) return fail(ctx, AHX_ERR_ARG, std::string(who) + ": bad tour length");
+  std::vector<uint8_t> seen(ctx->N, 0);
+  for (int32_t i = 0; i < L; ++i) {
+    const int32_t c = tour[i];
+    if (c < 0 || c >= ctx->N || seen[c]) return fail(ctx, AHX_ERR_ARG, std::string(who) + ": tour is not a set of distinct contig indices");
+    seen[c] = 1;
+  }
+  return AHX_OK;
+}
+
+template <typename IdxT>
+static int validate_tours(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours, const char *who) {
+  if (P < 0 || L < 0 || L > ctx->N || (static_cast<int64_t>(P) * L > 0 && !tours)) return fail(ctx, AHX_ERR_ARG, std::string(who) + ": bad population shape");
+  // Contig indices are range-checked on the device (errflag); a duplicated index
+  // inside a tour is the caller's bug, as it is in the reference.
+  return AHX_OK;
+}
+
+}  // namespace ahx
+
+using namespace ahx;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+// ---- batched Tour.Evaluate through host buffers --------------------------------
+// Chunks the population so the H2D copy of chunk k+1 overlaps the kernel of chunk k.
+template <typename IdxT>
+static int eval_m_host(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours, double *out, int kind, const char *who) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if ((rc = validate_tours(ctx, P, L, tours, who)) != AHX_OK) return rc;
+  if (P > 0 && !out) return fail(ctx, AHX_ERR_ARG, std::string(who) + ": null out");
+  if (P == 0) return AHX_OK;
+  constexpr bool k16 = sizeof(IdxT) == 2;
+  if (k16 && ctx->N > 65535) return fail(ctx, AHX_ERR_ARG, "ahx_eval_m_u16: n_tigs exceeds 65535");
+  const size_t total = static_cast<size_t>(P) * L;
+  IdxT *dt;
+  if constexpr (k16) { AHX_CUDA(ctx, ctx->d_tours16.reserve(total)); dt = ctx->d_tours16.p; }
+  else { AHX_CUDA(ctx, ctx->d_tours.reserve(total)); dt = ctx->d_tours.p; }
+  ctx->pop_P = ctx->pop_L = 0;  // the staging buffer doubles as the resident population
+  AHX_CUDA(ctx, ctx->d_scores.reserve(P));
+  // ~4 MB per chunk, at most 16 chunks, chunk sizes multiple of 4 tours
+  int nchunk = static_cast<int>(std::min<size_t>(16, std::max<size_t>(1, total * sizeof(IdxT) / (4u << 20))));
+  int32_t per = ((P + nchunk - 1) / nchunk + 3) & ~3;
+  nchunk = (P + per - 1) / per;
+  while (static_cast<int>(ctx->chunk_ev.size()) < nchunk) {
+    cudaEvent_t ev;
+    AHX_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ctx->chunk_ev.push_back(ev);
+  }
+  // the copy stream must not overwrite a buffer an earlier call is still using
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_a, 0));
+  for (int c = 0; c < nchunk; ++c) {
+    const int32_t p0 = c * per, pc = std::min(per, P - p0);
+    AHX_CUDA(ctx, cudaMemcpyAsync(dt + static_cast<size_t>(p0) * L, tours + static_cast<size_t>(p0) * L,
+                                  sizeof(IdxT) * static_cast<size_t>(pc) * L, cudaMemcpyHostToDevice, ctx->copy_stream));
+    AHX_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+    AHX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+    if (kind == 0) {
+      if constexpr (k16) rc = launch_eval_m_sparse(ctx, nullptr, dt + static_cast<size_t>(p0) * L, nullptr, pc, L, ctx->d_scores.p + p0, ctx->stream);
+      else rc = launch_eval_m_sparse(ctx, dt + static_cast<size_t>(p0) * L, nullptr, nullptr, pc, L, ctx->d_scores.p + p0, ctx->stream);
+    } else {
+      if constexpr (k16) return fail(ctx, AHX_ERR_ARG, "dense kernel takes int32 tours");
+      else rc = launch_eval_m_dense(ctx, dt + static_cast<size_t>(p0) * L, pc, L, ctx->d_scores.p + p0, ctx->stream);
+    }
+    if (rc != AHX_OK) return rc;
+  }
+  AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  return finish_checked(ctx, who);
+}
+
+
+extern "C" {
+
+int ahx_version(void) { return AHX_VERSION; }
+const char *ahx_last_error(const ahx_ctx *ctx) { return ctx ? ctx->err.c_str() : global_error(); }
+
+int ahx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ahx_create(int device, ahx_ctx **out) {
+  if (!out) return fail(nullptr, AHX_ERR_ARG, "ahx_create: null out");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, AHX_ERR_NODEVICE, "ahx_create: no CUDA device available; libahx has no CPU path");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, AHX_ERR_ARG, "ahx_create: device index out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major < 10) return fail(nullptr, AHX_ERR_NODEVICE, "ahx_create: libahx is built for sm_100a (Blackwell B200) only");
+  auto *ctx = new ahx_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  ctx->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "ahx_create");
+    delete ctx;
+    return rc;
+  }
+  if ((e = ctx->d_errflag.reserve(1)) != cudaSuccess || (e = cudaMemset(ctx->d_errflag.p, 0, sizeof(int))) != cudaSuccess) {
+    int rc = cuda_fail(nullptr, e, "ahx_create");
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return AHX_OK;
+}
+
+void ahx_destroy(ahx_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->d_sizes.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_pa.release(); ctx->d_pb.release();
+  ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
+  ctx->d_tours.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
+  ctx->d_flush.release(); ctx->d_errflag.release();
+  for (int i = 0; i < 2; ++i) { ctx->d_pop[i].release(); ctx->d_fit[i].release(); }
+  ctx->d_hof.release(); ctx->d_sel_idx.release(); ctx->d_sel_tours.release(); ctx->d_sel_fit.release(); ctx->d_taken.release();
+  ctx->d_state.release(); ctx->d_pos.release(); ctx->d_cum.release(); ctx->d_S4.release(); ctx->d_trace.release();
+  ctx->d_pairinfo.release(); ctx->d_stepacc.release(); ctx->d_counts.release();
+  for (auto ev : ctx->chunk_ev) cudaEventDestroy(ev);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+int ahx_host_alloc(void **ptr, uint64_t bytes) {
+  if (!ptr) return fail(nullptr, AHX_ERR_ARG, "ahx_host_alloc: null");
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+  return AHX_OK;
+}
+int ahx_host_free(void *ptr) {
+  if (ptr && cudaFreeHost(ptr) != cudaSuccess) return fail(nullptr, AHX_ERR_CUDA, "cudaFreeHost failed");
+  return AHX_OK;
+}
+
+int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int32_t *pa, const int32_t *pb,
+             const int32_t *nl, const int8_t *strand, const int32_t *slots, int64_t H, const int32_t *hist) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  if (ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_load: a GA run is active (call ahx_ga_end first)");
+  if (N <= 0 || !sizes || E < 0 || H < 0 || E > INT32_MAX / 8 || (E > 0 && (!pa || !pb || !nl || !slots)) || (H > 0 && !hist))
+    return fail(ctx, AHX_ERR_ARG, "ahx_load: bad argument");
+  for (int32_t i = 0; i < N; ++i)
+    if (sizes[i] < 1) return fail(ctx, AHX_ERR_ARG, "ahx_load: contig sizes must be >= 1 (a zero-length contig makes the reference divide by zero)");
+  for (int64_t e = 0; e < E; ++e) {
+    if (pa[e] < 0 || pa[e] >= pb[e] || pb[e] >= N) return fail(ctx, AHX_ERR_ARG, "ahx_load: pairs must satisfy 0 <= a < b < n_tigs");
+    if (e > 0 && (pa[e] < pa[e - 1] || (pa[e] == pa[e - 1] && pb[e] <= pb[e - 1])))
+      return fail(ctx, AHX_ERR_ARG, "ahx_load: pairs must be unique and sorted by (a, b)");
+    if (nl[e] < 0) return fail(ctx, AHX_ERR_ARG, "ahx_load: negative nlinks");
+    for (int k = 0; k < 8; ++k)
+      if (slots[e * 8 + k] < -1 || slots[e * 8 + k] >= H) return fail(ctx, AHX_ERR_ARG, "ahx_load: slot index out of range");
+  }
+  ctx->loaded = false; ctx->dense_ready = false;
+  ctx->N = N; ctx->E = E; ctx->H = H;
+  ctx->h_sizes.assign(sizes, sizes + N);
+  ctx->h_pa.assign(pa, pa + E); ctx->h_pb.assign(pb, pb + E); ctx->h_nl.assign(nl, nl + E);
+  if (strand) ctx->h_strand.assign(strand, strand + E); else ctx->h_strand.assign(E, 1);
+  ctx->coo16 = N <= 65535;
+  AHX_CUDA(ctx, ctx->d_sizes.reserve(N));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes.p, sizes, sizeof(int64_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, ctx->d_pa.reserve(E)); AHX_CUDA(ctx, ctx->d_pb.reserve(E));
+  AHX_CUDA(ctx, ctx->d_slots.reserve(E * 8)); AHX_CUDA(ctx, ctx->d_hist.reserve(H * 12));
+  std::vector<uint2> c16; std::vector<int4> c32;
+  if (ctx->coo16) {
+    c16.resize(E);
+    for (int64_t e = 0; e < E; ++e) c16[e] = make_uint2(static_cast<uint32_t>(pa[e]) | (static_cast<uint32_t>(pb[e]) << 16), static_cast<uint32_t>(nl[e]));
+    AHX_CUDA(ctx, ctx->d_coo16.reserve(E));
+    if (E) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo16.p, c16.data(), sizeof(uint2) * E, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    c32.resize(E);
+    for (int64_t e = 0; e < E; ++e) c32[e] = make_int4(pa[e], pb[e], nl[e], 0);
+    AHX_CUDA(ctx, ctx->d_coo32.reserve(E));
+    if (E) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo32.p, c32.data(), sizeof(int4) * E, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // CSR of pairs touching each contig (for flipOne's O(deg) deltas)
+  std::vector<int32_t> ptr(N + 1, 0), adj(2 * E);
+  for (int64_t e = 0; e < E; ++e) { ptr[pa[e] + 1]++; ptr[pb[e] + 1]++; }
+  for (int32_t i = 0; i < N; ++i) ptr[i + 1] += ptr[i];
+  {
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < E; ++e) { adj[fill[pa[e]]++] = static_cast<int32_t>(e); adj[fill[pb[e]]++] = static_cast<int32_t>(e); }
+  }
+  AHX_CUDA(ctx, ctx->d_adj_ptr.reserve(N + 1)); AHX_CUDA(ctx, ctx->d_adj_e.reserve(2 * E));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_adj_ptr.p, ptr.data(), sizeof(int32_t) * (N + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (E) {
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_adj_e.p, adj.data(), sizeof(int32_t) * 2 * E, cudaMemcpyHostToDevice, ctx->stream));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pa.p, pa, 4 * E, cudaMemcpyHostToDevice, ctx->stream));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pb.p, pb, 4 * E, cudaMemcpyHostToDevice, ctx->stream));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots.p, slots, 4 * 8 * E, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (H) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_hist.p, hist, 4 * 12 * H, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->loaded = true;
+  ctx->pop_P = ctx->pop_L = 0;
+  return AHX_OK;
+}
+
+int ahx_load_clm(ahx_ctx *ctx, const ahx_clm *clm) {
+  if (!ctx || !clm) return fail(ctx, AHX_ERR_ARG, "ahx_load_clm: null argument");
+  const ClmView v = view_of(clm);
+  if (!v.finalized) return fail(ctx, AHX_ERR_STATE, "ahx_load_clm: call ahx_clm_finalize first");
+  return ahx_load(ctx, v.n, v.sizes, v.E, v.pa, v.pb, v.nl, v.strand, v.slots, v.H, v.hist);
+}
+
+int ahx_eval_m(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours, double *out) { return eval_m_host<int32_t>(ctx, P, L, tours, out, 0, "ahx_eval_m"); }
+int ahx_eval_m_u16(ahx_ctx *ctx, int32_t P, int32_t L, const uint16_t *tours, double *out) { return eval_m_host<uint16_t>(ctx, P, L, tours, out, 0, "ahx_eval_m_u16"); }
+int ahx_eval_m_dense(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours, double *out) { return eval_m_host<int32_t>(ctx, P, L, tours, out, 1, "ahx_eval_m_dense"); }
+
+int ahx_eval_q(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours, int32_t shared_tour, const uint8_t *signs, double *out) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  const int32_t PT = shared_tour ? (P > 0 ? 1 : 0) : P;
+  if ((rc = validate_tours(ctx, PT, L, tours, "ahx_eval_q")) != AHX_OK) return rc;
+  if (P > 0 && (!signs || !out)) return fail(ctx, AHX_ERR_ARG, "ahx_eval_q: null signs/out");
+  if (P == 0) return AHX_OK;
+  // pos[] is an inverse permutation: a duplicated contig would silently drop terms
+  for (int32_t p = 0; p < PT; ++p)
+    if ((rc = validate_tour(ctx, L, tours + static_cast<size_t>(p) * L, "ahx_eval_q")) != AHX_OK) return rc;
+  AHX_CUDA(ctx, ctx->d_tours.reserve(static_cast<size_t>(PT) * L));
+  ctx->pop_P = ctx->pop_L = 0;
+  AHX_CUDA(ctx, ctx->d_signs.reserve(static_cast<size_t>(P) * ctx->N));
+  AHX_CUDA(ctx, ctx->d_scores.reserve(P));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(PT) * L, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_signs.p, signs, static_cast<size_t>(P) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_eval_q(ctx, ctx->d_tours.p, shared_tour, ctx->d_signs.p, P, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+  AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+// ---- resident population ----------------------------------------------------------
+int ahx_pop_set(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if ((rc = validate_tours(ctx, P, L, tours, "ahx_pop_set")) != AHX_OK) return rc;
+  AHX_CUDA(ctx, ctx->d_tours.reserve(static_cast<size_t>(P) * L));
+  AHX_CUDA(ctx, ctx->d_scores.reserve(P));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(P) * L, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->pop_P = P; ctx->pop_L = L;
+  return AHX_OK;
+}
+
+int ahx_pop_eval_m(ahx_ctx *ctx, int32_t kind, int32_t repeat, float *elapsed_ms) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (ctx->pop_P <= 0) return fail(ctx, AHX_ERR_STATE, "ahx_pop_eval_m: no resident population (call ahx_pop_set)");
+  if (repeat < 1 || (kind != 0 && kind != 1)) return fail(ctx, AHX_ERR_ARG, "ahx_pop_eval_m: bad argument");
+  if (kind == 1 && (rc = ensure_dense(ctx)) != AHX_OK) return rc;
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  for (int r = 0; r < repeat; ++r) {
+    rc = kind == 0 ? launch_eval_m_sparse(ctx, ctx->d_tours.p, nullptr, nullptr, ctx->pop_P, ctx->pop_L, ctx->d_scores.p, ctx->stream)
+                   : launch_eval_m_dense(ctx, ctx->d_tours.p, ctx->pop_P, ctx->pop_L, ctx->d_scores.p, ctx->stream);
+    if (rc != AHX_OK) return rc;
+  }
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  AHX_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+  float ms = 0.f;
+  AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return finish_checked(ctx, "ahx_pop_eval_m");
+}
+
+int ahx_pop_scores(ahx_ctx *ctx, double *out) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (ctx->pop_P <= 0 || !out) return fail(ctx, AHX_ERR_STATE, "ahx_pop_scores: no resident population");
+  AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * ctx->pop_P, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+int ahx_flush_l2(ahx_ctx *ctx) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  const size_t bytes = std::max<size_t>(ctx->l2_bytes * 2, 256u << 20);
+  AHX_CUDA(ctx, ctx->d_flush.reserve(bytes));
+  fill_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<int4 *>(ctx->d_flush.p), bytes / 16, 1);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+// ---- probes -------------------------------------------------------------------------
+int ahx_probe_fp64(ahx_ctx *ctx, double *dfma_tflops, double *ddiv_gops) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  const int grid = ctx->sm_count * 8, block = 256, iters = 1 << 14;
+  DevBuf<double> buf;
+  AHX_CUDA(ctx, buf.reserve(static_cast<size_t>(grid) * block));
+  float ms = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0 warms up
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    probe_dfma_kernel<<<grid, block, 0, ctx->stream>>>(buf.p, iters);
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    AHX_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+    AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  }
+  if (dfma_tflops) *dfma_tflops = 2.0 * 8.0 * iters * static_cast<double>(grid) * block / (ms * 1e-3) / 1e12;
+  const int diters = 1 << 11;
+  for (int pass = 0; pass < 2; ++pass) {
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    probe_ddiv_kernel<<<grid, block, 0, ctx->stream>>>(buf.p, diters);
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    AHX_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+    AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  }
+  if (ddiv_gops) *ddiv_gops = 4.0 * diters * static_cast<double>(grid) * block / (ms * 1e-3) / 1e9;
+  ctx->launches += 4;
+  buf.release();
+  return AHX_OK;
+}
+
+int ahx_probe_l2(ahx_ctx *ctx, uint64_t bytes, double *gbs) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  if (bytes < 4096) return fail(ctx, AHX_ERR_ARG, "ahx_probe_l2: buffer too small");
+  DevBuf<char> buf;
+  AHX_CUDA(ctx, buf.reserve(bytes + 16));
+  const size_t n = bytes / 16;
+  fill_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(reinterpret_cast<int4 *>(buf.p), n, 3);
+  const int reps = static_cast<int>(std::max<uint64_t>(4, (8ull << 30) / bytes));
+  float ms = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    probe_read_kernel<<<ctx->sm_count * 8, 512, 0, ctx->stream>>>(reinterpret_cast<const int4 *>(buf.p), n, reps, reinterpret_cast<int4 *>(buf.p) + n);
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    AHX_CUDA(ctx, cudaEventSynchronize(ctx->ev_b));
+    AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  }
+  if (gbs) *gbs = static_cast<double>(n) * 16.0 * reps / (ms * 1e-3) / 1e9;
+  ctx->launches += 3;
+  buf.release();
+  return AHX_OK;
+}
+
+int64_t ahx_launch_count(const ahx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int ahx_sm_count(const ahx_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"

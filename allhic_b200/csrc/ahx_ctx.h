@@ -1,0 +1,124 @@
+// ahx_ctx.h -- the context object behind the opaque ahx_ctx handle.
+#ifndef AHX_CTX_H_
+#define AHX_CTX_H_
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ahx_internal.h"
+
+namespace ahx {
+
+// A device allocation that only ever grows.
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Device-resident GA bookkeeping (one per context), evaluate.go:281-306.
+struct GaState {
+  long long gen;        // ga.Generations
+  long long updated;    // *updated
+  long long evals;      // Tour.Evaluate calls on the device
+  double hof_fit;       // HallOfFame[0].Fitness (minimised)
+  int stop;             // EarlyStop fired or max_gens reached
+  unsigned int ticket;  // "last CTA done" counter
+  int best_idx;         // argmin of the newest generation
+  int pad;
+};
+
+}  // namespace ahx
+
+struct ahx_ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  std::string err;
+  int sm_count = 0;
+  size_t smem_optin = 0, l2_bytes = 0;
+  int64_t launches = 0;
+
+  // ---- loaded linkage group
+  bool loaded = false;
+  int32_t N = 0;
+  int64_t E = 0, H = 0;
+  bool coo16 = false;
+  ahx::DevBuf<long long> d_sizes;
+  ahx::DevBuf<uint2> d_coo16;
+  ahx::DevBuf<int4> d_coo32;
+  ahx::DevBuf<int32_t> d_pa, d_pb, d_slots, d_hist, d_M;
+  bool dense_ready = false;
+  ahx::DevBuf<int32_t> d_adj_ptr, d_adj_e;   // CSR: pairs touching each contig
+  std::vector<int64_t> h_sizes;
+  std::vector<int32_t> h_pa, h_pb, h_nl;
+  std::vector<int8_t> h_strand;
+
+  // ---- scratch
+  ahx::DevBuf<int32_t> d_tours;      // staging for ahx_eval_* / resident population
+  ahx::DevBuf<uint16_t> d_tours16;
+  ahx::DevBuf<double> d_scores;
+  ahx::DevBuf<uint8_t> d_signs;
+  ahx::DevBuf<double> d_xglobal;     // contig-space mid-points when N does not fit shared memory
+  ahx::DevBuf<char> d_flush;
+  ahx::DevBuf<int> d_errflag;        // set by kernels that meet an out-of-range contig index
+  int32_t pop_P = 0, pop_L = 0;
+
+  // ---- GA
+  bool ga_active = false;
+  ahx_ga_params ga_prm{};
+  int32_t ga_L = 0;
+  ahx::DevBuf<int32_t> d_pop[2];
+  ahx::DevBuf<double> d_fit[2];
+  ahx::DevBuf<int32_t> d_hof, d_sel_idx, d_sel_tours;
+  ahx::DevBuf<double> d_sel_fit;
+  ahx::DevBuf<uint8_t> d_taken;
+  ahx::DevBuf<ahx::GaState> d_state;
+  std::vector<int32_t> ga_active_set;  // sorted contig ids of the initial tour
+  double ga_ms = 0.0;
+
+  // ---- orientation scratch
+  ahx::DevBuf<int32_t> d_pos;
+  ahx::DevBuf<long long> d_cum;
+  ahx::DevBuf<double> d_S4, d_trace;
+  ahx::DevBuf<uint8_t> d_pairinfo, d_stepacc;
+  ahx::DevBuf<long long> d_counts;
+};
+
+namespace ahx {
+int fail(ahx_ctx *ctx, int code, const std::string &msg);
+int cuda_fail(ahx_ctx *ctx, cudaError_t e, const char *what);
+// Selects the device; returns AHX_OK or an error code.
+int enter(ahx_ctx *ctx, bool need_loaded);
+// Launches the contig-space EvaluateM kernel over P tours already on the device.
+// rows (optional): evaluate tours[rows[p]] and write out[rows[p]].
+int launch_eval_m_sparse(ahx_ctx *ctx, const int32_t *d_tours, const uint16_t *d_tours16, const int32_t *d_rows,
+                         int32_t P, int32_t L, double *d_out, cudaStream_t s);
+int launch_eval_m_dense(ahx_ctx *ctx, const int32_t *d_tours, int32_t P, int32_t L, double *d_out, cudaStream_t s);
+int launch_eval_q(ahx_ctx *ctx, const int32_t *d_tours, int shared_tour, const uint8_t *d_signs, int32_t P, int32_t L,
+                  double *d_out, cudaStream_t s);
+int finish_checked(ahx_ctx *ctx, const char *who);
+int validate_tour(ahx_ctx *ctx, int32_t L, const int32_t *tour, const char *who);
+size_t eval_m_smem_bytes(int T, int32_t N, int32_t L);
+}  // namespace ahx
+
+#define AHX_CUDA(ctx, call)                                              \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) return ahx::cuda_fail((ctx), e_, #call);      \
+  } while (0)
+
+#endif  // AHX_CTX_H_

@@ -1,0 +1,527 @@
+// ahx_ga.cu -- CLM.GARun (evaluate.go:258-315) as one kernel launch per generation.
+//
+// eaopt v0.4.2 semantics restated: ModGenerational with
+// SelTournament{NContestants:k} (offspring generated two at a time from two
+// distinct tournament winners, winners cloned with their fitness), CrossRate 0
+// (Tour.Crossover is empty, evaluate.go:235), per-offspring mutation with
+// probability MutRate by exactly one of the four operators of Tour.Mutate
+// (evaluate.go:221-232), only mutated offspring re-scored, HallOfFame of size
+// 1, EarlyStop when Generations - updated > NGen (evaluate.go:304-306).
+//
+// ga_generation_kernel: CTA o builds offspring o.  All random draws come from
+// Philox4x32-10 keyed by (seed, island) with counter (generation, index,
+// stream), so every CTA recomputes the decisions it needs and the population
+// never leaves HBM:
+//   1. tournament for offspring pair o/2 -> parent index
+//   2. clone + mutate in one pass: new[i] = parent[mut_source(i)] (the four
+//      operators are index remaps), written to the other population buffer
+//   3. if mutated: Tour.Evaluate in contig space (same code as eval_m_sparse),
+//      else inherit the parent's fitness (eaopt keeps Evaluated=true on clones)
+//   4. the last CTA to finish (atomic ticket) takes the arg-min of the new
+//      generation, updates the hall of fame / generation counters / stop flag.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#include "ahx_ctx.h"
+#include "ahx_device.cuh"
+
+namespace ahx {
+
+constexpr int kMaxContestants = 8;
+constexpr uint32_t kStreamSelect = 0x100, kStreamMutate = 0x200;
+
+struct GaDev {
+  int P, L, N, E, k;
+  double mut_prob;
+  uint32_t key0, key1;
+  long long ngen, max_gens;
+  const long long *sizes;
+  const void *coo;
+  int *pop[2];
+  double *fit[2];
+  int *hof;
+  GaState *st;
+};
+
+struct MutPlan { int mutated, op, p, q, dir; };
+
+// Draws of eaopt's `rng.Float64() < MutRate` and Tour.Mutate (evaluate.go:221-232)
+__host__ __device__ inline MutPlan plan_mutation(const Philox &ph, uint32_t glo, uint32_t ghi, uint32_t o, double mut_prob, int L) {
+  uint32_t r[4], s[4];
+  ph(glo, ghi, o, kStreamMutate, r);
+  MutPlan m{0, -1, 0, 0, 0};
+  if (!(rand_unit(r[0], r[1]) < mut_prob)) return m;
+  m.mutated = 1;
+  const double rd = rand_unit(r[2], r[3]);
+  ph(glo, ghi, o, kStreamMutate + 1, s);
+  if (rd >= 0.2 && rd < 0.4) {                 // MutSplice: k = Intn(L-1) + 1
+    m.op = 1; m.p = rand_below(s[0], L - 1) + 1; m.q = 0;
+    return m;
+  }
+  int p = rand_below(s[0], L), q = rand_below(s[1], L);   // randomTwoInts, evaluate.go:146-154
+  if (p > q) { const int t = p; p = q; q = t; }
+  m.p = p; m.q = q;
+  if (rd < 0.2) m.op = 0;                      // MutPermute
+  else if (rd < 0.7) { m.op = 2; m.dir = rand_unit(s[2], s[3]) < 0.5; }  // MutInsertion
+  else m.op = 3;                               // MutInversion
+  return m;
+}
+
+// SelTournament{k}.Apply(2, ...): two distinct winners; `which` picks one.
+__device__ inline int tournament_pair(const double *__restrict__ fit, int P, int k, const Philox &ph, uint32_t glo,
+                                      uint32_t ghi, uint32_t pair, int which) {
+  uint32_t r[2 * kMaxContestants];
+#pragma unroll
+  for (int c = 0; c < (2 * kMaxContestants) / 4; ++c) {
+    if (4 * c >= 2 * k) break;
+    uint32_t o4[4];
+    ph(glo, ghi, pair, kStreamSelect + c, o4);
+    r[4 * c] = o4[0]; r[4 * c + 1] = o4[1]; r[4 * c + 2] = o4[2]; r[4 * c + 3] = o4[3];
+  }
+  int banned = -1, winner = -1;
+  for (int round = 0; round <= which; ++round) {
+    const int pool = P - (banned >= 0 ? 1 : 0);
+    int chosen[kMaxContestants];
+    int best = -1; double bestfit = 0.0;
+    for (int i = 0; i < k; ++i) {
+      int v = rand_below(r[round * k + i], pool - i);   // v-th not yet sampled index
+      int pos = 0;
+      while (pos < i && chosen[pos] <= v) { ++v; ++pos; }
+      for (int m = i; m > pos; --m) chosen[m] = chosen[m - 1];
+      chosen[pos] = v;
+      const int id = (banned >= 0 && v >= banned) ? v + 1 : v;
+      const double f = fit[id];
+      if (best < 0 || f < bestfit) { best = id; bestfit = f; }
+    }
+    winner = best; banned = best;
+  }
+  return winner;
+}
+
+template <typename Coo>
+__global__ void __launch_bounds__(kBlock) ga_generation_kernel(GaDev g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ long long scan_scratch[kWarps];
+  __shared__ double red_scratch[kWarps];
+  __shared__ int red_idx[kWarps];
+  __shared__ int s_flag;
+  __shared__ int s_best;
+  __shared__ double s_bestfit;
+  double *x = reinterpret_cast<double *>(smem_raw);
+  int *tig = reinterpret_cast<int *>(smem_raw + sizeof(double) * static_cast<size_t>(g.N));
+  const int tid = threadIdx.x, o = blockIdx.x;
+  GaState *st = g.st;
+  if (*reinterpret_cast<volatile int *>(&st->stop)) return;
+  const long long gen = *reinterpret_cast<volatile long long *>(&st->gen);
+  const int cur = static_cast<int>(gen & 1);
+  const int *popc = g.pop[cur]; int *popn = g.pop[cur ^ 1];
+  const double *fitc = g.fit[cur]; double *fitn = g.fit[cur ^ 1];
+  const Philox ph{g.key0, g.key1};
+  const uint32_t glo = static_cast<uint32_t>(gen), ghi = static_cast<uint32_t>(gen >> 32);
+
+  const int parent = tournament_pair(fitc, g.P, g.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
+  const MutPlan mp = plan_mutation(ph, glo, ghi, static_cast<uint32_t>(o), g.mut_prob, g.L);
+
+  const int *src = popc + static_cast<size_t>(parent) * g.L;
+  int *dst = popn + static_cast<size_t>(o) * g.L;
+  for (int i = tid; i < g.L; i += kBlock) {
+    const int v = src[mut_source(mp.op, mp.p, mp.q, mp.dir, g.L, i)];
+    tig[i] = v;
+    dst[i] = v;
+  }
+  if (!mp.mutated) {
+    if (tid == 0) fitn[o] = fitc[parent];
+  } else {
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = tid; i < g.N; i += kBlock) x[i] = qnan;
+    __syncthreads();
+    scatter_mids<1>(tig, g.L, g.sizes, x, 0, scan_scratch, tid);
+    __syncthreads();
+    double acc[1] = {0.0};
+    accumulate_pairs<1, Coo>(x, reinterpret_cast<const typename Coo::Elem *>(g.coo), g.E, acc, tid);
+    const double s = block_sum(acc[0], red_scratch, tid);
+    if (tid == 0) {
+      fitn[o] = 0.0 - s;
+      atomicAdd(reinterpret_cast<unsigned long long *>(&st->evals), 1ULL);
+    }
+  }
+  // ---- last CTA done: hall of fame + bookkeeping (evaluate.go:287-306)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  double bf = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+  int bi = 0x7fffffff;
+  for (int i = tid; i < g.P; i += kBlock) {
+    const double f = __ldcg(fitn + i);
+    if (f < bf) { bf = f; bi = i; }   // ascending i per thread => lowest index on ties
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double of = __shfl_down_sync(0xffffffffu, bf, d);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+    if (of < bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+  }
+  if ((tid & 31) == 0) { red_scratch[tid >> 5] = bf; red_idx[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kWarps; ++w)
+      if (red_scratch[w] < bf || (red_scratch[w] == bf && red_idx[w] < bi)) { bf = red_scratch[w]; bi = red_idx[w]; }
+    s_best = bi; s_bestfit = bf;
+    s_flag = bf < st->hof_fit;        // updateHallOfFame keeps the best ever
+  }
+  __syncthreads();
+  if (s_flag) {
+    const int *best_row = popn + static_cast<size_t>(s_best) * g.L;
+    for (int i = tid; i < g.L; i += kBlock) g.hof[i] = __ldcg(best_row + i);
+  }
+  if (tid == 0) {
+    const long long ngen_now = gen + 1;
+    if (s_flag) { st->hof_fit = s_bestfit; st->updated = ngen_now; }   // currentBest > *best
+    st->best_idx = s_best;
+    st->ticket = 0;
+    if (ngen_now - st->updated > g.ngen || ngen_now >= g.max_gens) st->stop = 1;
+    __threadfence();
+    st->gen = ngen_now;
+  }
+}
+
+__global__ void ga_init_kernel(GaDev g, const int *__restrict__ init, const double *__restrict__ f0) {
+  const size_t total = static_cast<size_t>(g.P) * g.L;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    g.pop[0][i] = init[i % g.L];   // MakeTour = r.Tour.Clone(): PopSize copies of one tour (evaluate.go:259-262)
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < static_cast<size_t>(g.P); i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    g.fit[0][i] = f0[0];
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < g.L; i += blockDim.x) g.hof[i] = init[i];
+    if (threadIdx.x == 0) {
+      GaState s{};
+      s.gen = 0; s.updated = 0; s.evals = 1; s.hof_fit = f0[0];
+      s.stop = (g.max_gens <= 0 || 0 - s.updated > g.ngen) ? 1 : 0;
+      s.ticket = 0; s.best_idx = 0;
+      *g.st = s;
+    }
+  }
+}
+
+// n rounds of arg-min (want_max = 0) or arg-max over fit[0..P) without replacement.
+__global__ void __launch_bounds__(1024) select_extreme_kernel(const double *__restrict__ fit, int P, int n, int want_max,
+                                                              unsigned char *taken, int *out_idx, double *out_fit) {
+  __shared__ double sf[32];
+  __shared__ int si[32];
+  const int tid = threadIdx.x;
+  for (int r = 0; r < n; ++r) {
+    double bf = 0.0; int bi = 0x7fffffff;
+    for (int i = tid; i < P; i += blockDim.x) {
+      if (taken[i]) continue;
+      const double f = want_max ? -fit[i] : fit[i];
+      if (bi == 0x7fffffff || f < bf) { bf = f; bi = i; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double of = __shfl_down_sync(0xffffffffu, bf, d);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || of < bf || (of == bf && oi < bi))) { bf = of; bi = oi; }
+    }
+    if ((tid & 31) == 0) { sf[tid >> 5] = bf; si[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+        if (si[w] != 0x7fffffff && (bi == 0x7fffffff || sf[w] < bf || (sf[w] == bf && si[w] < bi))) { bf = sf[w]; bi = si[w]; }
+      out_idx[r] = bi;
+      out_fit[r] = want_max ? -bf : bf;
+      taken[bi] = 1;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void gather_rows_kernel(const int *__restrict__ pop, const int *__restrict__ idx, int L, int *__restrict__ out) {
+  const int *src = pop + static_cast<size_t>(idx[blockIdx.x]) * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) out[static_cast<size_t>(blockIdx.x) * L + i] = src[i];
+}
+__global__ void scatter_rows_kernel(int *__restrict__ pop, const int *__restrict__ idx, int L, const int *__restrict__ in) {
+  int *dst = pop + static_cast<size_t>(idx[blockIdx.x]) * L;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) dst[i] = in[static_cast<size_t>(blockIdx.x) * L + i];
+}
+// After migrants were written and scored: refresh the hall of fame from fit[0..P).
+__global__ void __launch_bounds__(1024) hof_refresh_kernel(const double *__restrict__ fit, const int *__restrict__ pop, int P, int L,
+                                                           int *hof, GaState *st, int n_new_evals) {
+  __shared__ double sf[32];
+  __shared__ int si[32];
+  __shared__ int s_best, s_improved;
+  const int tid = threadIdx.x;
+  double bf = __longlong_as_double(0x7ff0000000000000LL); int bi = 0x7fffffff;
+  for (int i = tid; i < P; i += blockDim.x) { const double f = fit[i]; if (f < bf) { bf = f; bi = i; } }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double of = __shfl_down_sync(0xffffffffu, bf, d);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+    if (of < bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+  }
+  if ((tid & 31) == 0) { sf[tid >> 5] = bf; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+      if (sf[w] < bf || (sf[w] == bf && si[w] < bi)) { bf = sf[w]; bi = si[w]; }
+    s_best = bi; s_improved = bf < st->hof_fit;
+    st->evals += n_new_evals;
+    if (s_improved) { st->hof_fit = bf; st->updated = st->gen; st->stop = 0; }
+  }
+  __syncthreads();
+  if (s_improved)
+    for (int i = tid; i < L; i += blockDim.x) hof[i] = pop[static_cast<size_t>(s_best) * L + i];
+}
+
+__global__ void mutate_kernel(const int *__restrict__ in, int L, int op, int p, int q, int dir, int *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) out[i] = in[mut_source(op, p, q, dir, L, i)];
+}
+
+static GaDev make_dev(ahx_ctx *ctx) {
+  GaDev g{};
+  const ahx_ga_params &p = ctx->ga_prm;
+  g.P = p.npop; g.L = ctx->ga_L; g.N = ctx->N; g.E = static_cast<int>(ctx->E); g.k = p.tournament_k;
+  g.mut_prob = p.mut_prob;
+  // SplitMix-style whitening of (seed, island) into the Philox key
+  uint64_t z = p.seed + 0x9e3779b97f4a7c15ULL * (static_cast<uint64_t>(static_cast<uint32_t>(p.island)) + 1);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
+  g.key0 = static_cast<uint32_t>(z); g.key1 = static_cast<uint32_t>(z >> 32);
+  g.ngen = p.ngen; g.max_gens = p.max_gens;
+  g.sizes = ctx->d_sizes.p;
+  g.coo = ctx->coo16 ? static_cast<const void *>(ctx->d_coo16.p) : static_cast<const void *>(ctx->d_coo32.p);
+  g.pop[0] = ctx->d_pop[0].p; g.pop[1] = ctx->d_pop[1].p;
+  g.fit[0] = ctx->d_fit[0].p; g.fit[1] = ctx->d_fit[1].p;
+  g.hof = ctx->d_hof.p; g.st = ctx->d_state.p;
+  return g;
+}
+
+static int launch_generation(ahx_ctx *ctx, const GaDev &g, cudaStream_t s) {
+  const size_t smem = eval_m_smem_bytes(1, ctx->N, ctx->ga_L);
+  if (ctx->coo16) ga_generation_kernel<Coo16><<<g.P, kBlock, smem, s>>>(g);
+  else ga_generation_kernel<Coo32><<<g.P, kBlock, smem, s>>>(g);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  return AHX_OK;
+}
+
+static int read_state(ahx_ctx *ctx, GaState *hs) {
+  AHX_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_state.p, sizeof(GaState), cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+static void fill_stats(const ahx_ctx *ctx, const GaState &hs, ahx_ga_stats *stats) {
+  if (!stats) return;
+  stats->best_score = -hs.hof_fit;
+  stats->generations = hs.gen;
+  stats->updated = hs.updated;
+  stats->evaluations = hs.evals;
+  stats->stopped = hs.stop;
+  stats->reserved = 0;
+  stats->device_ms = ctx->ga_ms;
+}
+
+}  // namespace ahx
+
+using namespace ahx;
+
+extern "C" {
+
+void ahx_ga_default_params(ahx_ga_params *p) {
+  if (!p) return;
+  p->npop = 100;          // base.go:67 Npop
+  p->ngen = 5000;         // base.go:69 Ngen
+  p->max_gens = 1000000;  // evaluate.go:270
+  p->mut_prob = 0.2;      // base.go:71 MutaProb
+  p->seed = 42;           // base.go:65 Seed
+  p->tournament_k = 3;    // evaluate.go:273
+  p->log_every = 500;     // evaluate.go:294
+  p->phase = 1;
+  p->island = 0;
+}
+
+int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_t *init_tour) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_ga_begin: a GA run is already active");
+  if (!prm) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: null params");
+  if ((rc = validate_tour(ctx, L, init_tour, "ahx_ga_begin")) != AHX_OK) return rc;
+  if (L < 2) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: tour needs at least 2 contigs (MutSplice calls Intn(L-1), evaluate.go:214)");
+  if (prm->tournament_k < 1 || prm->tournament_k > kMaxContestants) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: tournament_k must be in [1,8]");
+  // eaopt: "Not enough individuals to select 2 with NContestants = k"
+  if (prm->npop < 2 || prm->npop - 2 < prm->tournament_k - 1) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: npop too small for 2 tournaments of k contestants");
+  if (!(prm->mut_prob >= 0.0 && prm->mut_prob <= 1.0) || prm->ngen < 0 || prm->max_gens < 0 || prm->log_every < 0)
+    return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: bad parameter");
+  const size_t smem = eval_m_smem_bytes(1, ctx->N, L);
+  if (smem + 2048 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: group too large for the generation kernel's shared memory");
+  if (ctx->coo16) AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  else AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  ctx->ga_prm = *prm; ctx->ga_L = L; ctx->ga_ms = 0.0;
+  const size_t PL = static_cast<size_t>(prm->npop) * L;
+  for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_pop[i].reserve(PL)); AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); }
+  AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1));
+  AHX_CUDA(ctx, ctx->d_tours.reserve(L)); AHX_CUDA(ctx, ctx->d_scores.reserve(1));
+  ctx->pop_P = ctx->pop_L = 0;
+  ctx->ga_active_set.assign(init_tour, init_tour + L);
+  std::sort(ctx->ga_active_set.begin(), ctx->ga_active_set.end());
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, init_tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_eval_m_sparse(ctx, ctx->d_tours.p, nullptr, nullptr, 1, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+  const GaDev g = make_dev(ctx);
+  ga_init_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g, ctx->d_tours.p, ctx->d_scores.p);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->ga_active = true;
+  return AHX_OK;
+}
+
+int ahx_ga_advance(ahx_ctx *ctx, int64_t n_gens, ahx_ga_stats *stats) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_ga_advance: no active GA run");
+  if (n_gens < 0) return fail(ctx, AHX_ERR_ARG, "ahx_ga_advance: negative n_gens");
+  const GaDev g = make_dev(ctx);
+  GaState hs{};
+  if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+  int64_t left = n_gens;
+  while (left > 0 && !hs.stop) {
+    const int64_t batch = std::min<int64_t>(left, 256);   // one host sync per batch to poll the stop flag
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    for (int64_t i = 0; i < batch; ++i)
+      if ((rc = launch_generation(ctx, g, ctx->stream)) != AHX_OK) return rc;
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+    float ms = 0.f;
+    AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->ga_ms += ms;
+    left -= batch;
+  }
+  fill_stats(ctx, hs, stats);
+  return AHX_OK;
+}
+
+int ahx_ga_best(ahx_ctx *ctx, int32_t *best_tour, double *best_score) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_ga_best: no active GA run");
+  GaState hs{};
+  if (best_tour) AHX_CUDA(ctx, cudaMemcpyAsync(best_tour, ctx->d_hof.p, sizeof(int32_t) * ctx->ga_L, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+  if (best_score) *best_score = -hs.hof_fit;
+  return AHX_OK;
+}
+
+int ahx_ga_get_elites(ahx_ctx *ctx, int32_t n, int32_t *tours, double *fitness) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_ga_get_elites: no active GA run");
+  if (n < 0 || n > ctx->ga_prm.npop || (n > 0 && (!tours || !fitness))) return fail(ctx, AHX_ERR_ARG, "ahx_ga_get_elites: bad argument");
+  if (n == 0) return AHX_OK;
+  GaState hs{};
+  if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+  const int cur = static_cast<int>(hs.gen & 1), P = ctx->ga_prm.npop, L = ctx->ga_L;
+  AHX_CUDA(ctx, ctx->d_taken.reserve(P)); AHX_CUDA(ctx, ctx->d_sel_idx.reserve(n)); AHX_CUDA(ctx, ctx->d_sel_fit.reserve(n));
+  AHX_CUDA(ctx, ctx->d_sel_tours.reserve(static_cast<size_t>(n) * L));
+  AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_taken.p, 0, P, ctx->stream));
+  select_extreme_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, P, n, 0, ctx->d_taken.p, ctx->d_sel_idx.p, ctx->d_sel_fit.p);
+  gather_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[cur].p, ctx->d_sel_idx.p, L, ctx->d_sel_tours.p);
+  ctx->launches += 2;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaMemcpyAsync(tours, ctx->d_sel_tours.p, sizeof(int32_t) * static_cast<size_t>(n) * L, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaMemcpyAsync(fitness, ctx->d_sel_fit.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_ga_put_migrants: no active GA run");
+  if (n < 0 || n > ctx->ga_prm.npop || (n > 0 && !tours)) return fail(ctx, AHX_ERR_ARG, "ahx_ga_put_migrants: bad argument");
+  if (n == 0) return AHX_OK;
+  const int P = ctx->ga_prm.npop, L = ctx->ga_L;
+  std::vector<int32_t> tmp(L);
+  for (int32_t m = 0; m < n; ++m) {   // bit-exact validity: a migrant must be a permutation of the active set
+    std::copy(tours + static_cast<size_t>(m) * L, tours + static_cast<size_t>(m + 1) * L, tmp.begin());
+    std::sort(tmp.begin(), tmp.end());
+    if (tmp != ctx->ga_active_set) return fail(ctx, AHX_ERR_ARG, "ahx_ga_put_migrants: migrant is not a permutation of the active contigs");
+  }
+  GaState hs{};
+  if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+  const int cur = static_cast<int>(hs.gen & 1);
+  AHX_CUDA(ctx, ctx->d_taken.reserve(P)); AHX_CUDA(ctx, ctx->d_sel_idx.reserve(n)); AHX_CUDA(ctx, ctx->d_sel_fit.reserve(n));
+  AHX_CUDA(ctx, ctx->d_sel_tours.reserve(static_cast<size_t>(n) * L));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sel_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(n) * L, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_taken.p, 0, P, ctx->stream));
+  select_extreme_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, P, n, 1, ctx->d_taken.p, ctx->d_sel_idx.p, ctx->d_sel_fit.p);
+  scatter_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[cur].p, ctx->d_sel_idx.p, L, ctx->d_sel_tours.p);
+  ctx->launches += 2;
+  AHX_CUDA(ctx, cudaGetLastError());
+  if ((rc = launch_eval_m_sparse(ctx, ctx->d_pop[cur].p, nullptr, ctx->d_sel_idx.p, n, L, ctx->d_fit[cur].p, ctx->stream)) != AHX_OK) return rc;
+  hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[cur].p, P, L, ctx->d_hof.p, ctx->d_state.p, n);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+int ahx_ga_end(ahx_ctx *ctx) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  ctx->ga_active = false;
+  return AHX_OK;
+}
+
+int ahx_ga_run(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_t *init_tour, int32_t *best_tour,
+               ahx_ga_stats *stats, ahx_ga_callback cb, void *user) {
+  int rc = ahx_ga_begin(ctx, prm, L, init_tour);
+  if (rc != AHX_OK) return rc;
+  std::vector<int32_t> hof(L);
+  ahx_ga_stats st{};
+  auto report = [&](int64_t gen) -> int {
+    if (!cb) return AHX_OK;
+    double score = 0.0;
+    int r = ahx_ga_best(ctx, hof.data(), &score);
+    if (r != AHX_OK) return r;
+    cb(user, prm->phase, gen, score, hof.data(), L);
+    return AHX_OK;
+  };
+  rc = ahx_ga_advance(ctx, 0, &st);
+  if (rc == AHX_OK) rc = report(0);   // ga.init's callback at generation 0
+  const int64_t period = prm->log_every > 0 ? prm->log_every : 500;
+  while (rc == AHX_OK && !st.stopped) {
+    const int64_t next = (st.generations / period + 1) * period;
+    rc = ahx_ga_advance(ctx, next - st.generations, &st);
+    if (rc == AHX_OK && prm->log_every > 0 && st.generations % period == 0) rc = report(st.generations);
+  }
+  if (rc == AHX_OK) {
+    double score = 0.0;
+    rc = ahx_ga_best(ctx, best_tour, &score);   // r.Tour = ga.HallOfFame[0] (evaluate.go:313)
+    if (stats) *stats = st;
+  }
+  ahx_ga_end(ctx);
+  return rc;
+}
+
+int ahx_mutate(ahx_ctx *ctx, int32_t L, const int32_t *tour_in, int32_t op, int32_t p, int32_t q, int32_t dir, int32_t *tour_out) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  if (L < 1 || !tour_in || !tour_out || op < 0 || op > 3) return fail(ctx, AHX_ERR_ARG, "ahx_mutate: bad argument");
+  if (op == 1 ? (p < 1 || p >= L) : (p < 0 || q < p || q >= L)) return fail(ctx, AHX_ERR_ARG, "ahx_mutate: positions out of range");
+  DevBuf<int32_t> a, b;
+  AHX_CUDA(ctx, a.reserve(L)); AHX_CUDA(ctx, b.reserve(L));
+  AHX_CUDA(ctx, cudaMemcpyAsync(a.p, tour_in, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
+  mutate_kernel<<<std::min(64, (L + 255) / 256), 256, 0, ctx->stream>>>(a.p, L, op, p, q, dir, b.p);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaMemcpyAsync(tour_out, b.p, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  a.release(); b.release();
+  return AHX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""Island-model GA across GPUs (one process per GPU, torch.distributed).
+
+The reference pins eaopt to a single population (`ga.NPops = 1`,
+evaluate.go:269) although eaopt has multi-population + migration support;
+SURVEY.md 8(e) maps that facility onto the 8 GPUs of a box: every rank runs
+the device-resident GA of libahx on its own sub-population and Philox stream
+(`island` = rank), and every `migrate_every` generations there is ONE exchange
+step: an all-gather of each island's `n_elite` best tours (L int32 + one f64
+each -- a few KB, latency-bound), after which every island replaces its worst
+individuals by the other islands' elites.  The exchange is the only
+collective; it runs over NCCL (NVLink/NVSwitch) when the process group is
+NCCL and over gloo in the CPU tests.
+
+`engine` only needs ga_begin / ga_advance / ga_get_elites / ga_put_migrants /
+ga_best / ga_end, so the protocol is testable on CPU with a stand-in engine.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _device_for(group):
+    backend = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+class IslandGA:
+    def __init__(self, engine, init_tour, params, migrate_every=50, n_elite=2, group=None):
+        self.eng, self.group = engine, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.L = len(init_tour)
+        self.migrate_every, self.n_elite = int(migrate_every), int(n_elite)
+        params.island = self.rank                       # independent Philox stream per island
+        self.params = params
+        self.dev = _device_for(group)
+        self.exchanges = 0
+        self.eng.ga_begin(np.ascontiguousarray(init_tour, np.int32), params)
+
+    def exchange(self):
+        """All-gather elites; replace this island's worst by everyone else's best."""
+        tours, fit = self.eng.ga_get_elites(self.n_elite)
+        payload = torch.empty(self.n_elite, self.L + 2, dtype=torch.int32)
+        payload[:, : self.L] = torch.from_numpy(tours)
+        payload[:, self.L:] = torch.from_numpy(fit.view(np.int32).reshape(self.n_elite, 2))   # f64 bits as 2 x int32
+        payload = payload.to(self.dev)
+        gathered = torch.empty(self.world * self.n_elite, self.L + 2, dtype=torch.int32, device=self.dev)
+        dist.all_gather_into_tensor(gathered, payload, group=self.group)
+        g = gathered.cpu().numpy().reshape(self.world, self.n_elite, self.L + 2)
+        others = np.concatenate([g[r, :, : self.L] for r in range(self.world) if r != self.rank], axis=0) if self.world > 1 else None
+        if others is not None and len(others):
+            self.eng.ga_put_migrants(np.ascontiguousarray(others, np.int32))
+        self.exchanges += 1
+        fits = np.ascontiguousarray(g[:, :, self.L:]).view(np.float64).reshape(self.world, self.n_elite)
+        return fits
+
+    def run(self, max_gens, on_exchange=None):
+        """Advance all islands in lock step until every island's EarlyStop fired or
+        `max_gens` generations ran.  Returns (best_tour, best_score, stats) with the
+        global best replicated on every rank."""
+        done, st = 0, None
+        while done < max_gens:
+            n = min(self.migrate_every, max_gens - done)
+            st = self.eng.ga_advance(n)
+            done += n
+            if self.world > 1:
+                fits = self.exchange()
+                if on_exchange:
+                    on_exchange(done, fits)
+                st = self.eng.ga_advance(0)
+            flag = torch.tensor([int(st.stopped)], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 1:
+                break
+        tour, score = self.eng.ga_best()
+        best = torch.tensor([score], dtype=torch.float64, device=self.dev)
+        allbest = torch.empty(self.world, dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(allbest, best, group=self.group)
+        owner = int(torch.argmax(allbest).item())
+        t = torch.from_numpy(np.ascontiguousarray(tour, np.int32)).to(self.dev)
+        dist.broadcast(t, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner, group=self.group)
+        return t.cpu().numpy(), float(allbest[owner].item()), st
+
+    def close(self):
+        self.eng.ga_end()
+
+
+def farm_groups(n_groups, rank, world, weights=None):
+    """One linkage group per GPU, no collective (allhic.go:170-173, 285-293):
+    longest-processing-time-first assignment by weight (~N^2)."""
+    order = sorted(range(n_groups), key=lambda g: -(weights[g] if weights is not None else 1))
+    load = [0.0] * world
+    mine = []
+    for g in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += weights[g] if weights is not None else 1
+        if r == rank:
+            mine.append(g)
+    return sorted(mine)

@@ -32,7 +32,7 @@ def config4_groups():
     return [dict(n=int(n), seed=4204 + g, npop=1000) for g, n in enumerate(ns)]
 
 
-def generate(n, seed, pairs_per_contig=100, mean_size=100_000):
+def generate(n, seed, pairs_per_contig=300, mean_size=100_000):
     """Returns dict(names, sizes, pa, pb, dists) where dists[e] is a (4, nlinks)
     int64 array in file orientation order ++, +-, -+, -- for pair (pa[e] < pb[e])."""
     rng = np.random.Generator(np.random.PCG64(seed))

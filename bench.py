@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- tour fitness evaluations/s of the `allhic optimize` hot path.
+
+One "step" = one pass of batched Tour.Evaluate ("EvaluateM", evaluate.go:116)
+over a population of P synthetic tours of one linkage group.
+  value  evals/s with the population resident in HBM (CUDA-event time of the
+         evaluate kernel, L2 flushed between steps)
+  e2e    evals/s through the C ABI call a host makes (ahx_eval_m_u16): pinned
+         host tours -> H2D -> kernel -> D2H scores, all inside the timed region
+  ga     (extra) generations/s and evals/s of the device-resident GA, as an
+         island model over NCCL when launched on N > 1 GPUs
+`--impl reference` times the CPU restatement of the reference's own
+implementation (oracle/, C, all host threads) on the same workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config3] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LIMIT = 10_000_000
+METRIC = "tour fitness evals/sec"
+UNIT = "evals/s"
+
+
+def workload(name):
+    from allhic_b200 import synth
+    cfg = synth.CONFIGS[name]
+    ids, clm, _ = synth.materialize(name)
+    desc = {"config2": "synthetic 500-contig linkage group, population 1k, EvaluateM (BASELINE configs[1])",
+            "config3": "synthetic 2,000-contig linkage group, population 8k, EvaluateM (BASELINE configs[2], the north_star target size)",
+            "config5": "synthetic 10,000-contig linkage group, population 8k, EvaluateM (BASELINE configs[4])"}[name]
+    return ids, clm, cfg["n"], cfg["npop"], desc
+
+
+def make_tours(n, P, seed):
+    rng = np.random.default_rng(seed)
+    return np.stack([rng.permutation(n) for _ in range(P)]).astype(np.int32)
+
+
+def work_per_tour(sizes, tables, tours, sample=128):
+    """Mean pair-terms per tour: E_act (contig-space kernel: stored pairs within
+    LIMIT) and W (position-space window pairs of the reference loop)."""
+    idx = np.linspace(0, len(tours) - 1, min(sample, len(tours))).astype(int)
+    e_act, w = [], []
+    for i in idx:
+        t = tours[i]
+        s = sizes[t].astype(np.float64)
+        mid = np.cumsum(s) - s / 2
+        x = np.full(len(sizes), np.nan); x[t] = mid
+        d = np.abs(x[tables["pa"]] - x[tables["pb"]])
+        e_act.append(int((d <= LIMIT).sum()))
+        hi = np.searchsorted(mid, mid + LIMIT, side="right")
+        w.append(int((hi - np.arange(len(t)) - 1).sum()))
+    return float(np.mean(e_act)), float(np.mean(w))
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.p = gpu, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # samples taken while the GPU idles between phases pull the median down: keep the busy half
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_population_evals(ids, clm, tours, min_seconds, threads):
+    """The CPU restatement's ParallelEval over the same population (oracle, kind=port)."""
+    from oracle_lib import OracleCLM
+    orc = OracleCLM(clm, ids)
+    t64 = np.ascontiguousarray(tours, np.int64)
+    orc.population_evaluate(t64[: max(threads, 8)], nthreads=threads)       # warm-up: builds M
+    t0 = time.perf_counter(); reps = 0
+    while True:
+        orc.population_evaluate(t64, nthreads=threads); reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return reps * len(t64) / dt, reps, dt
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path.  The Go
+    binary cannot be built in this image (no Go toolchain), so this is the C
+    restatement in oracle/ (kind=port) on all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    ids, clm, n, P, desc = workload(args.workload)
+    threads = os.cpu_count() or 1
+    from oracle_lib import OracleCLM
+    orc = OracleCLM(clm, ids)
+    S = min(P, max(threads * 16, 512))          # bounded sample of the population per step
+    tours = np.ascontiguousarray(make_tours(n, S, 1234), np.int64)
+    for _ in range(max(1, args.warmup)):
+        orc.population_evaluate(tours[: threads * 2], nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.population_evaluate(tours, nthreads=threads)
+    dt = time.perf_counter() - t0
+    v = args.steps * S / dt
+    sample = "%d of the %d tours per step x %d steps, oracle/allhic_oracle.c orc_population_evaluate, %d threads" % (S, P, args.steps, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": desc, "n_contigs": n, "population": P, "sample_per_step": S},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config5"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ga-gens", type=int, default=300)
+    ap.add_argument("--no-ga", action="store_true")
+    ap.add_argument("--no-dense", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import allhic_b200 as A
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if rank == 0:
+        ids, clmf, n, P, desc = workload(args.workload)
+    barrier()
+    ids, clmf, n, P, desc = workload(args.workload)       # other ranks reuse the files rank 0 wrote
+    clm = A.CLM(clmf, ids)
+    tables, sizes = clm.tables(), clm.sizes()
+    E = len(tables["pa"])
+    eng = A.Engine(local)
+    eng.load(clm)
+    tours = make_tours(n, P, 1000 + rank)                  # weak scaling: P tours per GPU
+    L = n
+    e_act, w_dense = work_per_tour(sizes, tables, tours)
+
+    # pinned host buffers for the e2e call
+    use16 = n <= 65535
+    pin_t = A.PinnedArray((P, L), np.uint16 if use16 else np.int32)
+    pin_o = A.PinnedArray((P,), np.float64)
+    pin_t.array[:] = tours
+    h2d, d2h = pin_t.nbytes, pin_o.nbytes
+
+    eng.pop_set(tours)
+    dfma_tflops, ddiv_g = eng.probe_fp64()
+    l2_gbs = eng.probe_l2(64 << 20)
+    for _ in range(max(3, args.warmup)):
+        eng.flush_l2(); eng.pop_eval_m("sparse", 1)
+    for _ in range(max(3, args.warmup)):
+        eng.eval_m(pin_t.array, out=pin_o.array)
+
+    clocks = ClockSampler(local); clocks.start()
+    # ---- device-resident steps (value)
+    barrier()
+    lc0 = eng.launch_count()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        eng.flush_l2()                                    # not timed: evict the tours/COO from L2
+        dev_ms += eng.pop_eval_m("sparse", 1)             # CUDA events around the kernel on its own stream
+    eval_launches = (eng.launch_count() - lc0) - args.steps   # minus the flush kernels
+    barrier()
+    dev_ms = max_over_ranks(dev_ms)
+    scores_dev = eng.pop_scores()
+    # ---- end-to-end steps (e2e): host buffers through the C ABI
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.eval_m(pin_t.array, out=pin_o.array)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clk = clocks.stop()
+    assert np.array_equal(scores_dev, pin_o.array), "resident and e2e paths disagree"
+
+    value = world * P * args.steps / (dev_ms * 1e-3)
+    e2e_v = world * P * args.steps / e2e_s
+    kern_s = dev_ms * 1e-3 / args.steps
+    terms_per_s = P * e_act / kern_s                       # per GPU (roofline is a per-kernel figure)
+    roof = {"bound": "fp64", "achieved": 2.0 * terms_per_s / 1e12, "peak": dfma_tflops, "unit": "TFLOP/s",
+            "frac": 2.0 * terms_per_s / 1e12 / dfma_tflops, "traffic": None,
+            "peak_source": "DFMA microbenchmark measured live by this run (MEASURED_PEAKS.json has no fp64 figure)",
+            "kernel": "eval_m_sparse_kernel", "pair_terms_per_tour": e_act, "flops_per_pair_term": 2,
+            "pair_terms_per_s": terms_per_s, "measured_div_add_peak_per_s": ddiv_g * 1e9,
+            "frac_of_div_add_peak": terms_per_s / (ddiv_g * 1e9),
+            "dense_equivalent": {"window_pairs_per_tour": w_dense, "bytes_per_tour": 4 * w_dense + 12 * L,
+                                 "algorithmic_GBs": P * (4 * w_dense + 12 * L) / kern_s / 1e9, "hbm_peak_GBs": 6544.3,
+                                 "note": "algorithmic speed-up of the contig-space formulation, not a roofline fraction"}}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": desc, "n_contigs": n, "population_per_gpu": P, "contig_pairs_E": E, "l2": "flushed between device-timed steps (write of 2x L2)",
+                      "parallelism": "independent sub-populations, one per GPU" if world > 1 else "single GPU"},
+           "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "call": "ahx_eval_m_u16" if use16 else "ahx_eval_m", "ms_per_step": e2e_s / args.steps * 1e3},
+           "gpu_launches": int(eval_launches), "clocks": clk, "roofline": roof,
+           "probes": {"dfma_tflops": dfma_tflops, "ddiv_add_gops": ddiv_g, "l2_read_GBs_64MB": l2_gbs}}
+
+    # ---- dense (north_star literal) kernel, for the record
+    if not args.no_dense and rank == 0:
+        sub = min(P, 2048)
+        eng.pop_set(tours[:sub])
+        eng.pop_eval_m("dense", 1)
+        ms = 0.0
+        for _ in range(5):
+            eng.flush_l2(); ms += eng.pop_eval_m("dense", 1)
+        dk = ms * 1e-3 / 5
+        out["dense_kernel"] = {"evals_per_s": sub / dk, "population": sub,
+                               "roofline": {"bound": "hbm", "achieved": sub * (4 * w_dense + 12 * L) / dk / 1e9, "peak": 6544.3, "unit": "GB/s",
+                                            "frac": sub * (4 * w_dense + 12 * L) / dk / 1e9 / 6544.3,
+                                            "note": "M (%.0f MB int32) is %s" % (4.0 * n * n / 1e6, "L2-resident: bytes come from L2, not HBM" if 4 * n * n < 100e6 else "larger than L2")}}
+
+    # ---- GA (generations/s), islands over NCCL when world > 1
+    if not args.no_ga:
+        prm = eng.ga_params(npop=P, ngen=1 << 30, max_gens=1 << 40, seed=42)
+        init = tours[0]
+        if world > 1:
+            from allhic_b200.islands import IslandGA
+            ga = IslandGA(eng, init, prm, migrate_every=50, n_elite=2)
+            ga.run(50)                                    # warm-up
+            barrier(); t0 = time.perf_counter()
+            _, best, st = ga.run(args.ga_gens)
+            torch.cuda.synchronize(); ga_s = max_over_ranks(time.perf_counter() - t0)
+            ga.close()
+        else:
+            eng.ga_begin(init, prm)
+            st0 = eng.ga_advance(50)
+            barrier(); t0 = time.perf_counter()
+            st = eng.ga_advance(args.ga_gens)
+            ga_s = time.perf_counter() - t0
+            best = st.best_score
+            eng.ga_end()
+            st = type("S", (), dict(evaluations=st.evaluations - st0.evaluations))
+        ev = torch.tensor([float(st.evaluations)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ev)
+        out["ga"] = {"generations_per_s": args.ga_gens / ga_s, "population_per_gpu": P, "generations": args.ga_gens,
+                     "evals_per_s_inside_ga": float(ev.item()) / ga_s if world == 1 else None, "best_score": best,
+                     "model": "islands, all-gather of 2 elites every 50 generations over NCCL" if world > 1 else "single population"}
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only)
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        v, reps, dt = cpu_population_evals(ids, clmf, tours, args.cpu_seconds, threads)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "the same %d-tour population x %d passes (%.1f s), C restatement of Tour.Evaluate + eaopt ParallelEval chunking, %d threads" % (P, reps, dt, threads)}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    pin_t.close(); pin_o.close(); eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+"""CPU: the oracle against the golden vectors, the independent Python
+restatement, and the semantics of the reference code it restates."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import FIX_CLM, FIX_IDS, GOLDEN
+import oracle_lib as O
+from pyref import PyCLM, golden_array as py_golden, sum_log as py_sumlog, GR, LIMIT
+
+
+@pytest.fixture(scope="module")
+def known():
+    return json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+
+
+def test_baseline_known_answers(oracle_fixture):
+    """BASELINE.md section 2 (values derived in the survey from a third restatement)."""
+    c = oracle_fixture
+    idt = np.arange(100)
+    assert c.evaluate(idt) == -0.12543807565816803
+    assert c.evaluate(idt[::-1].copy()) == -0.12543807565816817
+    c.set_tour(idt); c.set_signs(np.full(100, ord('+'), np.uint8))
+    assert c.evaluate_q() == pytest.approx(-97972.039312616194, rel=1e-15)
+    c.set_signs(np.full(100, ord('-'), np.uint8))
+    assert c.evaluate_q() == pytest.approx(-118435.21363012613, rel=1e-15)
+    M = c.M()
+    assert (M[0, 1], M[1, 2], (M != 0).sum(), np.triu(M).sum()) == (60, 96, 1076, 9795)
+    assert (M == M.T).all() and c.sizes().sum() == 9999998
+
+
+def test_golden_cases(oracle_fixture, known):
+    c = oracle_fixture
+    assert known["N"] == c.N and known["ncontacts"] == 538 and known["noriented"] == 4304
+    for case in known["cases"]:
+        t = np.array(case["tour"], np.int64)
+        c.set_tour(t); c.set_signs(np.frombuffer(case["signs"].encode(), np.uint8))
+        assert c.evaluate(t) == case["evaluate"]
+        assert c.evaluate_q() == case["evaluate_q"]
+        assert c.evaluate_q(literal=True) == case["evaluate_q"]
+
+
+def test_oracle_vs_python_restatement(oracle_fixture):
+    c, py = oracle_fixture, PyCLM(FIX_CLM, FIX_IDS)
+    assert c.names() == py.names and c.sizes().tolist() == py.sizes
+    ai, bi, st, nl, md = c.contacts()
+    assert len(ai) == len(py.contacts)
+    for k in range(len(ai)):
+        s, n, m = py.contacts[(int(ai[k]), int(bi[k]))]
+        assert (s, n) == (st[k], nl[k]) and abs(m - md[k]) <= 1e-13 * abs(m)
+    oa, ob, ao, bo, g = c.oriented()
+    assert len(oa) == len(py.oriented)
+    for k in range(len(oa)):
+        assert py.oriented[(int(oa[k]), int(ob[k]), chr(ao[k]), chr(bo[k]))] == g[k].tolist()
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        t = rng.permutation(c.N)
+        s = np.where(rng.random(c.N) < 0.5, ord('+'), ord('-')).astype(np.uint8)
+        assert c.evaluate(t) == py.evaluate(t.tolist())
+        c.set_tour(t); c.set_signs(s)
+        assert c.evaluate_q() == pytest.approx(py.evaluate_q(t.tolist(), [chr(x) for x in s]), rel=1e-13)
+
+
+def test_go_log_and_golden_bins():
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([rng.integers(1, 1 << 28, 2000), [1, 2, 3, 5778, 1149851, 2047, 2048, (1 << 27)]])
+    for x in xs:
+        a, b = O.go_log(float(x)), math.log(float(x))
+        assert abs(a - b) <= 2 * math.ulp(b)
+    # bins do not depend on last-ulp differences of the log: every boundary phi^(k+.5) is far from an integer
+    phi = math.exp(0.4812118250596684)
+    for k in range(17, 31):
+        bnd = phi ** (k + 0.5)
+        assert min(bnd - math.floor(bnd), math.ceil(bnd) - bnd) > 1e-3
+    for _ in range(50):
+        a = rng.integers(1, 1 << 27, rng.integers(1, 200))
+        assert O.golden_array(a).tolist() == py_golden(a.tolist())
+        assert O.sumlog(a) == pytest.approx(py_sumlog(a.tolist()), rel=1e-14)
+    assert O.golden_array([1, 10, 5778, 7349, 7350, 10 ** 9]).tolist() == [4, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]
+
+
+def test_limit_window_and_w_count(synth_small):
+    ids, clm, g = synth_small
+    c = O.OracleCLM(clm, ids)
+    n = c.N
+    idt = np.arange(n)
+    W = c.count_W(idt)
+    assert 0 < W < n * (n - 1) // 2          # G = 30 Mb > LIMIT: the window truncates
+    py = PyCLM(clm, ids)
+    rng = np.random.default_rng(2)
+    for t in (idt, rng.permutation(n), rng.permutation(n)[:123]):
+        assert c.evaluate(t) == py.evaluate(list(map(int, t)))
+    s = np.where(rng.random(n) < 0.5, ord('+'), ord('-')).astype(np.uint8)
+    t = rng.permutation(n)
+    c.set_tour(t); c.set_signs(s)
+    q, terms = c.evaluate_q_terms()
+    assert q == c.evaluate_q(literal=True)
+    assert q == pytest.approx(py.evaluate_q(list(map(int, t)), [chr(x) for x in s]), rel=1e-13)
+    assert 0 < terms <= len(g["pa"])
+
+
+def test_empty_and_tiny_tours(oracle_fixture):
+    c = oracle_fixture
+    assert c.evaluate(np.zeros(0, np.int64)) == 0.0
+    assert c.evaluate(np.array([7], np.int64)) == 0.0
+    c.set_tour(np.array([3], np.int64))
+    assert c.evaluate_q() == 0.0
+    c.set_tour(np.array([0, 1], np.int64)); c.set_signs(np.full(100, ord('+'), np.uint8))
+    # adjacent contigs: dist = cumsize[j-1]-cumsize[i] = 0 (orientation.go:181)
+    g = PyCLM(FIX_CLM, FIX_IDS).oriented[(0, 1, '+', '+')]
+    want = 0.0
+    for k in range(12):
+        want -= g[k] * math.log(GR[k])
+    assert c.evaluate_q() == pytest.approx(want, rel=1e-14)
+
+
+def test_mutation_operators():
+    rng = np.random.default_rng(3)
+    for L in (1, 2, 3, 10, 57):
+        base = rng.permutation(L).astype(np.int64)
+        for _ in range(40):
+            p, q = sorted(rng.integers(0, L, 2).tolist())
+            b = base.tolist()
+            # MutPermute evaluate.go:200-208
+            want = b.copy(); want[p], want[q] = want[q], want[p]
+            assert O.mutate(base, "permute", p=p, q=q).tolist() == want
+            # MutInversion evaluate.go:157-169
+            want = b[:p] + b[p:q + 1][::-1] + b[q + 1:]
+            assert O.mutate(base, "inversion", p=p, q=q).tolist() == want
+            # MutInsertion evaluate.go:172-197
+            want = b[:p] + [b[q]] + b[p:q] + b[q + 1:]
+            assert O.mutate(base, "insertion", p=p, q=q, front=1).tolist() == want
+            want = b[:p] + b[p + 1:q + 1] + [b[p]] + b[q + 1:]
+            assert O.mutate(base, "insertion", p=p, q=q, front=0).tolist() == want
+            if L > 1:                                  # MutSplice evaluate.go:212-218
+                k = int(rng.integers(1, L))
+                assert O.mutate(base, "splice", k=k).tolist() == b[k:] + b[:k]
+
+
+def test_parse_semantics(tmp_path):
+    ids = tmp_path / "a.ids"; clm = tmp_path / "a.clm"
+    ids.write_text("#Contig\tRECounts\tLength\nA\t1\t1000\nB 7 recover 2000\nC\t3000\n")
+    clm.write_text("A+ B+\t2\t5000 6000\n"
+                   "A+ B-\t3\t100 200 300\n"          # SumLog 15.6 < 17.3: replaces the first line in contacts (clm.go:229-236)
+                   "A+ B+\t1\t900000\n"               # SumLog 13.7: replaces again; and last line wins the oriented key (clm.go:237)
+                   "A- X+\t1\t10\n"                   # unknown contig skipped (clm.go:211-218)
+                   "C- A+\t2\t7000 8000\n")           # written with the higher index first
+    c = O.OracleCLM(str(clm), str(ids))
+    assert c.names() == ["A", "B", "C"] and c.sizes().tolist() == [1000, 2000, 3000]
+    ai, bi, st, nl, md = c.contacts()
+    d = {(int(a), int(b)): (int(s), int(n)) for a, b, s, n in zip(ai, bi, st, nl)}
+    assert d == {(0, 1): (1, 1), (2, 0): (-1, 2)}
+    M = c.M()
+    assert M[0, 1] == 1 and M[1, 0] == 1 and M[0, 2] == 2 and M[2, 0] == 2 and M[1, 2] == 0
+    oa, ob, ao, bo, g = c.oriented()
+    om = {(int(a), int(b), chr(x), chr(y)): gg.tolist() for a, b, x, y, gg in zip(oa, ob, ao, bo, g)}
+    assert om[(0, 1, '+', '+')] == py_golden([900000])
+    assert om[(1, 0, '-', '-')] == py_golden([900000])     # mirror key (b,a,rr(bo),rr(ao))
+    assert om[(1, 0, '+', '-')] == py_golden([100, 200, 300])
+    assert om[(2, 0, '-', '+')] == om[(0, 2, '-', '+')] == py_golden([7000, 8000])
+    assert len(om) == 6
+
+
+def test_flips_and_ga_invariants(oracle_fixture):
+    c = oracle_fixture
+    rng = np.random.default_rng(9)
+    t = rng.permutation(c.N)
+    c.set_tour(t); c.set_signs(np.where(rng.random(c.N) < 0.5, ord('+'), ord('-')).astype(np.uint8))
+    q0 = c.evaluate_q()
+    acc, a, b = c.flip_whole()
+    assert a == q0 and acc == (b > a) and c.evaluate_q() == max(a, b)
+    q1 = c.evaluate_q()
+    any_, na, nr, fs, trace, steps = c.flip_one()
+    assert na + nr == c.N and any_ == (na > 0) and fs == c.evaluate_q() and fs >= q1
+    assert (np.diff(trace[:, 0]) >= 0).all() and steps.sum() == na
+    # flipAll: eigenvector sign pattern can only improve or keep the score (orientation.go:57)
+    acc, a, b = c.flip_all()
+    assert c.evaluate_q() == (b if acc else a) and (b >= a) == acc
+    c.set_tour(t)
+    f0 = -c.evaluate()
+    r = c.ga_run(npop=60, ngen=30, mutprob=0.2, seed=42, max_gens=400)
+    assert sorted(c.tour().tolist()) == list(range(c.N))
+    assert r.best_score >= f0 and r.best_score == -c.evaluate()
+    assert r.generations <= 400 and r.evaluations >= 60

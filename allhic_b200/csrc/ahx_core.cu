@@ -96,6 +96,65 @@ eval_m_sparse_kernel(const IdxT *__restrict__ tours, const int *__restrict__ row
 }
 
 // ---------------------------------------------------------------------------
+// Tour.Evaluate, contig-space kernel with 32-bit coordinates (the product path).
+//   grid = ceil(P / T) CTAs, kBlock threads.  Dynamic shared memory:
+//     tiles  Elem[kStages*kTile]  pair-table tiles filled by TMA bulk copies
+//     X      uint32[N*T]          2*mid of contig c in tour t at X[c*T+t]
+//     tig    int[L]               staging of one tour
+//   The pair table is pre-ordered on the host so that the 8 lanes of every
+//   quarter-warp hit 8 different 16-byte bank groups (see order_pairs()).
+// ---------------------------------------------------------------------------
+template <int T, typename Coo, typename IdxT>
+__global__ void __launch_bounds__(kBlock)
+eval_m_x32_kernel(const IdxT *__restrict__ tours, const int *__restrict__ rows, int P, int L, int N,
+                  const long long *__restrict__ sizes, const typename Coo::Elem *__restrict__ coo, int E_pad,
+                  double *__restrict__ out, int *__restrict__ errflag) {
+  using Elem = typename Coo::Elem;
+  extern __shared__ __align__(128) unsigned char smem_x32[];
+  __shared__ long long scan_scratch[kWarps];
+  __shared__ double red_scratch[kWarps];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  Elem *tiles = reinterpret_cast<Elem *>(smem_x32);
+  uint32_t *X = reinterpret_cast<uint32_t *>(smem_x32 + sizeof(Elem) * kStages * kTile);
+  int *tig = reinterpret_cast<int *>(X + static_cast<size_t>(N) * T);
+  const int tid = threadIdx.x;
+  const int p0 = blockIdx.x * T;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    mbar_init_fence();
+  }
+  for (int i = tid; i < N * T; i += kBlock) X[i] = kInactiveX;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    if (p0 + t >= P) break;
+    const int row = rows ? rows[p0 + t] : p0 + t;
+    const IdxT *src = tours + static_cast<size_t>(row) * L;
+    for (int i = tid; i < L; i += kBlock) {
+      int v = static_cast<int>(src[i]);
+      if (static_cast<unsigned>(v) >= static_cast<unsigned>(N)) { *errflag = 1; v = 0; }
+      tig[i] = v;
+    }
+    __syncthreads();
+    scatter_x32<T>(tig, L, sizes, X, t, scan_scratch, tid);
+    __syncthreads();
+  }
+  double acc[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t] = 0.0;
+  stream_pairs_x32<T, Coo>(X, coo, E_pad, tiles, bars, acc, tid);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const double s = block_sum(acc[t], red_scratch, tid);
+    if (tid == 0 && p0 + t < P) {
+      const int row = rows ? rows[p0 + t] : p0 + t;
+      out[row] = 0.0 - s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Tour.Evaluate, position-space kernel over the dense int32 M (literal loop of
 // evaluate.go:129-141).  One CTA per tour; warp w owns rows i = w, w+8, ...;
 // lanes sweep j = i+1.. and stop at the first j beyond LIMIT.
@@ -265,11 +324,11 @@ size_t eval_m_smem_bytes(int T, int32_t N, int32_t L) {
 static int pick_T(const ahx_ctx *ctx, int32_t P, int32_t L) {
   if (const char *env = getenv("AHX_EVAL_T")) {
     const int t = atoi(env);
-    if ((t == 1 || t == 2 || t == 4) && eval_m_smem_bytes(t, ctx->N, L) <= ctx->smem_optin - 1024) return t;
+    if ((t == 1 || t == 2) && eval_m_smem_bytes(t, ctx->N, L) <= ctx->smem_optin - 1024) return t;
   }
   // Amortise the COO stream over several tours while keeping >= 2 CTAs per SM
   // and enough CTAs to fill the machine.
-  for (int t : {4, 2}) {
+  for (int t : {2}) {
     const size_t bytes = eval_m_smem_bytes(t, ctx->N, L);
     if (bytes * 2 + 4096 <= ctx->smem_optin && (P + t - 1) / t >= 4 * ctx->sm_count) return t;
   }
@@ -304,24 +363,74 @@ static cudaError_t launch_sparse_c(ahx_ctx *ctx, const IdxT *tours, const int32_
   if (eval_m_smem_bytes(1, ctx->N, L) + 1024 > ctx->smem_optin)
     return launch_sparse_t<1, Coo, IdxT, true>(ctx, tours, rows, P, L, out, s);
   switch (pick_T(ctx, P, L)) {
-    case 4: return launch_sparse_t<4, Coo, IdxT, false>(ctx, tours, rows, P, L, out, s);
     case 2: return launch_sparse_t<2, Coo, IdxT, false>(ctx, tours, rows, P, L, out, s);
     default: return launch_sparse_t<1, Coo, IdxT, false>(ctx, tours, rows, P, L, out, s);
   }
+}
+
+size_t eval_x32_smem_bytes(int T, bool coo16, int32_t N, int32_t L) {
+  return (coo16 ? sizeof(uint2) : sizeof(int4)) * static_cast<size_t>(kStages) * kTile + sizeof(uint32_t) * static_cast<size_t>(N) * T +
+         sizeof(int) * static_cast<size_t>(L);
+}
+
+static int pick_T32(const ahx_ctx *ctx, int32_t P, int32_t L) {
+  auto fits = [&](int t, int ctas) { return (eval_x32_smem_bytes(t, ctx->coo16, ctx->N, L) + 1536) * ctas <= ctx->smem_optin + 1024 * (ctas - 1) && eval_x32_smem_bytes(t, ctx->coo16, ctx->N, L) + 2048 <= ctx->smem_optin; };
+  if (const char *env = getenv("AHX_EVAL_T")) {
+    const int t = atoi(env);
+    if ((t == 1 || t == 2 || t == 4) && fits(t, 1)) return t;
+  }
+  // several tours per CTA amortise the pair-table stream and make each shared-memory
+  // gather serve T tours; keep >= 3 CTAs per SM and enough CTAs for two waves
+  for (int t : {4, 2})
+    if (fits(t, 3) && (P + t - 1) / t >= 2 * ctx->sm_count) return t;
+  return 1;
+}
+
+template <int T, typename Coo, typename IdxT>
+static cudaError_t launch_x32_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
+  auto kern = eval_m_x32_kernel<T, Coo, IdxT>;
+  const size_t smem = eval_x32_smem_bytes(T, ctx->coo16, ctx->N, L);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const typename Coo::Elem *coo;
+  if constexpr (sizeof(typename Coo::Elem) == 8) coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo16o.p);
+  else coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo32o.p);
+  kern<<<(P + T - 1) / T, kBlock, smem, s>>>(tours, rows, P, L, ctx->N, ctx->d_sizes.p, coo, static_cast<int>(ctx->E_pad), out, ctx->d_errflag.p);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+template <typename Coo, typename IdxT>
+static cudaError_t launch_x32_c(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
+  switch (pick_T32(ctx, P, L)) {
+    case 4: return launch_x32_t<4, Coo, IdxT>(ctx, tours, rows, P, L, out, s);
+    case 2: return launch_x32_t<2, Coo, IdxT>(ctx, tours, rows, P, L, out, s);
+    default: return launch_x32_t<1, Coo, IdxT>(ctx, tours, rows, P, L, out, s);
+  }
+}
+
+// Which formulation can run: 32-bit coordinates need 2*sum(sizes) + 2*LIMIT + 2 < 2^32
+// and N*4 bytes of shared memory; otherwise the fp64 kernel (x in shared or global memory).
+bool use_x32(const ahx_ctx *ctx, int32_t L) {
+  if (const char *env = getenv("AHX_EVAL_FP64")) if (atoi(env)) return false;
+  return ctx->x32_ok && eval_x32_smem_bytes(1, ctx->coo16, ctx->N, L) + 2048 <= ctx->smem_optin;
 }
 
 int launch_eval_m_sparse(ahx_ctx *ctx, const int32_t *d_tours, const uint16_t *d_tours16, const int32_t *d_rows,
                          int32_t P, int32_t L, double *d_out, cudaStream_t s) {
   if (P == 0) return AHX_OK;
   cudaError_t e;
-  if (d_tours16) {
+  if (use_x32(ctx, L)) {
+    if (d_tours16) e = ctx->coo16 ? launch_x32_c<Coo16, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s) : launch_x32_c<Coo32, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s);
+    else e = ctx->coo16 ? launch_x32_c<Coo16, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s) : launch_x32_c<Coo32, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s);
+  } else if (d_tours16) {
     e = ctx->coo16 ? launch_sparse_c<Coo16, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s)
                    : launch_sparse_c<Coo32, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s);
   } else {
     e = ctx->coo16 ? launch_sparse_c<Coo16, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s)
                    : launch_sparse_c<Coo32, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s);
   }
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "eval_m_sparse_kernel launch");
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "eval_m kernel launch");
   return AHX_OK;
 }
 
@@ -403,6 +512,43 @@ static int validate_tours(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours,
   return AHX_OK;
 }
 
+
+// Bank-conflict-free ordering of the pair table for the x32 kernel.  With T = 4
+// tours per CTA a contig's coordinates are one 16-byte shared-memory word and a
+// 128-bit load is served one quarter-warp (8 lanes) at a time across 8 bank
+// groups, group = contig mod 8.  Pairs are therefore emitted in blocks of 8 in
+// which all `a mod 8` and all `b mod 8` are distinct (greedy over the 64
+// (a mod 8, b mod 8) buckets, largest bucket first); blocks that cannot be
+// filled are padded with (0,0,0) entries, which contribute nothing (d = 0).
+// The order of the terms only changes the (fixed) summation order.
+void order_pairs(int64_t E, const int32_t *pa, const int32_t *pb, std::vector<int64_t> *order /* -1 = padding */) {
+  std::vector<std::vector<int64_t>> bucket(64);
+  for (int64_t e = E - 1; e >= 0; --e) bucket[(pa[e] & 7) * 8 + (pb[e] & 7)].push_back(e);   // pop_back yields ascending e
+  order->clear();
+  order->reserve(static_cast<size_t>(E + E / 8 + 512));
+  int64_t left = E;
+  int rot = 0;
+  while (left > 0) {
+    bool used_b[8] = {false, false, false, false, false, false, false, false};
+    int filled = 0;
+    for (int i = 0; i < 8; ++i) {
+      const int r = (i + rot) & 7;
+      int best = -1; size_t best_n = 0;
+      for (int c = 0; c < 8; ++c) {
+        const size_t n = bucket[r * 8 + c].size();
+        if (!used_b[c] && n > best_n) { best = c; best_n = n; }
+      }
+      if (best >= 0) {
+        order->push_back(bucket[r * 8 + best].back());
+        bucket[r * 8 + best].pop_back();
+        used_b[best] = true; --left; ++filled;
+      }
+    }
+    for (; filled < 8; ++filled) order->push_back(-1);
+    rot = (rot + 1) & 7;
+  }
+  while (order->size() % kBlock) order->push_back(-1);
+}
 }  // namespace ahx
 
 using namespace ahx;
@@ -425,7 +571,6 @@ static int eval_m_host(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours, do
   IdxT *dt;
   if constexpr (k16) { AHX_CUDA(ctx, ctx->d_tours16.reserve(total)); dt = ctx->d_tours16.p; }
   else { AHX_CUDA(ctx, ctx->d_tours.reserve(total)); dt = ctx->d_tours.p; }
-  ctx->pop_P = ctx->pop_L = 0;  // the staging buffer doubles as the resident population
   AHX_CUDA(ctx, ctx->d_scores.reserve(P));
   // ~4 MB per chunk, at most 16 chunks, chunk sizes multiple of 4 tours
   int nchunk = static_cast<int>(std::min<size_t>(16, std::max<size_t>(1, total * sizeof(IdxT) / (4u << 20))));
@@ -508,9 +653,9 @@ void ahx_destroy(ahx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  ctx->d_sizes.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_pa.release(); ctx->d_pb.release();
+  ctx->d_sizes.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
-  ctx->d_tours.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
+  ctx->d_tours.release(); ctx->d_res_tours.release(); ctx->d_res_scores.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
   ctx->d_flush.release(); ctx->d_errflag.release();
   for (int i = 0; i < 2; ++i) { ctx->d_pop[i].release(); ctx->d_fit[i].release(); }
   ctx->d_hof.release(); ctx->d_sel_idx.release(); ctx->d_sel_tours.release(); ctx->d_sel_fit.release(); ctx->d_taken.release();
@@ -574,6 +719,27 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
     AHX_CUDA(ctx, ctx->d_coo32.reserve(E));
     if (E) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo32.p, c32.data(), sizeof(int4) * E, cudaMemcpyHostToDevice, ctx->stream));
   }
+  {
+    long long total = 0;
+    for (int32_t i = 0; i < N; ++i) total += sizes[i];
+    ctx->x32_ok = 2 * total + 2LL * AHX_LIMIT + 2 < 0xFFFFFFFFLL;
+    std::vector<int64_t> ord;
+    order_pairs(E, pa, pb, &ord);
+    ctx->E_pad = static_cast<int64_t>(ord.size());
+    if (ctx->coo16) {
+      std::vector<uint2> o16(ord.size());
+      for (size_t i = 0; i < ord.size(); ++i) o16[i] = ord[i] < 0 ? make_uint2(0, 0) : c16[ord[i]];
+      AHX_CUDA(ctx, ctx->d_coo16o.reserve(ord.size()));
+      if (!ord.empty()) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo16o.p, o16.data(), sizeof(uint2) * ord.size(), cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+      std::vector<int4> o32(ord.size());
+      for (size_t i = 0; i < ord.size(); ++i) o32[i] = ord[i] < 0 ? make_int4(0, 0, 0, 0) : c32[ord[i]];
+      AHX_CUDA(ctx, ctx->d_coo32o.reserve(ord.size()));
+      if (!ord.empty()) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo32o.p, o32.data(), sizeof(int4) * ord.size(), cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
   // CSR of pairs touching each contig (for flipOne's O(deg) deltas)
   std::vector<int32_t> ptr(N + 1, 0), adj(2 * E);
   for (int64_t e = 0; e < E; ++e) { ptr[pa[e] + 1]++; ptr[pb[e] + 1]++; }
@@ -619,7 +785,6 @@ int ahx_eval_q(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours, int32_t
   for (int32_t p = 0; p < PT; ++p)
     if ((rc = validate_tour(ctx, L, tours + static_cast<size_t>(p) * L, "ahx_eval_q")) != AHX_OK) return rc;
   AHX_CUDA(ctx, ctx->d_tours.reserve(static_cast<size_t>(PT) * L));
-  ctx->pop_P = ctx->pop_L = 0;
   AHX_CUDA(ctx, ctx->d_signs.reserve(static_cast<size_t>(P) * ctx->N));
   AHX_CUDA(ctx, ctx->d_scores.reserve(P));
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(PT) * L, cudaMemcpyHostToDevice, ctx->stream));
@@ -635,9 +800,9 @@ int ahx_pop_set(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours) {
   int rc = enter(ctx, true);
   if (rc != AHX_OK) return rc;
   if ((rc = validate_tours(ctx, P, L, tours, "ahx_pop_set")) != AHX_OK) return rc;
-  AHX_CUDA(ctx, ctx->d_tours.reserve(static_cast<size_t>(P) * L));
-  AHX_CUDA(ctx, ctx->d_scores.reserve(P));
-  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(P) * L, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, ctx->d_res_tours.reserve(static_cast<size_t>(P) * L));
+  AHX_CUDA(ctx, ctx->d_res_scores.reserve(P));
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_res_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(P) * L, cudaMemcpyHostToDevice, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->pop_P = P; ctx->pop_L = L;
   return AHX_OK;
@@ -651,8 +816,8 @@ int ahx_pop_eval_m(ahx_ctx *ctx, int32_t kind, int32_t repeat, float *elapsed_ms
   if (kind == 1 && (rc = ensure_dense(ctx)) != AHX_OK) return rc;
   AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
   for (int r = 0; r < repeat; ++r) {
-    rc = kind == 0 ? launch_eval_m_sparse(ctx, ctx->d_tours.p, nullptr, nullptr, ctx->pop_P, ctx->pop_L, ctx->d_scores.p, ctx->stream)
-                   : launch_eval_m_dense(ctx, ctx->d_tours.p, ctx->pop_P, ctx->pop_L, ctx->d_scores.p, ctx->stream);
+    rc = kind == 0 ? launch_eval_m_sparse(ctx, ctx->d_res_tours.p, nullptr, nullptr, ctx->pop_P, ctx->pop_L, ctx->d_res_scores.p, ctx->stream)
+                   : launch_eval_m_dense(ctx, ctx->d_res_tours.p, ctx->pop_P, ctx->pop_L, ctx->d_res_scores.p, ctx->stream);
     if (rc != AHX_OK) return rc;
   }
   AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
@@ -667,7 +832,7 @@ int ahx_pop_scores(ahx_ctx *ctx, double *out) {
   int rc = enter(ctx, true);
   if (rc != AHX_OK) return rc;
   if (ctx->pop_P <= 0 || !out) return fail(ctx, AHX_ERR_STATE, "ahx_pop_scores: no resident population");
-  AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * ctx->pop_P, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_res_scores.p, sizeof(double) * ctx->pop_P, cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AHX_OK;
 }

@@ -58,8 +58,10 @@ struct ahx_ctx {
   int64_t E = 0, H = 0;
   bool coo16 = false;
   ahx::DevBuf<long long> d_sizes;
-  ahx::DevBuf<uint2> d_coo16;
-  ahx::DevBuf<int4> d_coo32;
+  ahx::DevBuf<uint2> d_coo16, d_coo16o;   // sorted by (a,b) / bank-conflict-free order, padded
+  ahx::DevBuf<int4> d_coo32, d_coo32o;
+  int64_t E_pad = 0;                      // entries in the ordered table (multiple of 256)
+  bool x32_ok = false;                    // 2*sum(sizes) + 2*LIMIT + 2 < 2^32
   ahx::DevBuf<int32_t> d_pa, d_pb, d_slots, d_hist, d_M;
   bool dense_ready = false;
   ahx::DevBuf<int32_t> d_adj_ptr, d_adj_e;   // CSR: pairs touching each contig
@@ -68,7 +70,9 @@ struct ahx_ctx {
   std::vector<int8_t> h_strand;
 
   // ---- scratch
-  ahx::DevBuf<int32_t> d_tours;      // staging for ahx_eval_* / resident population
+  ahx::DevBuf<int32_t> d_tours;      // staging for ahx_eval_*
+  ahx::DevBuf<int32_t> d_res_tours;  // resident population (ahx_pop_*)
+  ahx::DevBuf<double> d_res_scores;
   ahx::DevBuf<uint16_t> d_tours16;
   ahx::DevBuf<double> d_scores;
   ahx::DevBuf<uint8_t> d_signs;
@@ -113,6 +117,8 @@ int launch_eval_q(ahx_ctx *ctx, const int32_t *d_tours, int shared_tour, const u
 int finish_checked(ahx_ctx *ctx, const char *who);
 int validate_tour(ahx_ctx *ctx, int32_t L, const int32_t *tour, const char *who);
 size_t eval_m_smem_bytes(int T, int32_t N, int32_t L);
+size_t eval_x32_smem_bytes(int T, bool coo16, int32_t N, int32_t L);
+bool use_x32(const ahx_ctx *ctx, int32_t L);
 }  // namespace ahx
 
 #define AHX_CUDA(ctx, call)                                              \

@@ -75,12 +75,18 @@ struct Coo16 {
     const uint2 v = __ldg(p + e);
     a = static_cast<int>(v.x & 0xffffu); b = static_cast<int>(v.x >> 16); n = static_cast<double>(v.y);
   }
+  __device__ static __forceinline__ void unpack(const Elem v, int &a, int &b, uint32_t &n) {
+    a = static_cast<int>(v.x & 0xffffu); b = static_cast<int>(v.x >> 16); n = v.y;
+  }
 };
 struct Coo32 {
   using Elem = int4;
   __device__ static __forceinline__ void get(const Elem *p, int e, int &a, int &b, double &n) {
     const int4 v = __ldg(p + e);
     a = v.x; b = v.y; n = static_cast<double>(v.z);
+  }
+  __device__ static __forceinline__ void unpack(const Elem v, int &a, int &b, uint32_t &n) {
+    a = v.x; b = v.y; n = static_cast<uint32_t>(v.z);
   }
 };
 
@@ -133,6 +139,129 @@ __device__ __forceinline__ void accumulate_pairs(const double *x, const typename
         const double d = fabs(xa[t] - xb[t]);
         if (d <= kLimit) acc[t] += n / d;
       }
+    }
+  }
+}
+
+// ---- Tour.Evaluate, 32-bit coordinate form -----------------------------------
+// X_c = 2*mid_c = 2*cumSum + size is an exact integer; when 2*sum(sizes) +
+// 2*LIMIT + 2 < 2^32 it fits a uint32 and
+//     dist = |X_a - X_b| / 2,   dist <= LIMIT  <=>  0 < |X_a - X_b| <= 2*LIMIT,
+//     nlinks / dist = (2*nlinks) / |X_a - X_b|     (scaling by 2 is exact in fp64)
+// so the window test runs on the integer pipe and only in-window pairs touch the
+// fp64 pipe.  Inactive contigs hold 0xFFFFFFFF: against an active contig the
+// difference exceeds 2*LIMIT, against each other it is 0, both fail the test
+// (d - 1 < 2*LIMIT, unsigned).  Element (c, t) of the T tours of a CTA lives at
+// X[c*T + t], so one 4*T-byte shared-memory load fetches contig c for all T tours.
+constexpr uint32_t kLimit2 = 20000000u;      // 2 * LIMIT
+constexpr uint32_t kInactiveX = 0xFFFFFFFFu;
+
+template <int T>
+__device__ __forceinline__ void scatter_x32(const int *tig, int L, const long long *__restrict__ sizes,
+                                            uint32_t *X, int t, long long *scan_scratch, int tid) {
+  const int per = (L + kBlock - 1) / kBlock;
+  const int beg = min(L, tid * per), end = min(L, beg + per);
+  long long local = 0;
+  for (int i = beg; i < end; ++i) local += __ldg(sizes + tig[i]);
+  long long cum = block_excl_scan(local, scan_scratch, tid);
+  for (int i = beg; i < end; ++i) {
+    const int c = tig[i];
+    const long long s = __ldg(sizes + c);
+    X[static_cast<size_t>(c) * T + t] = static_cast<uint32_t>(2 * cum + s);
+    cum += s;
+  }
+}
+
+template <int T> struct XVec;
+template <> struct XVec<1> { using type = uint32_t; };
+template <> struct XVec<2> { using type = uint2; };
+template <> struct XVec<4> { using type = uint4; };
+
+__device__ __forceinline__ void x_unpack(uint32_t v, uint32_t (&o)[1]) { o[0] = v; }
+__device__ __forceinline__ void x_unpack(uint2 v, uint32_t (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void x_unpack(uint4 v, uint32_t (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+
+// One stored pair (a, b, nlinks) against the T tours of this CTA.
+template <int T>
+__device__ __forceinline__ void pair_terms_x32(const uint32_t *X, int a, int b, uint32_t nlinks, double (&acc)[T]) {
+  using V = typename XVec<T>::type;
+  uint32_t xa[T], xb[T];
+  x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(a) * T), xa);
+  x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(b) * T), xb);
+  const double n2 = 2.0 * static_cast<double>(nlinks);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint32_t d = xa[t] > xb[t] ? xa[t] - xb[t] : xb[t] - xa[t];
+    if (d - 1u < kLimit2) acc[t] += n2 / static_cast<double>(d);   // evaluate.go:135-140
+  }
+}
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "AHX_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra AHX_DONE;\n"
+      "bra AHX_WAIT;\n"
+      "AHX_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// The pair table streamed through shared memory: kStages tiles of kTile entries,
+// filled by TMA bulk copies (one elected thread issues, an mbarrier per stage
+// signals arrival), consumed by all threads.  E_pad is a multiple of kBlock.
+constexpr int kTile = 1024;
+constexpr int kStages = 2;
+
+template <int T, typename Coo>
+__device__ __forceinline__ void stream_pairs_x32(const uint32_t *X, const typename Coo::Elem *__restrict__ coo, int E_pad,
+                                                 typename Coo::Elem *tiles, uint64_t *bars, double (&acc)[T], int tid) {
+  using Elem = typename Coo::Elem;
+  const int ntiles = (E_pad + kTile - 1) / kTile;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      if (s < ntiles) {
+        const int n = min(kTile, E_pad - s * kTile);
+        mbar_expect_tx(&bars[s], n * static_cast<uint32_t>(sizeof(Elem)));
+        bulk_copy_g2s(tiles + static_cast<size_t>(s) * kTile, coo + static_cast<size_t>(s) * kTile, n * static_cast<uint32_t>(sizeof(Elem)), &bars[s]);
+      }
+    }
+  }
+  for (int k = 0; k < ntiles; ++k) {
+    const int s = k % kStages;
+    mbar_wait(&bars[s], (k / kStages) & 1);
+    const Elem *tile = tiles + static_cast<size_t>(s) * kTile;
+    const int n = min(kTile, E_pad - k * kTile);
+#pragma unroll
+    for (int i = 0; i < kTile / kBlock; ++i) {
+      const int e = tid + i * kBlock;
+      if (e < n) {
+        int a, b; uint32_t nl;
+        Coo::unpack(tile[e], a, b, nl);
+        pair_terms_x32<T>(X, a, b, nl, acc);
+      }
+    }
+    __syncthreads();   // every thread is done with stage s before it is refilled
+    if (tid == 0 && k + kStages < ntiles) {
+      const int kn = k + kStages;
+      const int nn = min(kTile, E_pad - kn * kTile);
+      mbar_expect_tx(&bars[s], nn * static_cast<uint32_t>(sizeof(Elem)));
+      bulk_copy_g2s(tiles + static_cast<size_t>(s) * kTile, coo + static_cast<size_t>(kn) * kTile, nn * static_cast<uint32_t>(sizeof(Elem)), &bars[s]);
     }
   }
 }

@@ -180,7 +180,6 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   AHX_CUDA(ctx, ctx->d_S4.reserve(static_cast<size_t>(std::max(E, 1)) * 4)); AHX_CUDA(ctx, ctx->d_pairinfo.reserve(std::max(E, 1)));
   AHX_CUDA(ctx, ctx->d_trace.reserve(static_cast<size_t>(Lm) * 2 + 1)); AHX_CUDA(ctx, ctx->d_stepacc.reserve(Lm));
   AHX_CUDA(ctx, ctx->d_counts.reserve(2)); AHX_CUDA(ctx, ctx->d_signs.reserve(ctx->N)); AHX_CUDA(ctx, ctx->d_tours.reserve(Lm));
-  ctx->pop_P = ctx->pop_L = 0;
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_signs.p, signs, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
   if (L) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
   if (E > 0) {

@@ -365,7 +365,6 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_pop[i].reserve(PL)); AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); }
   AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1));
   AHX_CUDA(ctx, ctx->d_tours.reserve(L)); AHX_CUDA(ctx, ctx->d_scores.reserve(1));
-  ctx->pop_P = ctx->pop_L = 0;
   ctx->ga_active_set.assign(init_tour, init_tour + L);
   std::sort(ctx->ga_active_set.begin(), ctx->ga_active_set.end());
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, init_tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));

@@ -65,42 +65,57 @@ def work_per_tour(sizes, tables, tours, sample=128):
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock + throttle reasons DURING the timed region (NVML from a
+    thread; ctypes calls release the GIL so sampling continues while kernels run)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu):
-        self.gpu, self.p = gpu, None
+        import threading
+        self.gpu, self.samples, self.mask, self.max_mhz, self.err = gpu, [], 0, None, None
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical GPUs; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    try:
+                        self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    except Exception:
+                        pass
+                self.samples.append((float(sm), pw))
+                self._stop.wait(0.01)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.p = None
+        self._t.start()
 
     def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            self.p.kill(); out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        # samples taken while the GPU idles between phases pull the median down: keep the busy half
-        busy = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set(); self._t.join(timeout=5)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples: %s" % self.err]}
+        # the GPU idles between phases (host-side setup): keep the samples taken under load (upper half by power)
+        by_power = sorted(self.samples, key=lambda x: x[1])
+        busy = [s for s, _ in by_power[len(by_power) // 2:]]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit), "samples": len(self.samples)}
 
 
 def cpu_population_evals(ids, clm, tours, min_seconds, threads):
@@ -128,7 +143,7 @@ def run_reference(args, rank, world):
     threads = os.cpu_count() or 1
     from oracle_lib import OracleCLM
     orc = OracleCLM(clm, ids)
-    S = min(P, max(threads * 16, 512))          # bounded sample of the population per step
+    S = P                                       # the whole population per step (0.3-2 s of CPU work per step)
     tours = np.ascontiguousarray(make_tours(n, S, 1234), np.int64)
     for _ in range(max(1, args.warmup)):
         orc.population_evaluate(tours[: threads * 2], nthreads=threads)
@@ -154,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=["config2", "config3", "config5"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ga-gens", type=int, default=300)
+    ap.add_argument("--ga-gens", type=int, default=2000)
     ap.add_argument("--no-ga", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
     args = ap.parse_args()
@@ -202,6 +217,7 @@ def main():
     pin_t.array[:] = tours
     h2d, d2h = pin_t.nbytes, pin_o.nbytes
 
+    clocks = ClockSampler(local); clocks.start()
     eng.pop_set(tours)
     dfma_tflops, ddiv_g = eng.probe_fp64()
     l2_gbs = eng.probe_l2(64 << 20)
@@ -210,7 +226,6 @@ def main():
     for _ in range(max(3, args.warmup)):
         eng.eval_m(pin_t.array, out=pin_o.array)
 
-    clocks = ClockSampler(local); clocks.start()
     # ---- device-resident steps (value)
     barrier()
     lc0 = eng.launch_count()
@@ -230,7 +245,6 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    clk = clocks.stop()
     assert np.array_equal(scores_dev, pin_o.array), "resident and e2e paths disagree"
 
     value = world * P * args.steps / (dev_ms * 1e-3)
@@ -253,7 +267,7 @@ def main():
                       "parallelism": "independent sub-populations, one per GPU" if world > 1 else "single GPU"},
            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "call": "ahx_eval_m_u16" if use16 else "ahx_eval_m", "ms_per_step": e2e_s / args.steps * 1e3},
-           "gpu_launches": int(eval_launches), "clocks": clk, "roofline": roof,
+           "gpu_launches": int(eval_launches), "roofline": roof,
            "probes": {"dfma_tflops": dfma_tflops, "ddiv_add_gops": ddiv_g, "l2_read_GBs_64MB": l2_gbs}}
 
     # ---- dense (north_star literal) kernel, for the record
@@ -298,6 +312,7 @@ def main():
                      "evals_per_s_inside_ga": float(ev.item()) / ga_s if world == 1 else None, "best_score": best,
                      "model": "islands, all-gather of 2 elites every 50 generations over NCCL" if world > 1 else "single population"}
 
+    out["clocks"] = clocks.stop()
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1

@@ -67,10 +67,14 @@ def test_eval_m_population_fixture(fix, P):
     assert close(eng.eval_m(tours.astype(np.uint16)), want)
 
 
+@pytest.mark.parametrize("fp64", ["0", "1"])
 @pytest.mark.parametrize("T", ["1", "2", "4"])
-def test_eval_m_tours_per_cta(syn, T, monkeypatch):
+def test_eval_m_tours_per_cta(syn, T, fp64, monkeypatch):
+    """Both formulations of the contig-space kernel (32-bit coordinates + TMA-staged
+    pair table; fp64 coordinates fallback) at every tours-per-CTA setting."""
     eng, clm, orc = syn
     monkeypatch.setenv("AHX_EVAL_T", T)
+    monkeypatch.setenv("AHX_EVAL_FP64", fp64)
     rng = np.random.default_rng(int(T))
     tours = np.stack([rng.permutation(clm.N) for _ in range(203)]).astype(np.int32)
     tours[0] = np.arange(clm.N); tours[1] = np.arange(clm.N)[::-1]
@@ -110,6 +114,33 @@ def test_eval_m_errors(fix, built_lib):
     with pytest.raises(A.AhxError):
         e2.load_arrays([5, 0, 7], [0], [1], [3], [1], -np.ones((1, 8), np.int32), np.zeros((0, 12), np.int32))
     e2.close()
+
+
+def test_eval_m_giant_group_uses_fp64_coordinates(built_lib, tmp_path):
+    """sum(sizes) > 2^31: 2*mid no longer fits 32 bits, the fp64-coordinate kernel must run."""
+    import allhic_b200 as A
+    rng = np.random.default_rng(13)
+    n = 40
+    ids = tmp_path / "big.ids"; clmf = tmp_path / "big.clm"
+    sizes = rng.integers(1_000_000, 120_000_000, n)
+    sizes[:8] = rng.integers(1000, 200_000, 8)
+    assert sizes.sum() > 2 ** 31
+    ids.write_text("".join("c%d\t1\t%d\n" % (i, s) for i, s in enumerate(sizes)))
+    lines = []
+    for a in range(n):
+        for b in range(a + 1, n):
+            if rng.random() < 0.4:
+                d = rng.integers(1, 3_000_000, rng.integers(1, 6))
+                lines.append("c%d+ c%d-\t%d\t%s\n" % (a, b, len(d), " ".join(map(str, d))))
+    clmf.write_text("".join(lines))
+    clm = A.CLM(str(clmf), str(ids)); orc = O.OracleCLM(str(clmf), str(ids))
+    eng = A.Engine(0); eng.load(clm)
+    tours = np.stack([rng.permutation(n) for _ in range(33)]).astype(np.int32)
+    tours[:, :8] = np.sort(tours[:, :8], axis=1)
+    want = orc.population_evaluate(tours.astype(np.int64))
+    assert (want != 0).any()
+    assert close(eng.eval_m(tours), want) and close(eng.eval_m(tours, kind="dense"), want)
+    eng.close()
 
 
 # ---------------------------------------------------------------- CLM.EvaluateQ

@@ -105,48 +105,49 @@ eval_m_sparse_kernel(const IdxT *__restrict__ tours, const int *__restrict__ row
 //   quarter-warp hit 8 different 16-byte bank groups (see order_pairs()).
 // ---------------------------------------------------------------------------
 template <int T, typename Coo, typename IdxT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, T == 4 ? 3 : 4)
 eval_m_x32_kernel(const IdxT *__restrict__ tours, const int *__restrict__ rows, int P, int L, int N,
-                  const long long *__restrict__ sizes, const typename Coo::Elem *__restrict__ coo, int E_pad,
+                  const uint32_t *__restrict__ sizes32, const typename Coo::Elem *__restrict__ coo, int E_pad,
                   double *__restrict__ out, int *__restrict__ errflag) {
   using Elem = typename Coo::Elem;
   extern __shared__ __align__(128) unsigned char smem_x32[];
-  __shared__ long long scan_scratch[kWarps];
+  __shared__ long long scan_scratch[kWarps * T];
   __shared__ double red_scratch[kWarps];
-  __shared__ __align__(8) uint64_t bars[kStages];
+  __shared__ __align__(8) uint64_t bars[2 * kStages];
   Elem *tiles = reinterpret_cast<Elem *>(smem_x32);
-  uint32_t *X = reinterpret_cast<uint32_t *>(smem_x32 + sizeof(Elem) * kStages * kTile);
-  int *tig = reinterpret_cast<int *>(X + static_cast<size_t>(N) * T);
+  Elem *queues = tiles + kStages * kTile;
+  uint32_t *X = reinterpret_cast<uint32_t *>(queues + kWarps * kQueue);
+  uint32_t *S = X + static_cast<size_t>(N) * T;
   const int tid = threadIdx.x;
   const int p0 = blockIdx.x * T;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[kStages + s], kWarps); }
     mbar_init_fence();
+    prefetch_pairs<Elem>(coo, E_pad, tiles, bars);
   }
-  for (int i = tid; i < N * T; i += kBlock) X[i] = kInactiveX;
+  {
+    uint4 *X4 = reinterpret_cast<uint4 *>(X);
+    const uint4 inact = make_uint4(kInactiveX, kInactiveX, kInactiveX, kInactiveX);
+    for (int i = tid; i < (N * T) / 4; i += kBlock) X4[i] = inact;
+    for (int i = (N * T) / 4 * 4 + tid; i < N * T; i += kBlock) X[i] = kInactiveX;
+  }
+  for (int i = tid; i < N; i += kBlock) S[i] = __ldg(sizes32 + i);
+  const IdxT *tour_ptr[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int p = p0 + t;
+    tour_ptr[t] = p < P ? tours + static_cast<size_t>(rows ? rows[p] : p) * L : nullptr;
+  }
   __syncthreads();
+  scatter_tours_x32<T, IdxT>(tour_ptr, L, N, S, X, scan_scratch, errflag, tid);
+  __syncthreads();
+  PairSink<T, Coo> sink;
+  sink.init(queues + (tid >> 5) * kQueue, X, tid & 31);
+  stream_pairs_x32<T, Coo>(coo, E_pad, tiles, bars, sink, tid);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    if (p0 + t >= P) break;
-    const int row = rows ? rows[p0 + t] : p0 + t;
-    const IdxT *src = tours + static_cast<size_t>(row) * L;
-    for (int i = tid; i < L; i += kBlock) {
-      int v = static_cast<int>(src[i]);
-      if (static_cast<unsigned>(v) >= static_cast<unsigned>(N)) { *errflag = 1; v = 0; }
-      tig[i] = v;
-    }
-    __syncthreads();
-    scatter_x32<T>(tig, L, sizes, X, t, scan_scratch, tid);
-    __syncthreads();
-  }
-  double acc[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) acc[t] = 0.0;
-  stream_pairs_x32<T, Coo>(X, coo, E_pad, tiles, bars, acc, tid);
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const double s = block_sum(acc[t], red_scratch, tid);
+    const double s = block_sum(sink.acc[t], red_scratch, tid);
     if (tid == 0 && p0 + t < P) {
       const int row = rows ? rows[p0 + t] : p0 + t;
       out[row] = 0.0 - s;
@@ -369,8 +370,9 @@ static cudaError_t launch_sparse_c(ahx_ctx *ctx, const IdxT *tours, const int32_
 }
 
 size_t eval_x32_smem_bytes(int T, bool coo16, int32_t N, int32_t L) {
-  return (coo16 ? sizeof(uint2) : sizeof(int4)) * static_cast<size_t>(kStages) * kTile + sizeof(uint32_t) * static_cast<size_t>(N) * T +
-         sizeof(int) * static_cast<size_t>(L);
+  (void)L;
+  return (coo16 ? sizeof(uint2) : sizeof(int4)) * (static_cast<size_t>(kStages) * kTile + kWarps * kQueue) +
+         sizeof(uint32_t) * static_cast<size_t>(N) * (T + 1);
 }
 
 static int pick_T32(const ahx_ctx *ctx, int32_t P, int32_t L) {
@@ -382,7 +384,7 @@ static int pick_T32(const ahx_ctx *ctx, int32_t P, int32_t L) {
   // several tours per CTA amortise the pair-table stream and make each shared-memory
   // gather serve T tours; keep >= 3 CTAs per SM and enough CTAs for two waves
   for (int t : {4, 2})
-    if (fits(t, 3) && (P + t - 1) / t >= 2 * ctx->sm_count) return t;
+    if (fits(t, 3) && (P + t - 1) / t >= ctx->sm_count) return t;
   return 1;
 }
 
@@ -395,7 +397,7 @@ static cudaError_t launch_x32_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *
   const typename Coo::Elem *coo;
   if constexpr (sizeof(typename Coo::Elem) == 8) coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo16o.p);
   else coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo32o.p);
-  kern<<<(P + T - 1) / T, kBlock, smem, s>>>(tours, rows, P, L, ctx->N, ctx->d_sizes.p, coo, static_cast<int>(ctx->E_pad), out, ctx->d_errflag.p);
+  kern<<<(P + T - 1) / T, kBlock, smem, s>>>(tours, rows, P, L, ctx->N, ctx->d_sizes32.p, coo, static_cast<int>(ctx->E_pad), out, ctx->d_errflag.p);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -653,7 +655,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  ctx->d_sizes.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); ctx->d_pa.release(); ctx->d_pb.release();
+  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
   ctx->d_tours.release(); ctx->d_res_tours.release(); ctx->d_res_scores.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
   ctx->d_flush.release(); ctx->d_errflag.release();
@@ -723,6 +725,11 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
     long long total = 0;
     for (int32_t i = 0; i < N; ++i) total += sizes[i];
     ctx->x32_ok = 2 * total + 2LL * AHX_LIMIT + 2 < 0xFFFFFFFFLL;
+    std::vector<uint32_t> s32(N);
+    for (int32_t i = 0; i < N; ++i) s32[i] = static_cast<uint32_t>(std::min<int64_t>(sizes[i], 0xFFFFFFFFLL));
+    AHX_CUDA(ctx, ctx->d_sizes32.reserve(N));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes32.p, s32.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+    AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<int64_t> ord;
     order_pairs(E, pa, pb, &ord);
     ctx->E_pad = static_cast<int64_t>(ord.size());

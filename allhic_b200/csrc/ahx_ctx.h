@@ -58,6 +58,7 @@ struct ahx_ctx {
   int64_t E = 0, H = 0;
   bool coo16 = false;
   ahx::DevBuf<long long> d_sizes;
+  ahx::DevBuf<uint32_t> d_sizes32;       // sizes as uint32 for the x32 kernels (valid when x32_ok)
   ahx::DevBuf<uint2> d_coo16, d_coo16o;   // sorted by (a,b) / bank-conflict-free order, padded
   ahx::DevBuf<int4> d_coo32, d_coo32o;
   int64_t E_pad = 0;                      // entries in the ordered table (multiple of 256)

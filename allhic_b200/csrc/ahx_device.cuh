@@ -156,22 +156,6 @@ __device__ __forceinline__ void accumulate_pairs(const double *x, const typename
 constexpr uint32_t kLimit2 = 20000000u;      // 2 * LIMIT
 constexpr uint32_t kInactiveX = 0xFFFFFFFFu;
 
-template <int T>
-__device__ __forceinline__ void scatter_x32(const int *tig, int L, const long long *__restrict__ sizes,
-                                            uint32_t *X, int t, long long *scan_scratch, int tid) {
-  const int per = (L + kBlock - 1) / kBlock;
-  const int beg = min(L, tid * per), end = min(L, beg + per);
-  long long local = 0;
-  for (int i = beg; i < end; ++i) local += __ldg(sizes + tig[i]);
-  long long cum = block_excl_scan(local, scan_scratch, tid);
-  for (int i = beg; i < end; ++i) {
-    const int c = tig[i];
-    const long long s = __ldg(sizes + c);
-    X[static_cast<size_t>(c) * T + t] = static_cast<uint32_t>(2 * cum + s);
-    cum += s;
-  }
-}
-
 template <int T> struct XVec;
 template <> struct XVec<1> { using type = uint32_t; };
 template <> struct XVec<2> { using type = uint2; };
@@ -181,20 +165,203 @@ __device__ __forceinline__ void x_unpack(uint32_t v, uint32_t (&o)[1]) { o[0] = 
 __device__ __forceinline__ void x_unpack(uint2 v, uint32_t (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 __device__ __forceinline__ void x_unpack(uint4 v, uint32_t (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 
-// One stored pair (a, b, nlinks) against the T tours of this CTA.
+// Exclusive block scan of T values per thread with one pair of barriers.
+// scratch: kWarps * T long longs.
 template <int T>
-__device__ __forceinline__ void pair_terms_x32(const uint32_t *X, int a, int b, uint32_t nlinks, double (&acc)[T]) {
-  using V = typename XVec<T>::type;
-  uint32_t xa[T], xb[T];
-  x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(a) * T), xa);
-  x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(b) * T), xb);
-  const double n2 = 2.0 * static_cast<double>(nlinks);
+__device__ __forceinline__ void block_excl_scan_vec(long long (&v)[T], long long *scratch, int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
+  long long incl[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    const uint32_t d = xa[t] > xb[t] ? xa[t] - xb[t] : xb[t] - xa[t];
-    if (d - 1u < kLimit2) acc[t] += n2 / static_cast<double>(d);   // evaluate.go:135-140
+    incl[t] = warp_incl_scan(v[t], lane);
+    if (lane == 31) scratch[wid * T + t] = incl[t];
   }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    long long base = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) base += (w < wid) ? scratch[w * T + t] : 0;
+    v[t] = base + incl[t] - v[t];
+  }
+  __syncthreads();
 }
+
+// Prologue of the x32 kernels: coordinates of up to T tours scattered to contig
+// space in one pass.  tour_ptr[t] = row of tour t (nullptr: slot unused);
+// S = contig sizes staged in shared memory (uint32: x32 mode implies sizes < 2^31).
+// Thread `tid` owns the contiguous chunk [tid*per, tid*per+per) of every tour and
+// keeps it in registers between the two passes (kChunk elements per round), so the
+// global loads of a round are independent and issued back to back.
+constexpr int kChunk = 8;
+
+template <int T, typename IdxT>
+__device__ __forceinline__ void scatter_tours_x32(const IdxT *const (&tour_ptr)[T], int L, int N, const uint32_t *S, uint32_t *X,
+                                                  long long *scan_scratch, int *errflag, int tid) {
+  const int per = (L + kBlock - 1) / kBlock;
+  const int beg = min(L, tid * per), end = min(L, beg + per);
+  bool bad = false;
+  if (per <= kChunk) {
+    unsigned c[T][kChunk];
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i)
+        c[t][i] = (tour_ptr[t] && beg + i < end) ? static_cast<unsigned>(tour_ptr[t][beg + i]) : 0xFFFFFFFFu;
+    long long cum[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      long long local = 0;
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        const bool live = tour_ptr[t] && beg + i < end;
+        if (live && c[t][i] >= static_cast<unsigned>(N)) { bad = true; c[t][i] = 0xFFFFFFFFu; }
+        if (c[t][i] != 0xFFFFFFFFu) local += S[c[t][i]];
+      }
+      cum[t] = local;
+    }
+    block_excl_scan_vec<T>(cum, scan_scratch, tid);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      uint32_t c2 = static_cast<uint32_t>(2 * cum[t]);
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        if (c[t][i] == 0xFFFFFFFFu) continue;
+        const uint32_t sz = S[c[t][i]];
+        X[static_cast<size_t>(c[t][i]) * T + t] = c2 + sz;   // 2*cum + size
+        c2 += 2u * sz;
+      }
+    }
+  } else {
+    long long cum[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      long long local = 0;
+      if (tour_ptr[t]) {
+        for (int i = beg; i < end; ++i) {
+          const unsigned c = static_cast<unsigned>(tour_ptr[t][i]);
+          if (c >= static_cast<unsigned>(N)) bad = true;
+          else local += S[c];
+        }
+      }
+      cum[t] = local;
+    }
+    block_excl_scan_vec<T>(cum, scan_scratch, tid);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (!tour_ptr[t]) continue;
+      uint32_t c2 = static_cast<uint32_t>(2 * cum[t]);
+      for (int i = beg; i < end; ++i) {
+        const unsigned c = static_cast<unsigned>(tour_ptr[t][i]);
+        if (c >= static_cast<unsigned>(N)) continue;
+        const uint32_t sz = S[c];
+        X[static_cast<size_t>(c) * T + t] = c2 + sz;
+        c2 += 2u * sz;
+      }
+    }
+  }
+  if (bad) *errflag = 1;   // reported by the host wrapper
+}
+
+// Two-stage evaluation of the pair stream.  A random tour keeps only ~LIMIT/G
+// of the stored pairs inside the window, and a divide issued for 3 live lanes
+// costs as much as one issued for 32, so the fp64 work is separated from the
+// window test:
+//   filter  (integer pipe) every lane tests its pair against the T tours of the
+//           CTA; pairs that are inside the window of at least one tour ("hot")
+//           are compacted into a per-warp queue in shared memory (ballot/popc);
+//   drain   (fp64 pipe) whenever the queue holds >= 32 pairs the warp pops 32
+//           and every lane evaluates its pair for all T tours, branch-free, as T
+//           independent divide chains.
+// Which lane sums which term depends on the data of the T tours sharing the CTA
+// but never on scheduling: the result is a deterministic function of (tours,
+// batch shape), bit-reproducible run to run; the last bits of one tour's score
+// may differ between batch shapes (different CTA mates), far inside 1e-12.
+// Exact uint32 -> double without the (quarter-rate) I2F conversion: 2^52 + v is
+// exactly representable, subtracting 2^52 leaves v.
+__device__ __forceinline__ double u32_to_double(uint32_t v) {
+  return __hiloint2double(0x43300000, static_cast<int>(v)) - 4503599627370496.0;
+}
+// n / d for 0 <= n < 2^34 and 1 <= d <= 2^32 (normal, finite operands): MUFU.RCP64H
+// seed (~23 bits), two Newton steps, quotient, one Markstein correction.  The
+// result is the correctly rounded quotient except for rare half-ulp ties of the
+// uncorrected estimate, i.e. <= 1 ulp from IEEE division -- per-term error
+// ~1e-16, four orders below the 1e-12 parity tolerance -- at a third of the
+// instructions of the compiler's guarded division sequence.
+__device__ __forceinline__ double div_pos(double n, double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  const double q = n * r;
+  return fma(fma(-d, q, n), r, q);
+}
+
+constexpr int kQueue = 64;
+
+template <int T, typename Coo>
+struct PairSink {
+  using Elem = typename Coo::Elem;
+  using V = typename XVec<T>::type;
+  Elem *q;             // this warp's queue
+  const uint32_t *X;
+  int cnt;             // warp-uniform fill level
+  int lane;
+  double acc[T];
+  __device__ __forceinline__ void init(Elem *warp_q, const uint32_t *X_, int lane_) {
+    q = warp_q; X = X_; lane = lane_; cnt = 0;
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+  }
+  __device__ __forceinline__ void evaluate(const Elem c) {
+    int a, b; uint32_t nl;
+    Coo::unpack(c, a, b, nl);
+    uint32_t xa[T], xb[T];
+    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(a) * T), xa);
+    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(b) * T), xb);
+    const double n2 = 2.0 * u32_to_double(nl);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const uint32_t d = __usad(xa[t], xb[t], 0u);
+      const bool in = d - 1u < kLimit2;                          // 0 < d <= 2*LIMIT
+      const double term = div_pos(n2, u32_to_double(in ? d : 1u));   // nlinks / dist, evaluate.go:140
+      acc[t] += in ? term : 0.0;
+    }
+  }
+  // window test of one pair against the T tours (integer pipe, no warp-level ops)
+  __device__ __forceinline__ bool test(const Elem c) const {
+    int a, b; uint32_t nl;
+    Coo::unpack(c, a, b, nl);
+    uint32_t xa[T], xb[T];
+    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(a) * T), xa);
+    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(b) * T), xb);
+    uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+    for (int t = 0; t < T; ++t) m = min(m, __usad(xa[t], xb[t], 0u) - 1u);
+    return m < kLimit2;
+  }
+  // called by all 32 lanes of the warp, each with its own pair
+  __device__ __forceinline__ void enqueue(const Elem c, bool hot) {
+    const unsigned bal = __ballot_sync(0xffffffffu, hot);
+    if (bal) {
+      if (hot) q[cnt + __popc(bal & ((1u << lane) - 1u))] = c;
+      cnt += __popc(bal);
+      if (cnt >= 32) {
+        __syncwarp();
+        cnt -= 32;
+        evaluate(q[cnt + lane]);
+        __syncwarp();
+      }
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    __syncwarp();
+    if (lane < cnt) evaluate(q[lane]);
+    cnt = 0;
+  }
+};
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -224,46 +391,66 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // The pair table streamed through shared memory: kStages tiles of kTile entries,
 // filled by TMA bulk copies (one elected thread issues, an mbarrier per stage
 // signals arrival), consumed by all threads.  E_pad is a multiple of kBlock.
-constexpr int kTile = 1024;
-constexpr int kStages = 2;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-template <int T, typename Coo>
-__device__ __forceinline__ void stream_pairs_x32(const uint32_t *X, const typename Coo::Elem *__restrict__ coo, int E_pad,
-                                                 typename Coo::Elem *tiles, uint64_t *bars, double (&acc)[T], int tid) {
-  using Elem = typename Coo::Elem;
+// The pair table streamed through shared memory as a kStages-deep ring of
+// kTile-entry tiles: full[s] is completed by the TMA bulk copy, empty[s] by one
+// arrival per warp once the warp is done with the tile.  Lane 0 of warp 0 is the
+// producer; no block-wide barrier inside the loop.  E_pad is a multiple of
+// kBlock so every warp runs the same trip counts.
+constexpr int kTile = 512;
+constexpr int kStages = 4;
+
+template <typename Elem>
+__device__ __forceinline__ void issue_tile(const Elem *__restrict__ coo, int E_pad, int k, Elem *tiles, uint64_t *full) {
+  const int s = k % kStages;
+  const uint32_t bytes = static_cast<uint32_t>(min(kTile, E_pad - k * kTile)) * static_cast<uint32_t>(sizeof(Elem));
+  mbar_expect_tx(&full[s], bytes);
+  bulk_copy_g2s(tiles + static_cast<size_t>(s) * kTile, coo + static_cast<size_t>(k) * kTile, bytes, &full[s]);
+}
+
+// Called by thread 0 right after the barriers are initialised: the first tiles
+// stream in while the CTA is still scattering its tours.
+template <typename Elem>
+__device__ __forceinline__ void prefetch_pairs(const Elem *__restrict__ coo, int E_pad, Elem *tiles, uint64_t *bars) {
   const int ntiles = (E_pad + kTile - 1) / kTile;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      if (s < ntiles) {
-        const int n = min(kTile, E_pad - s * kTile);
-        mbar_expect_tx(&bars[s], n * static_cast<uint32_t>(sizeof(Elem)));
-        bulk_copy_g2s(tiles + static_cast<size_t>(s) * kTile, coo + static_cast<size_t>(s) * kTile, n * static_cast<uint32_t>(sizeof(Elem)), &bars[s]);
-      }
-    }
-  }
+  for (int k = 0; k < kStages && k < ntiles; ++k) issue_tile<Elem>(coo, E_pad, k, tiles, bars);
+}
+
+// bars: full[kStages] then empty[kStages]; initialised by the caller (full: 1 arrival, empty: kWarps).
+template <int T, typename Coo>
+__device__ __forceinline__ void stream_pairs_x32(const typename Coo::Elem *__restrict__ coo, int E_pad,
+                                                 typename Coo::Elem *tiles, uint64_t *bars, PairSink<T, Coo> &sink, int tid) {
+  using Elem = typename Coo::Elem;
+  uint64_t *full = bars, *empty = bars + kStages;
+  const int ntiles = (E_pad + kTile - 1) / kTile;
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % kStages;
-    mbar_wait(&bars[s], (k / kStages) & 1);
+    const uint32_t parity = (k / kStages) & 1;
+    mbar_wait(&full[s], parity);
     const Elem *tile = tiles + static_cast<size_t>(s) * kTile;
     const int n = min(kTile, E_pad - k * kTile);
+    // loads and window tests of the whole tile slice first (independent, pipelined),
+    // then the warp-synchronous compaction
+    constexpr int U = kTile / kBlock;
+    Elem c[U]; bool hot[U];
 #pragma unroll
-    for (int i = 0; i < kTile / kBlock; ++i) {
-      const int e = tid + i * kBlock;
-      if (e < n) {
-        int a, b; uint32_t nl;
-        Coo::unpack(tile[e], a, b, nl);
-        pair_terms_x32<T>(X, a, b, nl, acc);
-      }
-    }
-    __syncthreads();   // every thread is done with stage s before it is refilled
+    for (int i = 0; i < U; ++i) c[i] = tile[min(tid + i * kBlock, kTile - 1)];
+#pragma unroll
+    for (int i = 0; i < U; ++i) hot[i] = (tid + i * kBlock < n) && sink.test(c[i]);
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      if (i * kBlock < n) sink.enqueue(c[i], hot[i]);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
     if (tid == 0 && k + kStages < ntiles) {
-      const int kn = k + kStages;
-      const int nn = min(kTile, E_pad - kn * kTile);
-      mbar_expect_tx(&bars[s], nn * static_cast<uint32_t>(sizeof(Elem)));
-      bulk_copy_g2s(tiles + static_cast<size_t>(s) * kTile, coo + static_cast<size_t>(kn) * kTile, nn * static_cast<uint32_t>(sizeof(Elem)), &bars[s]);
+      mbar_wait(&empty[s], parity);          // all warps are done with stage s
+      issue_tile<Elem>(coo, E_pad, k + kStages, tiles, full);
     }
   }
+  sink.flush();
 }
 
 // ---- Philox4x32-10 (counter-based RNG, Salmon et al. SC'11) -------------------

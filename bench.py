@@ -245,7 +245,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    assert np.array_equal(scores_dev, pin_o.array), "resident and e2e paths disagree"
+    assert np.allclose(scores_dev, pin_o.array, rtol=1e-13, atol=0), "resident and e2e paths disagree"
 
     value = world * P * args.steps / (dev_ms * 1e-3)
     e2e_v = world * P * args.steps / e2e_s

@@ -326,7 +326,7 @@ def test_config3_size_properties(built_lib):
     s = eng.eval_m(tours)
     assert close(eng.eval_m(tours[:512], kind="dense"), s[:512])
     assert close(eng.eval_m(tours[:, ::-1].copy()), s, 1e-13)        # |x_a - x_b| is reversal invariant
-    assert (eng.eval_m(tours.astype(np.uint16)) == s).all()
+    assert close(eng.eval_m(tours.astype(np.uint16)), s, 1e-13)     # other batch shape: last bits may differ
     orc = O.OracleCLM(clmf, ids)
     idx = rng.choice(P, 24, replace=False)
     assert close(s[idx], orc.population_evaluate(tours[idx].astype(np.int64), nthreads=8))

@@ -133,14 +133,14 @@ eval_m_x32_kernel(const IdxT *__restrict__ tours, const int *__restrict__ rows, 
     for (int i = (N * T) / 4 * 4 + tid; i < N * T; i += kBlock) X[i] = kInactiveX;
   }
   for (int i = tid; i < N; i += kBlock) S[i] = __ldg(sizes32 + i);
-  const IdxT *tour_ptr[T];
+  DirectTours<T, IdxT> src;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int p = p0 + t;
-    tour_ptr[t] = p < P ? tours + static_cast<size_t>(rows ? rows[p] : p) * L : nullptr;
+    src.ptr[t] = p < P ? tours + static_cast<size_t>(rows ? rows[p] : p) * L : nullptr;
   }
   __syncthreads();
-  scatter_tours_x32<T, IdxT>(tour_ptr, L, N, S, X, scan_scratch, errflag, tid);
+  scatter_tours_x32<T>(src, L, N, S, X, scan_scratch, errflag, tid);
   __syncthreads();
   PairSink<T, Coo> sink;
   sink.init(queues + (tid >> 5) * kQueue, X, tid & 31);
@@ -661,7 +661,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   ctx->d_flush.release(); ctx->d_errflag.release();
   for (int i = 0; i < 2; ++i) { ctx->d_pop[i].release(); ctx->d_fit[i].release(); }
   ctx->d_hof.release(); ctx->d_sel_idx.release(); ctx->d_sel_tours.release(); ctx->d_sel_fit.release(); ctx->d_taken.release();
-  ctx->d_state.release(); ctx->d_pos.release(); ctx->d_cum.release(); ctx->d_S4.release(); ctx->d_trace.release();
+  ctx->d_state.release(); ctx->d_plan.release(); ctx->d_pos.release(); ctx->d_cum.release(); ctx->d_S4.release(); ctx->d_trace.release();
   ctx->d_pairinfo.release(); ctx->d_stepacc.release(); ctx->d_counts.release();
   for (auto ev : ctx->chunk_ev) cudaEventDestroy(ev);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);

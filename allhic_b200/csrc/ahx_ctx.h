@@ -92,6 +92,9 @@ struct ahx_ctx {
   ahx::DevBuf<double> d_sel_fit;
   ahx::DevBuf<uint8_t> d_taken;
   ahx::DevBuf<ahx::GaState> d_state;
+  ahx::DevBuf<int32_t> d_plan;         // per-offspring parent/info/p/q, mutated list, count
+  bool ga_x32 = false;
+  int ga_T = 1;
   std::vector<int32_t> ga_active_set;  // sorted contig ids of the initial tour
   double ga_ms = 0.0;
 

@@ -195,8 +195,19 @@ __device__ __forceinline__ void block_excl_scan_vec(long long (&v)[T], long long
 // global loads of a round are independent and issued back to back.
 constexpr int kChunk = 8;
 
+// Source of tour elements for the prologue: get(t, i) = contig at position i of
+// tour slot t (only called when live(t)); put(t, i, c) lets the GA write the
+// offspring row while it is being read.
 template <int T, typename IdxT>
-__device__ __forceinline__ void scatter_tours_x32(const IdxT *const (&tour_ptr)[T], int L, int N, const uint32_t *S, uint32_t *X,
+struct DirectTours {
+  const IdxT *ptr[T];
+  __device__ __forceinline__ bool live(int t) const { return ptr[t] != nullptr; }
+  __device__ __forceinline__ unsigned get(int t, int i) const { return static_cast<unsigned>(ptr[t][i]); }
+  __device__ __forceinline__ void put(int, int, unsigned) const {}
+};
+
+template <int T, typename Src>
+__device__ __forceinline__ void scatter_tours_x32(const Src &src, int L, int N, const uint32_t *S, uint32_t *X,
                                                   long long *scan_scratch, int *errflag, int tid) {
   const int per = (L + kBlock - 1) / kBlock;
   const int beg = min(L, tid * per), end = min(L, beg + per);
@@ -207,14 +218,15 @@ __device__ __forceinline__ void scatter_tours_x32(const IdxT *const (&tour_ptr)[
     for (int t = 0; t < T; ++t)
 #pragma unroll
       for (int i = 0; i < kChunk; ++i)
-        c[t][i] = (tour_ptr[t] && beg + i < end) ? static_cast<unsigned>(tour_ptr[t][beg + i]) : 0xFFFFFFFFu;
+        c[t][i] = (src.live(t) && beg + i < end) ? src.get(t, beg + i) : 0xFFFFFFFFu;
     long long cum[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       long long local = 0;
 #pragma unroll
       for (int i = 0; i < kChunk; ++i) {
-        const bool live = tour_ptr[t] && beg + i < end;
+        const bool live = src.live(t) && beg + i < end;
+        if (live) src.put(t, beg + i, c[t][i]);
         if (live && c[t][i] >= static_cast<unsigned>(N)) { bad = true; c[t][i] = 0xFFFFFFFFu; }
         if (c[t][i] != 0xFFFFFFFFu) local += S[c[t][i]];
       }
@@ -237,9 +249,10 @@ __device__ __forceinline__ void scatter_tours_x32(const IdxT *const (&tour_ptr)[
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       long long local = 0;
-      if (tour_ptr[t]) {
+      if (src.live(t)) {
         for (int i = beg; i < end; ++i) {
-          const unsigned c = static_cast<unsigned>(tour_ptr[t][i]);
+          const unsigned c = src.get(t, i);
+          src.put(t, i, c);
           if (c >= static_cast<unsigned>(N)) bad = true;
           else local += S[c];
         }
@@ -249,10 +262,10 @@ __device__ __forceinline__ void scatter_tours_x32(const IdxT *const (&tour_ptr)[
     block_excl_scan_vec<T>(cum, scan_scratch, tid);
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      if (!tour_ptr[t]) continue;
+      if (!src.live(t)) continue;
       uint32_t c2 = static_cast<uint32_t>(2 * cum[t]);
       for (int i = beg; i < end; ++i) {
-        const unsigned c = static_cast<unsigned>(tour_ptr[t][i]);
+        const unsigned c = src.get(t, i);
         if (c >= static_cast<unsigned>(N)) continue;
         const uint32_t sz = S[c];
         X[static_cast<size_t>(c) * T + t] = c2 + sz;

@@ -190,6 +190,201 @@ __global__ void __launch_bounds__(kBlock) ga_generation_kernel(GaDev g) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Two-kernel generation for the x32 evaluate path.
+//   ga_plan_kernel  (1 CTA)  tournaments + mutation plans for all P offspring, the
+//                   inherited fitness of clones, and the ORDERED list of mutated
+//                   offspring (block scan, so the grouping of tours into evaluate
+//                   CTAs -- and with it every bit of every score -- is a pure
+//                   function of the seed, never of scheduling)
+//   ga_apply_kernel CTAs [0, ceil(P/T)): T mutated offspring each -- clone+mutate
+//                   straight into the evaluate prologue, write the row, score it;
+//                   remaining CTAs copy the unmutated clones; the last CTA to
+//                   finish updates the hall of fame and the generation state.
+// ---------------------------------------------------------------------------
+struct GaPlan {
+  int *parent;    // [P]
+  int *info;      // [P] op | dir << 8 | mutated << 16   (op 0xff = identity)
+  int *p, *q;     // [P]
+  int *mlist;     // [P] mutated offspring, ascending
+  int *nmut;      // [1]
+};
+
+__global__ void __launch_bounds__(256) ga_plan_kernel(GaDev g, GaPlan pl, unsigned int *plan_ticket) {
+  __shared__ int warp_tot[8];
+  __shared__ int s_last;
+  GaState *st = g.st;
+  if (*reinterpret_cast<volatile int *>(&st->stop)) return;
+  const long long gen = *reinterpret_cast<volatile long long *>(&st->gen);
+  const int cur = static_cast<int>(gen & 1);
+  const double *fitc = g.fit[cur]; double *fitn = g.fit[cur ^ 1];
+  const Philox ph{g.key0, g.key1};
+  const uint32_t glo = static_cast<uint32_t>(gen), ghi = static_cast<uint32_t>(gen >> 32);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // one offspring per thread, all CTAs in parallel
+  const int o = blockIdx.x * blockDim.x + tid;
+  if (o < g.P) {
+    const int parent = tournament_pair(fitc, g.P, g.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
+    const MutPlan mp = plan_mutation(ph, glo, ghi, static_cast<uint32_t>(o), g.mut_prob, g.L);
+    pl.parent[o] = parent;
+    pl.info[o] = (mp.op & 0xff) | (mp.dir << 8) | (mp.mutated << 16);
+    pl.p[o] = mp.p; pl.q[o] = mp.q;
+    if (!mp.mutated) fitn[o] = fitc[parent];
+  }
+  // the last CTA to finish builds the ordered list of mutated offspring
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(plan_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int per = (g.P + 255) / 256;
+  const int beg = min(g.P, tid * per), end = min(g.P, beg + per);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) cnt += (__ldcg(pl.info + i) >> 16) & 1;
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += n; }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < wid; ++w) base += warp_tot[w];
+  int pos = base + incl - cnt;
+  for (int i = beg; i < end; ++i)
+    if ((__ldcg(pl.info + i) >> 16) & 1) pl.mlist[pos++] = i;
+  if (tid == 255) { *pl.nmut = base + incl; *plan_ticket = 0; }
+}
+
+template <int T>
+struct GaTours {
+  const int *popc; int *popn;
+  int L;
+  int o[T], parent[T], op[T], p[T], q[T], dir[T];
+  __device__ __forceinline__ bool live(int t) const { return o[t] >= 0; }
+  __device__ __forceinline__ unsigned get(int t, int i) const {
+    return static_cast<unsigned>(popc[static_cast<size_t>(parent[t]) * L + mut_source(op[t], p[t], q[t], dir[t], L, i)]);
+  }
+  __device__ __forceinline__ void put(int t, int i, unsigned c) const { popn[static_cast<size_t>(o[t]) * L + i] = static_cast<int>(c); }
+};
+
+template <int T, typename Coo>
+__global__ void __launch_bounds__(kBlock, T == 4 ? 3 : 4)
+ga_apply_kernel(GaDev g, GaPlan pl, int n_eval_ctas, const uint32_t *__restrict__ sizes32, int E_pad, int *__restrict__ errflag) {
+  using Elem = typename Coo::Elem;
+  extern __shared__ __align__(128) unsigned char smem_ga[];
+  __shared__ long long scan_scratch[kWarps * T];
+  __shared__ double red_scratch[kWarps];
+  __shared__ int red_idx[kWarps];
+  __shared__ __align__(8) uint64_t bars[2 * kStages];
+  __shared__ int s_flag, s_best;
+  __shared__ double s_bestfit;
+  const int tid = threadIdx.x;
+  GaState *st = g.st;
+  if (*reinterpret_cast<volatile int *>(&st->stop)) return;
+  const long long gen = *reinterpret_cast<volatile long long *>(&st->gen);
+  const int cur = static_cast<int>(gen & 1);
+  const int *popc = g.pop[cur]; int *popn = g.pop[cur ^ 1];
+  double *fitn = g.fit[cur ^ 1];
+  const int nmut = *pl.nmut;
+  if (static_cast<int>(blockIdx.x) < n_eval_ctas) {
+    const int base = blockIdx.x * T;
+    if (base < nmut) {
+      Elem *tiles = reinterpret_cast<Elem *>(smem_ga);
+      Elem *queues = tiles + kStages * kTile;
+      uint32_t *X = reinterpret_cast<uint32_t *>(queues + kWarps * kQueue);
+      uint32_t *S = X + static_cast<size_t>(g.N) * T;
+      const Elem *coo = reinterpret_cast<const Elem *>(g.coo);
+      if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[kStages + s], kWarps); }
+        mbar_init_fence();
+        prefetch_pairs<Elem>(coo, E_pad, tiles, bars);
+      }
+      for (int i = tid; i < g.N * T; i += kBlock) X[i] = kInactiveX;
+      for (int i = tid; i < g.N; i += kBlock) S[i] = __ldg(sizes32 + i);
+      GaTours<T> src;
+      src.popc = popc; src.popn = popn; src.L = g.L;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int o = base + t < nmut ? pl.mlist[base + t] : -1;
+        src.o[t] = o;
+        if (o >= 0) {
+          const int info = pl.info[o];
+          src.parent[t] = pl.parent[o]; src.op[t] = info & 0xff; src.dir[t] = (info >> 8) & 1; src.p[t] = pl.p[o]; src.q[t] = pl.q[o];
+        } else { src.parent[t] = 0; src.op[t] = 0xff; src.dir[t] = 0; src.p[t] = 0; src.q[t] = 0; }
+      }
+      __syncthreads();
+      scatter_tours_x32<T>(src, g.L, g.N, S, X, scan_scratch, errflag, tid);
+      __syncthreads();
+      PairSink<T, Coo> sink;
+      sink.init(queues + (tid >> 5) * kQueue, X, tid & 31);
+      stream_pairs_x32<T, Coo>(coo, E_pad, tiles, bars, sink, tid);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const double s = block_sum(sink.acc[t], red_scratch, tid);
+        if (tid == 0 && src.o[t] >= 0) fitn[src.o[t]] = 0.0 - s;
+      }
+    }
+  } else {
+    // clones: offspring row = parent row (eaopt Clone), fitness was inherited by the plan kernel
+    const int ncopy = gridDim.x - n_eval_ctas;
+    const bool vec = (g.L & 3) == 0;
+    for (int o = blockIdx.x - n_eval_ctas; o < g.P; o += ncopy) {
+      if ((pl.info[o] >> 16) & 1) continue;
+      const int *src = popc + static_cast<size_t>(pl.parent[o]) * g.L;
+      int *dst = popn + static_cast<size_t>(o) * g.L;
+      if (vec) {
+        const int4 *s4 = reinterpret_cast<const int4 *>(src); int4 *d4 = reinterpret_cast<int4 *>(dst);
+        for (int i = tid; i < g.L / 4; i += kBlock) d4[i] = s4[i];
+      } else {
+        for (int i = tid; i < g.L; i += kBlock) dst[i] = src[i];
+      }
+    }
+  }
+  // ---- last CTA done: hall of fame + bookkeeping (evaluate.go:287-306)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  double bf = __longlong_as_double(0x7ff0000000000000LL);
+  int bi = 0x7fffffff;
+  for (int i = tid; i < g.P; i += kBlock) {
+    const double f = __ldcg(fitn + i);
+    if (f < bf) { bf = f; bi = i; }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double of = __shfl_down_sync(0xffffffffu, bf, d);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+    if (of < bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+  }
+  if ((tid & 31) == 0) { red_scratch[tid >> 5] = bf; red_idx[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kWarps; ++w)
+      if (red_scratch[w] < bf || (red_scratch[w] == bf && red_idx[w] < bi)) { bf = red_scratch[w]; bi = red_idx[w]; }
+    s_best = bi; s_bestfit = bf;
+    s_flag = bf < st->hof_fit;
+  }
+  __syncthreads();
+  if (s_flag) {
+    const int *best_row = popn + static_cast<size_t>(s_best) * g.L;
+    for (int i = tid; i < g.L; i += kBlock) g.hof[i] = __ldcg(best_row + i);
+  }
+  if (tid == 0) {
+    const long long ngen_now = gen + 1;
+    if (s_flag) { st->hof_fit = s_bestfit; st->updated = ngen_now; }
+    st->best_idx = s_best;
+    st->ticket = 0;
+    st->evals += nmut;
+    if (ngen_now - st->updated > g.ngen || ngen_now >= g.max_gens) st->stop = 1;
+    __threadfence();
+    st->gen = ngen_now;
+  }
+}
+
 __global__ void ga_init_kernel(GaDev g, const int *__restrict__ init, const double *__restrict__ f0) {
   const size_t total = static_cast<size_t>(g.P) * g.L;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -299,7 +494,44 @@ static GaDev make_dev(ahx_ctx *ctx) {
   return g;
 }
 
+static int ga_T(const ahx_ctx *ctx) {
+  // tours per evaluate CTA: 4 when three CTAs fit an SM and a generation has enough mutants to fill the GPU
+  const double expect = ctx->ga_prm.npop * ctx->ga_prm.mut_prob;
+  for (int t : {4, 2})
+    if ((eval_x32_smem_bytes(t, ctx->coo16, ctx->N, ctx->ga_L) + 1536) * 3 <= ctx->smem_optin + 2048 && expect / t >= ctx->sm_count) return t;
+  return 1;
+}
+
+template <int T, typename Coo>
+static cudaError_t launch_apply(ahx_ctx *ctx, const GaDev &g, const GaPlan &pl, cudaStream_t s) {
+  auto kern = ga_apply_kernel<T, Coo>;
+  const size_t smem = eval_x32_smem_bytes(T, ctx->coo16, ctx->N, ctx->ga_L);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const int n_eval = (g.P + T - 1) / T;
+  const int n_copy = std::min(g.P, ctx->sm_count * 4);
+  kern<<<n_eval + n_copy, kBlock, smem, s>>>(g, pl, n_eval, ctx->d_sizes32.p, static_cast<int>(ctx->E_pad), ctx->d_errflag.p);
+  return cudaGetLastError();
+}
+
 static int launch_generation(ahx_ctx *ctx, const GaDev &g, cudaStream_t s) {
+  if (ctx->ga_x32) {
+    GaPlan pl{ctx->d_plan.p, ctx->d_plan.p + g.P, ctx->d_plan.p + 2 * static_cast<size_t>(g.P), ctx->d_plan.p + 3 * static_cast<size_t>(g.P),
+              ctx->d_plan.p + 4 * static_cast<size_t>(g.P), ctx->d_plan.p + 5 * static_cast<size_t>(g.P)};
+    GaDev g2 = g;
+    g2.coo = ctx->coo16 ? static_cast<const void *>(ctx->d_coo16o.p) : static_cast<const void *>(ctx->d_coo32o.p);
+    ga_plan_kernel<<<(g.P + 255) / 256, 256, 0, s>>>(g2, pl, reinterpret_cast<unsigned int *>(ctx->d_plan.p + 5 * static_cast<size_t>(g.P) + 1));
+    AHX_CUDA(ctx, cudaGetLastError());
+    cudaError_t e;
+    switch (ctx->ga_T) {
+      case 4: e = ctx->coo16 ? launch_apply<4, Coo16>(ctx, g2, pl, s) : launch_apply<4, Coo32>(ctx, g2, pl, s); break;
+      case 2: e = ctx->coo16 ? launch_apply<2, Coo16>(ctx, g2, pl, s) : launch_apply<2, Coo32>(ctx, g2, pl, s); break;
+      default: e = ctx->coo16 ? launch_apply<1, Coo16>(ctx, g2, pl, s) : launch_apply<1, Coo32>(ctx, g2, pl, s); break;
+    }
+    AHX_CUDA(ctx, e);
+    ctx->launches += 2;
+    return AHX_OK;
+  }
   const size_t smem = eval_m_smem_bytes(1, ctx->N, ctx->ga_L);
   if (ctx->coo16) ga_generation_kernel<Coo16><<<g.P, kBlock, smem, s>>>(g);
   else ga_generation_kernel<Coo32><<<g.P, kBlock, smem, s>>>(g);
@@ -356,11 +588,20 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   if (prm->npop < 2 || prm->npop - 2 < prm->tournament_k - 1) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: npop too small for 2 tournaments of k contestants");
   if (!(prm->mut_prob >= 0.0 && prm->mut_prob <= 1.0) || prm->ngen < 0 || prm->max_gens < 0 || prm->log_every < 0)
     return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: bad parameter");
+  ctx->ga_prm = *prm; ctx->ga_L = L;
+  ctx->ga_x32 = use_x32(ctx, L);
+  ctx->ga_T = ctx->ga_x32 ? ga_T(ctx) : 1;
+  if (const char *env = getenv("AHX_GA_T")) { const int t = atoi(env); if (ctx->ga_x32 && (t == 1 || t == 2 || t == 4)) ctx->ga_T = t; }
+  if (ctx->ga_x32) {
+    AHX_CUDA(ctx, ctx->d_plan.reserve(5 * static_cast<size_t>(prm->npop) + 2));
+    AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_plan.p + 5 * static_cast<size_t>(prm->npop), 0, 2 * sizeof(int32_t), ctx->stream));
+  }
   const size_t smem = eval_m_smem_bytes(1, ctx->N, L);
-  if (smem + 2048 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: group too large for the generation kernel's shared memory");
-  if (ctx->coo16) AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (!ctx->ga_x32 && smem + 2048 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: group too large for the generation kernel's shared memory");
+  if (ctx->ga_x32) { /* attributes are set per launch */ }
+  else if (ctx->coo16) AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   else AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  ctx->ga_prm = *prm; ctx->ga_L = L; ctx->ga_ms = 0.0;
+  ctx->ga_ms = 0.0;
   const size_t PL = static_cast<size_t>(prm->npop) * L;
   for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_pop[i].reserve(PL)); AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); }
   AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1));

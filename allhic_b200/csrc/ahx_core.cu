@@ -19,6 +19,7 @@
 
 #include "ahx_ctx.h"
 #include "ahx_device.cuh"
+#include "ahx_resident.cuh"
 
 namespace ahx {
 
@@ -411,6 +412,49 @@ static cudaError_t launch_x32_c(ahx_ctx *ctx, const IdxT *tours, const int32_t *
   }
 }
 
+// ---- resident-table kernel ------------------------------------------------------
+// Usable when the coordinates fit 32 bits, contig indices fit 16 bits and the
+// packed table + two X buffers fit one SM's shared memory.  T: as many tours per
+// batch as still leave one batch per SM.
+int resident_T(const ahx_ctx *ctx, int32_t P) {
+  if (const char *env = getenv("AHX_EVAL_RES")) if (!atoi(env)) return 0;
+  if (const char *env = getenv("AHX_EVAL_FP64")) if (atoi(env)) return 0;
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0) return 0;
+  auto fits = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res) + 1024 <= ctx->smem_optin; };
+  if (const char *env = getenv("AHX_EVAL_T")) {
+    const int t = atoi(env);
+    if (t == 1 || t == 2 || t == 4) return fits(t) ? t : 0;
+  }
+  for (int t : {4, 2})
+    if (fits(t) && (P + t - 1) / t >= ctx->sm_count) return t;
+  if (fits(1)) return 1;
+  return 0;
+}
+
+template <int T, typename IdxT>
+static cudaError_t launch_res_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
+  auto kern = eval_m_res_kernel<T, ResDirect<T, IdxT>>;
+  const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  ResArgs g{ctx->d_rpairs.p, ctx->d_rnl8.p, ctx->d_rnl32.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, out, ctx->d_errflag.p};
+  ResDirect<T, IdxT> src{};
+  src.tours = tours; src.rows = rows; src.P = P; src.L = L;
+  const int nb = (P + T - 1) / T;
+  kern<<<std::min(nb, ctx->sm_count), kRThreads, smem, s>>>(g, src);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+template <typename IdxT>
+static cudaError_t launch_res(ahx_ctx *ctx, int T, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
+  switch (T) {
+    case 4: return launch_res_t<4, IdxT>(ctx, tours, rows, P, L, out, s);
+    case 2: return launch_res_t<2, IdxT>(ctx, tours, rows, P, L, out, s);
+    default: return launch_res_t<1, IdxT>(ctx, tours, rows, P, L, out, s);
+  }
+}
+
 // Which formulation can run: 32-bit coordinates need 2*sum(sizes) + 2*LIMIT + 2 < 2^32
 // and N*4 bytes of shared memory; otherwise the fp64 kernel (x in shared or global memory).
 bool use_x32(const ahx_ctx *ctx, int32_t L) {
@@ -422,7 +466,9 @@ int launch_eval_m_sparse(ahx_ctx *ctx, const int32_t *d_tours, const uint16_t *d
                          int32_t P, int32_t L, double *d_out, cudaStream_t s) {
   if (P == 0) return AHX_OK;
   cudaError_t e;
-  if (use_x32(ctx, L)) {
+  if (const int rt = resident_T(ctx, P)) {
+    e = d_tours16 ? launch_res<uint16_t>(ctx, rt, d_tours16, d_rows, P, L, d_out, s) : launch_res<int32_t>(ctx, rt, d_tours, d_rows, P, L, d_out, s);
+  } else if (use_x32(ctx, L)) {
     if (d_tours16) e = ctx->coo16 ? launch_x32_c<Coo16, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s) : launch_x32_c<Coo32, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s);
     else e = ctx->coo16 ? launch_x32_c<Coo16, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s) : launch_x32_c<Coo32, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s);
   } else if (d_tours16) {
@@ -655,7 +701,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); ctx->d_pa.release(); ctx->d_pb.release();
+  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); ctx->d_rpairs.release(); ctx->d_rnl8.release(); ctx->d_rnl32.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
   ctx->d_tours.release(); ctx->d_res_tours.release(); ctx->d_res_scores.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
   ctx->d_flush.release(); ctx->d_errflag.release();
@@ -745,6 +791,25 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
       AHX_CUDA(ctx, ctx->d_coo32o.reserve(ord.size()));
       if (!ord.empty()) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo32o.p, o32.data(), sizeof(int4) * ord.size(), cudaMemcpyHostToDevice, ctx->stream));
       AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // resident-table form of the same ordered list (ahx_resident.cuh)
+    ctx->E_res = 0;
+    if (ctx->coo16 && E > 0) {
+      const size_t er = (ord.size() + kRPad - 1) / kRPad * kRPad;
+      std::vector<uint32_t> rp(er, 0u); std::vector<uint8_t> r8(er, 0); std::vector<int32_t> r32(er, 0);
+      for (size_t i = 0; i < ord.size(); ++i) {
+        if (ord[i] < 0) continue;
+        const int64_t e = ord[i];
+        rp[i] = static_cast<uint32_t>(pa[e]) | (static_cast<uint32_t>(pb[e]) << 16);
+        r8[i] = static_cast<uint8_t>(std::min<int32_t>(nl[e], 255));
+        r32[i] = nl[e];
+      }
+      AHX_CUDA(ctx, ctx->d_rpairs.reserve(er)); AHX_CUDA(ctx, ctx->d_rnl8.reserve(er + 16)); AHX_CUDA(ctx, ctx->d_rnl32.reserve(er));
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs.p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8.p, r8.data(), er, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl32.p, r32.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->E_res = static_cast<int64_t>(er);
     }
   }
   // CSR of pairs touching each contig (for flipOne's O(deg) deltas)

@@ -62,6 +62,11 @@ struct ahx_ctx {
   ahx::DevBuf<uint2> d_coo16, d_coo16o;   // sorted by (a,b) / bank-conflict-free order, padded
   ahx::DevBuf<int4> d_coo32, d_coo32o;
   int64_t E_pad = 0;                      // entries in the ordered table (multiple of 256)
+  // resident-table kernel (ahx_resident.cuh): packed a | b << 16, min(nlinks,255), full nlinks; same order, null padded
+  ahx::DevBuf<uint32_t> d_rpairs;
+  ahx::DevBuf<uint8_t> d_rnl8;
+  ahx::DevBuf<int32_t> d_rnl32;
+  int64_t E_res = 0;                      // multiple of kRPad (0 when E == 0)
   bool x32_ok = false;                    // 2*sum(sizes) + 2*LIMIT + 2 < 2^32
   ahx::DevBuf<int32_t> d_pa, d_pb, d_slots, d_hist, d_M;
   bool dense_ready = false;
@@ -123,6 +128,8 @@ int validate_tour(ahx_ctx *ctx, int32_t L, const int32_t *tour, const char *who)
 size_t eval_m_smem_bytes(int T, int32_t N, int32_t L);
 size_t eval_x32_smem_bytes(int T, bool coo16, int32_t N, int32_t L);
 bool use_x32(const ahx_ctx *ctx, int32_t L);
+// Tours per batch of the resident-table kernel for a population of P tours (0: not usable).
+int resident_T(const ahx_ctx *ctx, int32_t P);
 }  // namespace ahx
 
 #define AHX_CUDA(ctx, call)                                              \

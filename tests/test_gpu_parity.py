@@ -67,14 +67,16 @@ def test_eval_m_population_fixture(fix, P):
     assert close(eng.eval_m(tours.astype(np.uint16)), want)
 
 
-@pytest.mark.parametrize("fp64", ["0", "1"])
+@pytest.mark.parametrize("path", ["resident", "stream32", "fp64"])
 @pytest.mark.parametrize("T", ["1", "2", "4"])
-def test_eval_m_tours_per_cta(syn, T, fp64, monkeypatch):
-    """Both formulations of the contig-space kernel (32-bit coordinates + TMA-staged
-    pair table; fp64 coordinates fallback) at every tours-per-CTA setting."""
+def test_eval_m_tours_per_cta(syn, T, path, monkeypatch):
+    """All three formulations of the contig-space kernel (persistent kernel with the
+    pair table resident in shared memory; 32-bit coordinates + TMA-streamed pair
+    table; fp64 coordinates fallback) at every tours-per-batch setting."""
     eng, clm, orc = syn
     monkeypatch.setenv("AHX_EVAL_T", T)
-    monkeypatch.setenv("AHX_EVAL_FP64", fp64)
+    monkeypatch.setenv("AHX_EVAL_RES", "1" if path == "resident" else "0")
+    monkeypatch.setenv("AHX_EVAL_FP64", "1" if path == "fp64" else "0")
     rng = np.random.default_rng(int(T))
     tours = np.stack([rng.permutation(clm.N) for _ in range(203)]).astype(np.int32)
     tours[0] = np.arange(clm.N); tours[1] = np.arange(clm.N)[::-1]

@@ -909,6 +909,16 @@ int ahx_pop_scores(ahx_ctx *ctx, double *out) {
   return AHX_OK;
 }
 
+int ahx_eval_m_kernel(const ahx_ctx *ctx, int32_t P, int32_t L, int32_t *tours_per_batch) {
+  if (!ctx || !ctx->loaded) return AHX_ERR_STATE;
+  int kind = 0, T = 1;
+  if (const int rt = resident_T(ctx, P)) { kind = 2; T = rt; }
+  else if (use_x32(ctx, L)) { kind = 1; T = pick_T32(ctx, P, L); }
+  else if (eval_m_smem_bytes(1, ctx->N, L) + 1024 <= ctx->smem_optin) T = pick_T(ctx, P, L);
+  if (tours_per_batch) *tours_per_batch = T;
+  return kind;
+}
+
 int ahx_flush_l2(ahx_ctx *ctx) {
   int rc = enter(ctx, false);
   if (rc != AHX_OK) return rc;

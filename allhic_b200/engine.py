@@ -117,6 +117,14 @@ class Engine:
         self._ck(self._l.ahx_pop_scores(self.h, _ptr(out)))
         return out
 
+    def eval_m_kernel(self, P, L=None):
+        """(kind, tours_per_batch): 2 resident-table, 1 x32 streaming, 0 fp64 coordinates."""
+        t = C.c_int32()
+        kind = self._l.ahx_eval_m_kernel(self.h, P, self.N if L is None else L, C.byref(t))
+        if kind < 0:
+            self._ck(kind)
+        return kind, t.value
+
     def flush_l2(self):
         self._ck(self._l.ahx_flush_l2(self.h))
 

@@ -28,6 +28,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 LIMIT = 10_000_000
+HBM_PEAK = 6544.3   # GB/s, fallback when MEASURED_PEAKS.json is absent (it is driver-written per pod)
+try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as _f:
+        HBM_PEAK = float(json.load(_f)["hbm_gbs"])
+except Exception:
+    pass
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the evaluate kernel, from the committed
+# ncu --set full capture of (workload, P) -- profiles/r1b_ncu_full_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64232192 + 669952}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 
@@ -106,6 +115,13 @@ class ClockSampler:
 
     def start(self):
         self._t.start()
+
+    def peak_mhz(self):
+        """SM clock under load so far (median of the upper half by power), else the NVML max, else 1965."""
+        if self.samples:
+            by_power = sorted(self.samples, key=lambda x: x[1])
+            return float(np.median([s for s, _ in by_power[len(by_power) // 2:]]))
+        return float(self.max_mhz or 1965.0)
 
     def stop(self):
         self._stop.set(); self._t.join(timeout=5)
@@ -251,15 +267,28 @@ def main():
     e2e_v = world * P * args.steps / e2e_s
     kern_s = dev_ms * 1e-3 / args.steps
     terms_per_s = P * e_act / kern_s                       # per GPU (roofline is a per-kernel figure)
-    roof = {"bound": "fp64", "achieved": 2.0 * terms_per_s / 1e12, "peak": dfma_tflops, "unit": "TFLOP/s",
-            "frac": 2.0 * terms_per_s / 1e12 / dfma_tflops, "traffic": None,
-            "peak_source": "DFMA microbenchmark measured live by this run (MEASURED_PEAKS.json has no fp64 figure)",
-            "kernel": "eval_m_sparse_kernel", "pair_terms_per_tour": e_act, "flops_per_pair_term": 2,
-            "pair_terms_per_s": terms_per_s, "measured_div_add_peak_per_s": ddiv_g * 1e9,
-            "frac_of_div_add_peak": terms_per_s / (ddiv_g * 1e9),
+    # Roofline of the dominant kernel: per tour, E window tests each gathering two
+    # 4-byte coordinates from shared memory, E_act in-window pairs each one fp64 divide + add, and
+    # 4*L + 8 bytes of HBM.  The slowest leg at its measured/derived peak is the bound.
+    sm_mhz = clocks.peak_mhz()
+    smem_peak = 128.0 * eng.sm_count() * sm_mhz * 1e6 / 1e9                      # GB/s: 128 B/clk/SM
+    legs = {"smem": (P * 8.0 * E / kern_s / 1e9, smem_peak, "GB/s"),
+            "fp64": (terms_per_s / 1e9, ddiv_g, "Gdiv+add/s"),
+            "hbm": (P * (4.0 * L + 8.0) / kern_s / 1e9, HBM_PEAK, "GB/s")}
+    bound = max(legs, key=lambda k: legs[k][0] / legs[k][1])
+    roof = {"bound": bound, "achieved": legs[bound][0], "peak": legs[bound][1], "unit": legs[bound][2],
+            "frac": legs[bound][0] / legs[bound][1],
+            "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, P)),
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (profiles/), bytes per launch",
+            "peak_source": {"smem": "128 B/clk/SM x %d SMs x %.0f MHz (SM clock sampled during the timed region)" % (eng.sm_count(), sm_mhz),
+                            "fp64": "dependent-free fp64 divide+add microbenchmark measured live by this run (ahx_probe_fp64)",
+                            "hbm": "MEASURED_PEAKS.json hbm_gbs"}[bound],
+            "kernel": {2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[eng.eval_m_kernel(P, L)[0]], "tours_per_batch": eng.eval_m_kernel(P, L)[1],
+            "algorithmic_per_tour": {"window_tests_E": E, "smem_gather_bytes": 8 * E, "in_window_pairs_E_act": e_act, "hbm_bytes": 4 * L + 8},
+            "legs": {k: {"achieved": v[0], "peak": v[1], "unit": v[2], "frac": v[0] / v[1]} for k, v in legs.items()},
             "dense_equivalent": {"window_pairs_per_tour": w_dense, "bytes_per_tour": 4 * w_dense + 12 * L,
-                                 "algorithmic_GBs": P * (4 * w_dense + 12 * L) / kern_s / 1e9, "hbm_peak_GBs": 6544.3,
-                                 "note": "algorithmic speed-up of the contig-space formulation, not a roofline fraction"}}
+                                 "algorithmic_GBs": P * (4 * w_dense + 12 * L) / kern_s / 1e9, "hbm_peak_GBs": HBM_PEAK,
+                                 "note": "north_star's dense M-gather bytes at this eval rate: the algorithmic speed-up of the contig-space formulation, not a roofline fraction"}}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
@@ -280,8 +309,8 @@ def main():
             eng.flush_l2(); ms += eng.pop_eval_m("dense", 1)
         dk = ms * 1e-3 / 5
         out["dense_kernel"] = {"evals_per_s": sub / dk, "population": sub,
-                               "roofline": {"bound": "hbm", "achieved": sub * (4 * w_dense + 12 * L) / dk / 1e9, "peak": 6544.3, "unit": "GB/s",
-                                            "frac": sub * (4 * w_dense + 12 * L) / dk / 1e9 / 6544.3,
+                               "roofline": {"bound": "hbm", "achieved": sub * (4 * w_dense + 12 * L) / dk / 1e9, "peak": HBM_PEAK, "unit": "GB/s",
+                                            "frac": sub * (4 * w_dense + 12 * L) / dk / 1e9 / HBM_PEAK,
                                             "note": "M (%.0f MB int32) is %s" % (4.0 * n * n / 1e6, "L2-resident: bytes come from L2, not HBM" if 4 * n * n < 100e6 else "larger than L2")}}
 
     # ---- GA (generations/s), islands over NCCL when world > 1

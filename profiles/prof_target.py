@@ -37,7 +37,7 @@ for _ in range(3):
     ms = eng.pop_eval_m("sparse", 1)
 print("eval_m %s: %.3f ms -> %.2f M evals/s" % ("converged" if converged else "random", ms, P / ms / 1e3))
 eng.ga_begin(tours[0], eng.ga_params(npop=P, ngen=1 << 30, max_gens=1 << 40, seed=42))
-st = eng.ga_advance(6)
+st = eng.ga_advance(2)
 eng.ga_end()
 signs = np.where(rng.random((256, n)) < 0.5, ord('+'), ord('-')).astype(np.uint8)
 eng.eval_q(tours[0], signs)

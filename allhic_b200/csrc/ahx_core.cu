@@ -420,7 +420,7 @@ int resident_T(const ahx_ctx *ctx, int32_t P) {
   if (const char *env = getenv("AHX_EVAL_RES")) if (!atoi(env)) return 0;
   if (const char *env = getenv("AHX_EVAL_FP64")) if (atoi(env)) return 0;
   if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0) return 0;
-  auto fits = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res) + 1024 <= ctx->smem_optin; };
+  auto fits = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res) + 1024 <= ctx->smem_optin && static_cast<uint64_t>(ctx->N) * 4u * t <= 65535u; };
   if (const char *env = getenv("AHX_EVAL_T")) {
     const int t = atoi(env);
     if (t == 1 || t == 2 || t == 4) return fits(t) ? t : 0;
@@ -433,11 +433,11 @@ int resident_T(const ahx_ctx *ctx, int32_t P) {
 
 template <int T, typename IdxT>
 static cudaError_t launch_res_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
-  auto kern = eval_m_res_kernel<T, ResDirect<T, IdxT>>;
+  auto kern = L < ctx->N ? eval_m_res_kernel<T, true, ResDirect<T, IdxT>> : eval_m_res_kernel<T, false, ResDirect<T, IdxT>>;
   const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  ResArgs g{ctx->d_rpairs.p, ctx->d_rnl8.p, ctx->d_rnl32.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, out, ctx->d_errflag.p};
+  ResArgs g{ctx->d_rpairs[T == 4 ? 2 : T - 1].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, out, ctx->d_errflag.p};
   ResDirect<T, IdxT> src{};
   src.tours = tours; src.rows = rows; src.P = P; src.L = L;
   const int nb = (P + T - 1) / T;
@@ -701,7 +701,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); ctx->d_rpairs.release(); ctx->d_rnl8.release(); ctx->d_rnl32.release(); ctx->d_pa.release(); ctx->d_pb.release();
+  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); for (auto &b : ctx->d_rpairs) b.release(); ctx->d_rnl8.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
   ctx->d_tours.release(); ctx->d_res_tours.release(); ctx->d_res_scores.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
   ctx->d_flush.release(); ctx->d_errflag.release();
@@ -792,24 +792,39 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
       if (!ord.empty()) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_coo32o.p, o32.data(), sizeof(int4) * ord.size(), cudaMemcpyHostToDevice, ctx->stream));
       AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    // resident-table form of the same ordered list (ahx_resident.cuh)
+    // resident-table form (ahx_resident.cuh): 8-bit link counts, so a pair with more
+    // than 255 links becomes several entries; ordered and padded like the list above
     ctx->E_res = 0;
     if (ctx->coo16 && E > 0) {
-      const size_t er = (ord.size() + kRPad - 1) / kRPad * kRPad;
-      std::vector<uint32_t> rp(er, 0u); std::vector<uint8_t> r8(er, 0); std::vector<int32_t> r32(er, 0);
-      for (size_t i = 0; i < ord.size(); ++i) {
-        if (ord[i] < 0) continue;
-        const int64_t e = ord[i];
-        rp[i] = static_cast<uint32_t>(pa[e]) | (static_cast<uint32_t>(pb[e]) << 16);
-        r8[i] = static_cast<uint8_t>(std::min<int32_t>(nl[e], 255));
-        r32[i] = nl[e];
+      std::vector<int32_t> xa, xb, xn;
+      xa.reserve(E); xb.reserve(E); xn.reserve(E);
+      for (int64_t e = 0; e < E; ++e)
+        for (int32_t left = nl[e]; left > 0; left -= 255) { xa.push_back(pa[e]); xb.push_back(pb[e]); xn.push_back(std::min(left, 255)); }
+      if (xa.size() <= static_cast<size_t>(8) * E + 4096) {   // absurd link counts: leave it to the streaming kernels
+        std::vector<int64_t> rord;
+        order_pairs(static_cast<int64_t>(xa.size()), xa.data(), xb.data(), &rord);
+        const size_t er = (rord.size() + kRPad - 1) / kRPad * kRPad;
+        std::vector<uint8_t> r8(er + 16, 0);
+        std::vector<uint32_t> ra(er, 0u), rb(er, N > 1 ? 1u : 0u);   // padding: contigs (0, 1) with 0 links
+        for (size_t i = 0; i < rord.size(); ++i) {
+          if (rord[i] < 0) continue;
+          const int64_t x = rord[i];
+          ra[i] = static_cast<uint32_t>(xa[x]); rb[i] = static_cast<uint32_t>(xb[x]);
+          r8[i] = static_cast<uint8_t>(xn[x]);
+        }
+        AHX_CUDA(ctx, ctx->d_rnl8.reserve(er + 16));
+        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8.p, r8.data(), er + 16, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint32_t> rp(er);
+        for (int ti = 0; ti < 3; ++ti) {   // one table per tours-per-batch T = 1, 2, 4: entries are byte offsets into X
+          const uint32_t stride = 4u << ti;
+          if (static_cast<uint64_t>(N) * stride > 65535u) continue;
+          for (size_t i = 0; i < er; ++i) rp[i] = (ra[i] * stride) | ((rb[i] * stride) << 16);
+          AHX_CUDA(ctx, ctx->d_rpairs[ti].reserve(er));
+          AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs[ti].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
+          AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // rp is reused
+        }
+        ctx->E_res = static_cast<int64_t>(er);
       }
-      AHX_CUDA(ctx, ctx->d_rpairs.reserve(er)); AHX_CUDA(ctx, ctx->d_rnl8.reserve(er + 16)); AHX_CUDA(ctx, ctx->d_rnl32.reserve(er));
-      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs.p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
-      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8.p, r8.data(), er, cudaMemcpyHostToDevice, ctx->stream));
-      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl32.p, r32.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
-      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      ctx->E_res = static_cast<int64_t>(er);
     }
   }
   // CSR of pairs touching each contig (for flipOne's O(deg) deltas)

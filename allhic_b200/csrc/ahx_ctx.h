@@ -62,10 +62,11 @@ struct ahx_ctx {
   ahx::DevBuf<uint2> d_coo16, d_coo16o;   // sorted by (a,b) / bank-conflict-free order, padded
   ahx::DevBuf<int4> d_coo32, d_coo32o;
   int64_t E_pad = 0;                      // entries in the ordered table (multiple of 256)
-  // resident-table kernel (ahx_resident.cuh): packed a | b << 16, min(nlinks,255), full nlinks; same order, null padded
-  ahx::DevBuf<uint32_t> d_rpairs;
+  // resident-table kernel (ahx_resident.cuh): per entry the byte offsets of the two contigs in X,
+  // (a*4T) | (b*4T) << 16, one table per T = 1, 2, 4, and an 8-bit link count (pairs with more than
+  // 255 links are split over several entries); bank-conflict-free order, padded with (0, 1, 0)
+  ahx::DevBuf<uint32_t> d_rpairs[3];
   ahx::DevBuf<uint8_t> d_rnl8;
-  ahx::DevBuf<int32_t> d_rnl32;
   int64_t E_res = 0;                      // multiple of kRPad (0 when E == 0)
   bool x32_ok = false;                    // 2*sum(sizes) + 2*LIMIT + 2 < 2^32
   ahx::DevBuf<int32_t> d_pa, d_pb, d_slots, d_hist, d_M;

@@ -2,23 +2,29 @@
 // warp-specialised kernel with the pair table RESIDENT in shared memory.
 //
 // One CTA per SM (kRThreads = 640 threads, up to ~200 KB of shared memory):
-//   table   uint32[E_res]   nonzero pairs of M packed a | b << 16, in the
-//                           bank-conflict-free order of order_pairs(), padded
-//                           with null pairs (a == b) to a multiple of
-//                           kRCT * kRUnroll; loaded ONCE per CTA by TMA bulk copies
-//   nl8     uint8[E_res]    min(nlinks, 255); 255 = look nlinks up in global memory
+//   table   uint32[E_res]   nonzero pairs of M as the byte offsets of the two contigs in X,
+//                           (a*4T) | (b*4T) << 16 (N*4T < 64 KB whenever X fits), in the
+//                           bank-conflict-free order of order_pairs(), padded with
+//                           (0, 1, nlinks 0) entries to a multiple of kRCT * kRUnroll;
+//                           loaded ONCE per CTA by TMA bulk copies
+//   nl8     uint8[E_res]    nlinks of the entry (a pair with more than 255 links is split
+//                           over several entries: sum_i n_i / d == n / d up to rounding)
 //   X[2]    uint32[N*T]     2*mid of contig c in tour t at X[c*T + t], double buffered
-//   queues  uint32[16][160] per-consumer-warp queue of hot pair indices
 // Roles:
 //   4 producer warps  build X[buf] for batch k+1 (T tours: read the rows, prefix-sum
 //                     the sizes, scatter 2*cum+size to contig space) while the
 //                     consumers work on batch k; they also fold the 16 per-warp
 //                     partial sums of a finished batch in a fixed order and write
 //                     the scores.  full[buf] / done[buf] mbarriers hand the buffers over.
-//   16 consumer warps each owns 1/16 of the pair table: window test on the integer
-//                     pipe for the T tours of the batch, hot pairs (inside the window
-//                     of at least one tour) compacted into the warp's queue, 32 at a
-//                     time evaluated branch-free on the fp64 pipe (PairSink logic).
+//   16 consumer warps each owns 1/16 of the pair table and evaluates EVERY stored pair
+//                     for the T tours of the batch, branch-free: the window test
+//                     (integer pipe) only selects the numerator (nlinks or 0), the
+//                     reciprocal is MUFU.RCP64H + one cubic correction (<= 1 ulp).  The
+//                     cost is data independent -- random and converged tours run at the
+//                     same rate -- and bound by the fp64/XU pipes (profiles/microbench/
+//                     rcp_probe.cu: 16.3 SMSP-cycles per warp-term); filtering in-window
+//                     pairs first (the r1a/r1b design: ballot compaction into per-warp
+//                     queues, re-gather, divide) cost more than the divides it saved.
 // Batches are assigned round-robin (batch b -> CTA b mod gridDim.x) and every
 // reduction has a fixed shape, so a score depends only on the tours that share
 // its batch, never on scheduling: bit-reproducible run to run.
@@ -30,19 +36,16 @@
 namespace ahx {
 
 constexpr int kRC = 16;                       // consumer warps
-constexpr int kRP = 4;                        // producer warps
+constexpr int kRP = 8;                        // producer warps
 constexpr int kRCT = kRC * 32;                // consumer threads
 constexpr int kRPT = kRP * 32;                // producer threads
 constexpr int kRThreads = kRCT + kRPT;
 constexpr int kRUnroll = 4;                   // pairs per consumer lane per iteration
-constexpr int kRQueue = 32 + 32 * kRUnroll;   // queue entries per consumer warp
 constexpr int kRPad = kRCT * kRUnroll;        // E_res is a multiple of this
-constexpr int kRChunk = 16;                   // tour positions a producer thread keeps in registers
 
 struct ResArgs {
   const uint32_t *pairs;      // [E_res]
   const uint8_t *nl8;         // [E_res]
-  const int32_t *nl32;        // [E_res]
   const uint32_t *sizes32;    // [N]
   int E_res, N, L;
   double *out;
@@ -53,171 +56,164 @@ __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~sta
 // dynamic shared memory of the resident kernel
 inline size_t res_smem_bytes(int T, int N, long long E_res) {
   return res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res)) + 2 * res_align16(4ull * N * T) +
-         4ull * kRC * kRQueue + 8ull * 2 * kRC * T + 4ull * kRP * T + 8 * 8;
+         8ull * 2 * kRC * T + 4ull * kRP * T + 8 * 8;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// cp.async.bulk.prefetch.L2: bytes rounded down to a multiple of 16 from a 16-byte aligned start
+__device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes) {
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 15) & ~static_cast<uintptr_t>(15);
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~static_cast<uintptr_t>(15);
+  if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(static_cast<uint32_t>(e - a)) : "memory");
+}
+
 // ---- batch sources -------------------------------------------------------------
-// A source maps (batch, slot t) to a tour: n_batches(), bind(batch), live(t),
-// get(t, i), put(t, i, c) and out_row(batch, t) (-1: nothing to write).
+// A source maps (batch, slot t) to a tour: n_batches(), out_row(batch, t) (-1: slot
+// unused, nothing to write) and cursor(batch, t), a per-lane view of that tour with
+// live(), get(i) = contig at position i, put(i, c) (lets the GA write the offspring
+// row while it is being read).
 template <int T, typename IdxT>
 struct ResDirect {
   const IdxT *tours; const int *rows; int P, L;
-  const IdxT *ptr[T];
+  struct Cursor {
+    const IdxT *ptr;
+    __device__ __forceinline__ bool live() const { return ptr != nullptr; }
+    __device__ __forceinline__ unsigned get(int i) const { return static_cast<unsigned>(ptr[i]); }
+    __device__ __forceinline__ void put(int, unsigned) const {}
+  };
   __device__ __forceinline__ int n_batches() const { return (P + T - 1) / T; }
   __device__ __forceinline__ int out_row(int batch, int t) const {
     const int p = batch * T + t;
     return p < P ? (rows ? rows[p] : p) : -1;
   }
-  __device__ __forceinline__ void bind(int batch) {
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int r = out_row(batch, t);
-      ptr[t] = r >= 0 ? tours + static_cast<size_t>(r) * L : nullptr;
-    }
+  __device__ __forceinline__ Cursor cursor(int batch, int t) const {
+    const int r = out_row(batch, t);
+    return Cursor{r >= 0 ? tours + static_cast<size_t>(r) * L : nullptr};
   }
-  __device__ __forceinline__ bool live(int t) const { return ptr[t] != nullptr; }
-  __device__ __forceinline__ unsigned get(int t, int i) const { return static_cast<unsigned>(ptr[t][i]); }
-  __device__ __forceinline__ void put(int, int, unsigned) const {}
+  // asks the L2 for the rows of a later batch (called by T lanes, one row each)
+  __device__ __forceinline__ void prefetch(int batch, int t) const {
+    const int r = batch < n_batches() ? out_row(batch, t) : -1;
+    if (r >= 0) l2_prefetch(tours + static_cast<size_t>(r) * L, static_cast<uint32_t>(sizeof(IdxT)) * L);
+  }
 };
 
 // ---- producer: X[buf] for one batch ----------------------------------------------
-// Thread ptid owns positions [ptid*per, ptid*per + per) of every tour of the batch.
-// 2*sum(sizes) < 2^32 in x32 mode, so the prefix sums run in 32 bits.
+// Lane l of a producer warp works on tour t = l mod T at position offset l / T, so a
+// warp instruction covers 32/T consecutive positions of each of the T tours: the global
+// loads are sector-dense and the scatter X[c*T + t] spreads over all 32 banks (bank =
+// T*(c mod 32/T) + t).  Producer warp w owns positions [w*Q, (w+1)*Q).  Pass 1 sums the
+// sizes of the warp's range per tour, a named barrier publishes the 4 x T totals, pass 2
+// re-reads the range (L2/L1 hits), does a segmented warp scan per tour and scatters
+// 2*cum + size = 2*mid (evaluate.go:120-126).  2*sum(sizes) < 2^32 in x32 mode, so all
+// prefix sums run in 32 bits.
 template <int T, typename Src>
-__device__ __forceinline__ void res_build_x(const Src &src, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
+__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
                                             uint32_t *scan_scratch /* kRP*T */, int *errflag, int ptid) {
+  constexpr int PPI = 32 / T;                    // positions per warp instruction
+  constexpr int kU = 16;                         // independent loads in flight per lane
   const int lane = ptid & 31, wid = ptid >> 5;
-  const int per = (L + kRPT - 1) / kRPT;
-  const int beg = min(L, ptid * per), end = min(L, beg + per);
+  const int t = lane % T, sub = lane / T;
+  const auto cur = src.cursor(batch, t);
+  const bool live = cur.live();
+  const int Q = ((L + kRP - 1) / kRP + PPI - 1) / PPI * PPI;
+  const int beg = min(L, wid * Q), end = min(L, beg + Q);
   bool bad = false;
   if (L < N) {   // sub-tour: contigs outside the tour must fail every window test
     for (int i = ptid; i < N * T; i += kRPT) X[i] = kInactiveX;
-    named_bar_sync(1, kRPT);
   }
-  uint32_t cum[T];
-  if (per <= kRChunk) {
-    unsigned c[T][kRChunk];
+  // pass 1: sum of sizes over this warp's range, per tour
+  uint32_t local = 0;
+  for (int p0 = beg + sub; p0 < end; p0 += PPI * kU) {
+    unsigned c[kU];
 #pragma unroll
-    for (int t = 0; t < T; ++t)
+    for (int u = 0; u < kU; ++u) c[u] = (live && p0 + u * PPI < end) ? cur.get(p0 + u * PPI) : 0xFFFFFFFFu;
 #pragma unroll
-      for (int i = 0; i < kRChunk; ++i) c[t][i] = (src.live(t) && beg + i < end) ? src.get(t, beg + i) : 0xFFFFFFFFu;
+    for (int u = 0; u < kU; ++u) local += c[u] < static_cast<unsigned>(N) ? __ldg(sizes32 + c[u]) : 0u;
+  }
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      uint32_t local = 0;
+  for (int d = T; d < 32; d <<= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if (lane < T) scan_scratch[wid * T + lane] = local;
+  named_bar_sync(1, kRPT);
+  uint32_t carry = 0;
 #pragma unroll
-      for (int i = 0; i < kRChunk; ++i) {
-        const bool on = src.live(t) && beg + i < end;
-        if (on) src.put(t, beg + i, c[t][i]);
-        if (on && c[t][i] >= static_cast<unsigned>(N)) { bad = true; c[t][i] = 0xFFFFFFFFu; }
-        local += c[t][i] != 0xFFFFFFFFu ? __ldg(sizes32 + c[t][i]) : 0u;
-      }
-      cum[t] = local;
+  for (int w = 0; w < kRP; ++w) carry += (w < wid) ? scan_scratch[w * T + t] : 0u;
+  // pass 2: segmented scan + scatter
+  for (int p0 = beg + sub; p0 - sub < end; p0 += PPI * kU) {
+    unsigned c[kU]; uint32_t sz[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) c[u] = (live && p0 + u * PPI < end) ? cur.get(p0 + u * PPI) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const bool on = live && p0 + u * PPI < end;
+      if (on) cur.put(p0 + u * PPI, c[u]);
+      if (on && c[u] >= static_cast<unsigned>(N)) { bad = true; c[u] = 0xFFFFFFFFu; }
+      sz[u] = c[u] != 0xFFFFFFFFu ? __ldg(sizes32 + c[u]) : 0u;
     }
-    // exclusive scan over the kRPT producer threads
-    uint32_t incl[T];
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      uint32_t v = cum[t];
+    for (int u = 0; u < kU; ++u) {
+      uint32_t v = sz[u];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += n; }
-      incl[t] = v;
-      if (lane == 31) scan_scratch[wid * T + t] = v;
-    }
-    named_bar_sync(1, kRPT);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      uint32_t base = 0;
-#pragma unroll
-      for (int w = 0; w < kRP; ++w) base += (w < wid) ? scan_scratch[w * T + t] : 0u;
-      uint32_t c2 = 2u * (base + incl[t] - cum[t]);
-#pragma unroll
-      for (int i = 0; i < kRChunk; ++i) {
-        if (c[t][i] == 0xFFFFFFFFu) continue;
-        const uint32_t sz = __ldg(sizes32 + c[t][i]);               // L1 hit: read a moment ago
-        X[static_cast<size_t>(c[t][i]) * T + t] = c2 + sz;          // 2*cum + size = 2*mid, evaluate.go:120-126
-        c2 += 2u * sz;
-      }
-    }
-  } else {
-    uint32_t incl[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      uint32_t local = 0;
-      if (src.live(t))
-        for (int i = beg; i < end; ++i) {
-          const unsigned c = src.get(t, i);
-          src.put(t, i, c);
-          if (c >= static_cast<unsigned>(N)) bad = true; else local += __ldg(sizes32 + c);
-        }
-      cum[t] = local;
-      uint32_t v = local;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += n; }
-      incl[t] = v;
-      if (lane == 31) scan_scratch[wid * T + t] = v;
-    }
-    named_bar_sync(1, kRPT);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (!src.live(t)) continue;
-      uint32_t base = 0;
-#pragma unroll
-      for (int w = 0; w < kRP; ++w) base += (w < wid) ? scan_scratch[w * T + t] : 0u;
-      uint32_t c2 = 2u * (base + incl[t] - cum[t]);
-      for (int i = beg; i < end; ++i) {
-        const unsigned c = src.get(t, i);
-        if (c >= static_cast<unsigned>(N)) continue;
-        const uint32_t s = __ldg(sizes32 + c);
-        X[static_cast<size_t>(c) * T + t] = c2 + s;
-        c2 += 2u * s;
-      }
+      for (int d = T; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += n; }
+      if (c[u] != 0xFFFFFFFFu) X[static_cast<size_t>(c[u]) * T + t] = 2u * (carry + v - sz[u]) + sz[u];   // 2*cum + size
+      carry += __shfl_sync(0xffffffffu, v, 32 - T + t);
     }
   }
   if (bad) *errflag = 1;
-  named_bar_sync(1, kRPT);   // scan_scratch may be rewritten by the next batch
+  named_bar_sync(1, kRPT);   // scan_scratch may be rewritten by the next batch; X[buf] is complete
 }
 
-// ---- consumer: window test + hot-pair queue + fp64 drain ------------------------
-template <int T>
-struct ResSink {
-  using V = typename XVec<T>::type;
-  const uint32_t *table; const uint8_t *nl8; const int32_t *nl32;
-  uint32_t *q;
-  const uint32_t *X;
-  int cnt, lane;
-  double acc[T];
-  __device__ __forceinline__ bool test(uint32_t p) const {
-    uint32_t xa[T], xb[T];
-    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p & 0xffffu) * T), xa);
-    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p >> 16) * T), xb);
-    uint32_t m = 0xFFFFFFFFu;
-#pragma unroll
-    for (int t = 0; t < T; ++t) m = min(m, __usad(xa[t], xb[t], 0u) - 1u);
-    return m < kLimit2;                                   // 0 < |dX| <= 2*LIMIT for some tour
-  }
-  __device__ __forceinline__ void evaluate(uint32_t e) {
-    const uint32_t p = table[e];
-    uint32_t nl = nl8[e];
-    if (nl == 255u) nl = static_cast<uint32_t>(__ldg(nl32 + e));
-    uint32_t xa[T], xb[T];
-    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p & 0xffffu) * T), xa);
-    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p >> 16) * T), xb);
-    const double n2 = 2.0 * u32_to_double(nl);
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const uint32_t d = __usad(xa[t], xb[t], 0u);
-      const bool in = d - 1u < kLimit2;
-      const double term = div_pos(n2, u32_to_double(in ? d : 1u));   // nlinks / dist, evaluate.go:140
-      acc[t] += in ? term : 0.0;
-    }
-  }
-};
+// ---- consumer: every stored pair x T tours, branch-free ----------------------------
+// 1/x for a positive normal double: MUFU.RCP64H seed (relative error 2^-20 on
+// [1, 2^25], measured) and one cubic step r(1 + e + e^2), e = 1 - x r  => 2^-60
+// before rounding, i.e. <= 1 ulp of the IEEE quotient (rcp_probe.cu, V1).
+__device__ __forceinline__ double rcp_pos(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);
+}
 
-template <int T, typename Src>
+// acc[t] += nlinks / dist for one table entry:
+//   p  = byte offsets of the two contigs' coordinate groups in X: (a*4T) | (b*4T) << 16
+//   n8 = nlinks of the entry (<= 255)
+//   d  = |X_a - X_b| = 2 dist;  inside the window  <=>  0 < d <= 2 LIMIT  (evaluate.go:135-137)
+//   term = (2 nlinks) / d                                                  (evaluate.go:140)
+// The window mask is applied to the 32-bit reciprocal SEED: with r0 = 0 the cubic step
+// gives e = 1, r = 0 (0 * 2 + 0), so the term is exactly +0 whatever d is -- one SEL
+// instead of selects on 64-bit operands, and d = 0 (inf from MUFU) never propagates.
+// SUB = false (full tours, L == N): all X are distinct and padding entries are
+//   (0, 1, n = 0), so d >= 1 and the test is d <= 2 LIMIT.
+// SUB = true  (sub-tour): inactive contigs share X = 0xFFFFFFFF, d can be 0: the test is
+//   d - 1 < 2 LIMIT (unsigned).
+// Issue-slot model measured with profiles/microbench/term_probe.cu: an fp64 instruction
+// costs 2 issue cycles, anything else 1.
+template <int T, bool SUB>
+__device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, uint32_t n8, double (&acc)[T]) {
+  using V = typename XVec<T>::type;
+  uint32_t xa[T], xb[T];
+  const unsigned char *Xb = reinterpret_cast<const unsigned char *>(X);
+  x_unpack(*reinterpret_cast<const V *>(Xb + (p & 0xffffu)), xa);
+  x_unpack(*reinterpret_cast<const V *>(Xb + (p >> 16)), xb);
+  const double n2 = u32_to_double(2u * n8);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const uint32_t d = __usad(xa[t], xb[t], 0u);
+    const bool in = SUB ? (d - 1u < kLimit2) : (d <= kLimit2);
+    const double x = u32_to_double(d);
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));                 // MUFU.RCP64H: high word, relative error 2^-20
+    const double r = __hiloint2double(in ? __double2hiint(r0) : 0, 0);
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    acc[t] = fma(n2, fma(r, e, r), acc[t]);                                 // r (1 + e + e^2): <= 1 ulp of 1/x (rcp_probe.cu V1)
+  }
+}
+
+template <int T, bool SUB, typename Src>
 __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src src) {
   extern __shared__ __align__(128) unsigned char smem_res[];
   unsigned char *sp = smem_res;
@@ -226,7 +222,6 @@ __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src
   uint32_t *X0 = reinterpret_cast<uint32_t *>(sp);
   const size_t xstride = res_align16(4ull * g.N * T) / 4;   // words between the two X buffers
   sp += 2 * res_align16(4ull * g.N * T);
-  uint32_t *queues = reinterpret_cast<uint32_t *>(sp); sp += 4ull * kRC * kRQueue;
   double *partial = reinterpret_cast<double *>(sp); sp += 8ull * 2 * kRC * T;      // [buf][warp][t]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 8 * 8;                  // full[2], done[2], tab
   uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(sp);
@@ -266,54 +261,34 @@ __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src
     int k = 0;
     for (int b = blockIdx.x; b < nb; b += gridDim.x, ++k) {
       if (k >= 2) finalize(k - 2, b - 2 * static_cast<int>(gridDim.x));
-      src.bind(b);
-      res_build_x<T>(src, g.L, g.N, g.sizes32, X0 + (k & 1) * xstride, scan_scratch, g.errflag, ptid);
+      if (ptid < T) src.prefetch(b + static_cast<int>(gridDim.x), ptid);   // next batch's rows: HBM -> L2 now
+      res_build_x<T>(src, b, g.L, g.N, g.sizes32, X0 + (k & 1) * xstride, scan_scratch, g.errflag, ptid);
       mbar_arrive(&full[k & 1]);
     }
     for (int kk = max(0, k - 2); kk < k; ++kk) finalize(kk, static_cast<int>(blockIdx.x) + kk * static_cast<int>(gridDim.x));
   } else {
     // ------------------------------------------------------------ consumers
     const int lane = tid & 31, wid = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    ResSink<T> sink;
-    sink.table = table; sink.nl8 = nl8; sink.nl32 = g.nl32; sink.q = queues + wid * kRQueue; sink.lane = lane;
     bool table_ready = g.E_res == 0;
     int k = 0;
     for (int b = blockIdx.x; b < nb; b += gridDim.x, ++k) {
       const int buf = k & 1;
       if (!table_ready) { mbar_wait(tab, 0); table_ready = true; }
       mbar_wait(&full[buf], (k >> 1) & 1);
-      sink.X = X0 + buf * xstride;
-      sink.cnt = 0;
+      const uint32_t *X = X0 + buf * xstride;
+      double acc[T];
 #pragma unroll
-      for (int t = 0; t < T; ++t) sink.acc[t] = 0.0;
+      for (int t = 0; t < T; ++t) acc[t] = 0.0;
       for (int i = tid; i < g.E_res; i += kRPad) {
-        uint32_t p[kRUnroll]; bool hot[kRUnroll]; unsigned bal[kRUnroll];
+        uint32_t p[kRUnroll], n8[kRUnroll];
 #pragma unroll
-        for (int j = 0; j < kRUnroll; ++j) p[j] = table[i + j * kRCT];
+        for (int j = 0; j < kRUnroll; ++j) { p[j] = table[i + j * kRCT]; n8[j] = nl8[i + j * kRCT]; }
 #pragma unroll
-        for (int j = 0; j < kRUnroll; ++j) hot[j] = sink.test(p[j]);
-#pragma unroll
-        for (int j = 0; j < kRUnroll; ++j) bal[j] = __ballot_sync(0xffffffffu, hot[j]);
-        int base = sink.cnt;
-#pragma unroll
-        for (int j = 0; j < kRUnroll; ++j) {
-          if (hot[j]) sink.q[base + __popc(bal[j] & lt)] = static_cast<uint32_t>(i + j * kRCT);
-          base += __popc(bal[j]);
-        }
-        sink.cnt = base;
-        while (sink.cnt >= 32) {
-          __syncwarp();
-          sink.cnt -= 32;
-          sink.evaluate(sink.q[sink.cnt + lane]);
-          __syncwarp();
-        }
+        for (int j = 0; j < kRUnroll; ++j) res_pair_terms<T, SUB>(X, p[j], n8[j], acc);
       }
-      __syncwarp();
-      if (lane < sink.cnt) sink.evaluate(sink.q[lane]);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const double s = warp_sum(sink.acc[t]);
+        const double s = warp_sum(acc[t]);
         if (lane == 0) partial[(buf * kRC + wid) * T + t] = s;
       }
       __syncwarp();

@@ -1,0 +1,83 @@
+// term_probe.cu -- dev probe: SMSP cycles per warp-term of whole-term variants of
+//   acc += (0 < d <= LIM) ? n2 / d : 0      (d uint32, n2 double)
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o term_probe term_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#define LIM 20000000u
+__device__ __forceinline__ double u32_to_double(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+__device__ __forceinline__ double rcp64h(double d) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d)); return r; }
+__device__ __forceinline__ double cubic(double x, double r) { double e = fma(-x, r, 1.0); e = fma(e, e, e); return fma(r, e, r); }
+
+template <int V> __device__ __forceinline__ void term(double &acc, uint32_t d, double n2, int n2hi) {
+  if (V == 0) {          // kernel r1c: select d and the numerator's high word
+    const bool in = d - 1u < LIM;
+    const double r = cubic(u32_to_double(in ? d : 1u), rcp64h(u32_to_double(in ? d : 1u)));
+    acc = fma(__hiloint2double(in ? n2hi : 0, 0), r, acc);
+  } else if (V == 1) {   // no select on d; select the result (FSEL x2)
+    const bool in = d - 1u < LIM;
+    const double x = u32_to_double(d);
+    const double v = fma(n2, cubic(x, rcp64h(x)), acc);
+    acc = in ? v : acc;
+  } else if (V == 2) {   // V1 with I2F.F64.U32
+    const bool in = d - 1u < LIM;
+    const double x = (double)d;
+    const double v = fma(n2, cubic(x, rcp64h(x)), acc);
+    acc = in ? v : acc;
+  } else if (V == 3) {   // V1 with the seed's low word taken from x (any value works: 2^-19 seed)
+    const bool in = d - 1u < LIM;
+    const double x = u32_to_double(d);
+    const double r0 = __hiloint2double(__double2hiint(rcp64h(x)), __double2loint(x));
+    const double v = fma(n2, cubic(x, r0), acc);
+    acc = in ? v : acc;
+  } else if (V == 4) {   // d >= 1 guaranteed: test d <= LIM only, select numerator high word
+    const bool in = d <= LIM;
+    const double x = u32_to_double(d);
+    acc = fma(__hiloint2double(in ? n2hi : 0, 0), cubic(x, rcp64h(x)), acc);
+  } else if (V == 5) {   // V4 + seed low word from x
+    const bool in = d <= LIM;
+    const double x = u32_to_double(d);
+    const double r0 = __hiloint2double(__double2hiint(rcp64h(x)), __double2loint(x));
+    acc = fma(__hiloint2double(in ? n2hi : 0, 0), cubic(x, r0), acc);
+  }
+}
+
+template <int V> __global__ void throughput(double *out, int iters, uint32_t seed, int n2hi_in) {
+  constexpr int C = 16;
+  uint32_t d[C]; double acc[C];
+  const double n2 = __hiloint2double(n2hi_in, 0);
+#pragma unroll
+  for (int c = 0; c < C; ++c) { d[c] = seed + threadIdx.x * 977u + c * 131u + 1u; acc[c] = 0.0; }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      term<V>(acc[c], d[c], n2, n2hi_in);
+      d[c] = __usad(d[c], 12345u + i, 0u) + 1u;
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < C; ++c) s += acc[c];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int V> void run(double *buf, double clk_khz) {
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  printf("V%d", V);
+  for (int warps = 16; warps <= 32; warps *= 2) {
+    const int iters = 4096; float ms = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaEventRecord(a);
+      throughput<V><<<148, warps * 32>>>(buf, iters, 7u, 0x40340000);
+      cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
+    }
+    printf(" | %2d warps/SM: %.2f clk/warp-term/SMSP", warps, ms * 1e-3 * clk_khz * 1e3 / (iters * 16.0 * warps / 4.0));
+  }
+  printf("\n");
+}
+int main() {
+  double *buf; cudaMalloc(&buf, 148 * 1024 * 8);
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  run<0>(buf, clk); run<1>(buf, clk); run<2>(buf, clk); run<3>(buf, clk); run<4>(buf, clk); run<5>(buf, clk);
+  return 0;
+}

@@ -812,13 +812,18 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
           ra[i] = static_cast<uint32_t>(xa[x]); rb[i] = static_cast<uint32_t>(xb[x]);
           r8[i] = static_cast<uint8_t>(xn[x]);
         }
+        // storage order: consumer thread tid reads its kRUnroll entries of iteration I as one vector, so the
+        // logical entry I*kRPad + j*kRCT + tid lives at (I*kRCT + tid)*kRUnroll + j
+        auto phys = [](size_t i) { const size_t I = i / kRPad, r = i % kRPad; return (I * kRCT + r % kRCT) * kRUnroll + r / kRCT; };
+        std::vector<uint8_t> r8p(er + 16, 0);
+        for (size_t i = 0; i < er; ++i) r8p[phys(i)] = r8[i];
         AHX_CUDA(ctx, ctx->d_rnl8.reserve(er + 16));
-        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8.p, r8.data(), er + 16, cudaMemcpyHostToDevice, ctx->stream));
+        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8.p, r8p.data(), er + 16, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<uint32_t> rp(er);
         for (int ti = 0; ti < 3; ++ti) {   // one table per tours-per-batch T = 1, 2, 4: entries are byte offsets into X
           const uint32_t stride = 4u << ti;
           if (static_cast<uint64_t>(N) * stride > 65535u) continue;
-          for (size_t i = 0; i < er; ++i) rp[i] = (ra[i] * stride) | ((rb[i] * stride) << 16);
+          for (size_t i = 0; i < er; ++i) rp[phys(i)] = (ra[i] * stride) | ((rb[i] * stride) << 16);
           AHX_CUDA(ctx, ctx->d_rpairs[ti].reserve(er));
           AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs[ti].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
           AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // rp is reused

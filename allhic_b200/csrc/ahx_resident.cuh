@@ -7,6 +7,7 @@
 //                           bank-conflict-free order of order_pairs(), padded with
 //                           (0, 1, nlinks 0) entries to a multiple of kRCT * kRUnroll;
 //                           loaded ONCE per CTA by TMA bulk copies
+//   n2lut   double[256]     2n for n = 0..255 (the numerators)
 //   nl8     uint8[E_res]    nlinks of the entry (a pair with more than 255 links is split
 //                           over several entries: sum_i n_i / d == n / d up to rounding)
 //   X[2]    uint32[N*T]     2*mid of contig c in tour t at X[c*T + t], double buffered
@@ -40,7 +41,7 @@ constexpr int kRP = 8;                        // producer warps
 constexpr int kRCT = kRC * 32;                // consumer threads
 constexpr int kRPT = kRP * 32;                // producer threads
 constexpr int kRThreads = kRCT + kRPT;
-constexpr int kRUnroll = 4;                   // pairs per consumer lane per iteration
+constexpr int kRUnroll = 4;                   // pairs per consumer lane per iteration (one uint4 of the table)
 constexpr int kRPad = kRCT * kRUnroll;        // E_res is a multiple of this
 
 struct ResArgs {
@@ -56,7 +57,7 @@ __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~sta
 // dynamic shared memory of the resident kernel
 inline size_t res_smem_bytes(int T, int N, long long E_res) {
   return res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res)) + 2 * res_align16(4ull * N * T) +
-         8ull * 2 * kRC * T + 4ull * kRP * T + 8 * 8;
+         8ull * 256 + 8ull * 2 * kRC * T + 4ull * kRP * T + 8 * 8;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -83,6 +84,21 @@ struct ResDirect {
     __device__ __forceinline__ bool live() const { return ptr != nullptr; }
     __device__ __forceinline__ unsigned get(int i) const { return static_cast<unsigned>(ptr[i]); }
     __device__ __forceinline__ void put(int, unsigned) const {}
+    // positions i .. i+3 (i % 4 == 0), the ones at or beyond `end` as 0xFFFFFFFF; one vector load when the row allows it
+    __device__ __forceinline__ void get4(int i, int end, unsigned (&c)[4]) const {
+      if (i + 3 < end && (reinterpret_cast<uintptr_t>(ptr) & (4 * sizeof(IdxT) - 1)) == 0) {
+        if constexpr (sizeof(IdxT) == 4) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(ptr + i);
+          c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        } else {
+          const uint2 v = *reinterpret_cast<const uint2 *>(ptr + i);
+          c[0] = v.x & 0xffffu; c[1] = v.x >> 16; c[2] = v.y & 0xffffu; c[3] = v.y >> 16;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[e] = i + e < end ? static_cast<unsigned>(ptr[i + e]) : 0xFFFFFFFFu;
+      }
+    }
   };
   __device__ __forceinline__ int n_batches() const { return (P + T - 1) / T; }
   __device__ __forceinline__ int out_row(int batch, int t) const {
@@ -101,37 +117,39 @@ struct ResDirect {
 };
 
 // ---- producer: X[buf] for one batch ----------------------------------------------
-// Lane l of a producer warp works on tour t = l mod T at position offset l / T, so a
-// warp instruction covers 32/T consecutive positions of each of the T tours: the global
-// loads are sector-dense and the scatter X[c*T + t] spreads over all 32 banks (bank =
-// T*(c mod 32/T) + t).  Producer warp w owns positions [w*Q, (w+1)*Q).  Pass 1 sums the
-// sizes of the warp's range per tour, a named barrier publishes the 4 x T totals, pass 2
-// re-reads the range (L2/L1 hits), does a segmented warp scan per tour and scatters
-// 2*cum + size = 2*mid (evaluate.go:120-126).  2*sum(sizes) < 2^32 in x32 mode, so all
-// prefix sums run in 32 bits.
+// Lane l of a producer warp works on tour t = l mod T, on 4 consecutive positions at
+// offset 4 * (l / T): a warp instruction covers 4 * 32/T consecutive positions of each
+// of the T tours (vector loads, sector-dense), and the scatter X[c*T + t] spreads over
+// all 32 banks.  Producer warp w owns positions [w*Q, (w+1)*Q).  Pass 1 sums the sizes of
+// the warp's range per tour, a named barrier publishes the kRP x T totals, pass 2 re-reads
+// the range (L2/L1 hits), prefix-sums 4 positions in the lane and the lane totals with a
+// segmented warp scan per tour, and scatters 2*cum + size = 2*mid (evaluate.go:120-126).
+// 2*sum(sizes) < 2^32 in x32 mode, so all prefix sums run in 32 bits.
 template <int T, typename Src>
 __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
                                             uint32_t *scan_scratch /* kRP*T */, int *errflag, int ptid) {
-  constexpr int PPI = 32 / T;                    // positions per warp instruction
-  constexpr int kU = 16;                         // independent loads in flight per lane
+  constexpr int PPI = 4 * (32 / T);              // positions of one tour per warp instruction group
+  constexpr int kU = 4;                          // groups in flight per lane (16 positions)
   const int lane = ptid & 31, wid = ptid >> 5;
-  const int t = lane % T, sub = lane / T;
+  const int t = lane % T, sub = 4 * (lane / T);
   const auto cur = src.cursor(batch, t);
-  const bool live = cur.live();
   const int Q = ((L + kRP - 1) / kRP + PPI - 1) / PPI * PPI;
-  const int beg = min(L, wid * Q), end = min(L, beg + Q);
+  const int beg = min(L, wid * Q), end = cur.live() ? min(L, beg + Q) : beg;   // dead slot: every position is "beyond the end"
+  const int wend = min(L, beg + Q);                                            // warp-uniform loop bound
   bool bad = false;
   if (L < N) {   // sub-tour: contigs outside the tour must fail every window test
     for (int i = ptid; i < N * T; i += kRPT) X[i] = kInactiveX;
   }
   // pass 1: sum of sizes over this warp's range, per tour
   uint32_t local = 0;
-  for (int p0 = beg + sub; p0 < end; p0 += PPI * kU) {
-    unsigned c[kU];
+  for (int p0 = beg + sub; p0 - sub < wend; p0 += PPI * kU) {
+    unsigned c[kU][4];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) c[u] = (live && p0 + u * PPI < end) ? cur.get(p0 + u * PPI) : 0xFFFFFFFFu;
+    for (int u = 0; u < kU; ++u) cur.get4(p0 + u * PPI, end, c[u]);
 #pragma unroll
-    for (int u = 0; u < kU; ++u) local += c[u] < static_cast<unsigned>(N) ? __ldg(sizes32 + c[u]) : 0u;
+    for (int u = 0; u < kU; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) local += c[u][e] < static_cast<unsigned>(N) ? __ldg(sizes32 + c[u][e]) : 0u;
   }
 #pragma unroll
   for (int d = T; d < 32; d <<= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
@@ -140,24 +158,32 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
   uint32_t carry = 0;
 #pragma unroll
   for (int w = 0; w < kRP; ++w) carry += (w < wid) ? scan_scratch[w * T + t] : 0u;
-  // pass 2: segmented scan + scatter
-  for (int p0 = beg + sub; p0 - sub < end; p0 += PPI * kU) {
-    unsigned c[kU]; uint32_t sz[kU];
+  // pass 2: prefix sums + scatter
+  for (int p0 = beg + sub; p0 - sub < wend; p0 += PPI * kU) {
+    unsigned c[kU][4]; uint32_t sz[kU][4];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) c[u] = (live && p0 + u * PPI < end) ? cur.get(p0 + u * PPI) : 0xFFFFFFFFu;
+    for (int u = 0; u < kU; ++u) cur.get4(p0 + u * PPI, end, c[u]);
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool on = p0 + u * PPI + e < end;
+        if (on) cur.put(p0 + u * PPI + e, c[u][e]);
+        if (on && c[u][e] >= static_cast<unsigned>(N)) { bad = true; c[u][e] = 0xFFFFFFFFu; }
+        sz[u][e] = c[u][e] != 0xFFFFFFFFu ? __ldg(sizes32 + c[u][e]) : 0u;
+      }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const bool on = live && p0 + u * PPI < end;
-      if (on) cur.put(p0 + u * PPI, c[u]);
-      if (on && c[u] >= static_cast<unsigned>(N)) { bad = true; c[u] = 0xFFFFFFFFu; }
-      sz[u] = c[u] != 0xFFFFFFFFu ? __ldg(sizes32 + c[u]) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      uint32_t v = sz[u];
+      const uint32_t tot = sz[u][0] + sz[u][1] + sz[u][2] + sz[u][3];
+      uint32_t v = tot;
 #pragma unroll
       for (int d = T; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += n; }
-      if (c[u] != 0xFFFFFFFFu) X[static_cast<size_t>(c[u]) * T + t] = 2u * (carry + v - sz[u]) + sz[u];   // 2*cum + size
+      uint32_t cum = carry + v - tot;                                           // sizes before this lane's 4 positions
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (c[u][e] != 0xFFFFFFFFu) X[static_cast<size_t>(c[u][e]) * T + t] = 2u * cum + sz[u][e];   // 2*cum + size
+        cum += sz[u][e];
+      }
       carry += __shfl_sync(0xffffffffu, v, 32 - T + t);
     }
   }
@@ -179,7 +205,7 @@ __device__ __forceinline__ double rcp_pos(double x) {
 
 // acc[t] += nlinks / dist for one table entry:
 //   p  = byte offsets of the two contigs' coordinate groups in X: (a*4T) | (b*4T) << 16
-//   n8 = nlinks of the entry (<= 255)
+//   n2 = 2 * nlinks of the entry as a double (from the 256-entry table in shared memory)
 //   d  = |X_a - X_b| = 2 dist;  inside the window  <=>  0 < d <= 2 LIMIT  (evaluate.go:135-137)
 //   term = (2 nlinks) / d                                                  (evaluate.go:140)
 // The window mask is applied to the 32-bit reciprocal SEED: with r0 = 0 the cubic step
@@ -192,13 +218,12 @@ __device__ __forceinline__ double rcp_pos(double x) {
 // Issue-slot model measured with profiles/microbench/term_probe.cu: an fp64 instruction
 // costs 2 issue cycles, anything else 1.
 template <int T, bool SUB>
-__device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, uint32_t n8, double (&acc)[T]) {
+__device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, double n2, double (&acc)[T]) {
   using V = typename XVec<T>::type;
   uint32_t xa[T], xb[T];
   const unsigned char *Xb = reinterpret_cast<const unsigned char *>(X);
   x_unpack(*reinterpret_cast<const V *>(Xb + (p & 0xffffu)), xa);
   x_unpack(*reinterpret_cast<const V *>(Xb + (p >> 16)), xb);
-  const double n2 = u32_to_double(2u * n8);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const uint32_t d = __usad(xa[t], xb[t], 0u);
@@ -222,12 +247,14 @@ __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src
   uint32_t *X0 = reinterpret_cast<uint32_t *>(sp);
   const size_t xstride = res_align16(4ull * g.N * T) / 4;   // words between the two X buffers
   sp += 2 * res_align16(4ull * g.N * T);
+  double *n2lut = reinterpret_cast<double *>(sp); sp += 8ull * 256;                // n2lut[n] = 2n (numerators, evaluate.go:140)
   double *partial = reinterpret_cast<double *>(sp); sp += 8ull * 2 * kRC * T;      // [buf][warp][t]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 8 * 8;                  // full[2], done[2], tab
   uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(sp);
   uint64_t *full = bars, *done = bars + 2, *tab = bars + 4;
   const int tid = threadIdx.x;
   const int nb = src.n_batches();
+  if (tid < 256) n2lut[tid] = 2.0 * tid;
   if (tid == 0) {
     mbar_init(&full[0], kRPT); mbar_init(&full[1], kRPT);
     mbar_init(&done[0], kRC); mbar_init(&done[1], kRC);
@@ -249,7 +276,7 @@ __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src
     const int ptid = tid - kRCT;
     auto finalize = [&](int k, int batch) {
       const int buf = k & 1;
-      mbar_wait(&done[buf], (k >> 1) & 1);
+      mbar_wait_relaxed(&done[buf], (k >> 1) & 1);
       if (ptid < T) {
         double s = 0.0;
 #pragma unroll
@@ -279,12 +306,17 @@ __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src
       double acc[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) acc[t] = 0.0;
-      for (int i = tid; i < g.E_res; i += kRPad) {
-        uint32_t p[kRUnroll], n8[kRUnroll];
-#pragma unroll
-        for (int j = 0; j < kRUnroll; ++j) { p[j] = table[i + j * kRCT]; n8[j] = nl8[i + j * kRCT]; }
-#pragma unroll
-        for (int j = 0; j < kRUnroll; ++j) res_pair_terms<T, SUB>(X, p[j], n8[j], acc);
+      // entry j of thread tid in iteration I is stored at [(I*kRCT + tid)*4 + j]: one LDS.128 + one LDS.32
+      // fetch the thread's four entries and link counts (logical order: order_pairs(), ahx_core.cu)
+      const uint4 *table4 = reinterpret_cast<const uint4 *>(table);
+      const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(nl8);
+      for (int i = tid; i < g.E_res / kRUnroll; i += kRCT) {
+        const uint4 p = table4[i];
+        const uint32_t n = nl8x4[i];
+        res_pair_terms<T, SUB>(X, p.x, n2lut[n & 0xffu], acc);
+        res_pair_terms<T, SUB>(X, p.y, n2lut[(n >> 8) & 0xffu], acc);
+        res_pair_terms<T, SUB>(X, p.z, n2lut[(n >> 16) & 0xffu], acc);
+        res_pair_terms<T, SUB>(X, p.w, n2lut[n >> 24], acc);
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {

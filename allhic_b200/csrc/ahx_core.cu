@@ -437,9 +437,9 @@ static cudaError_t launch_res_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *
   const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  ResArgs g{ctx->d_rpairs[T == 4 ? 2 : T - 1].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, out, ctx->d_errflag.p};
+  ResArgs g{ctx->d_rpairs[T == 4 ? 2 : T - 1].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, ctx->d_errflag.p};
   ResDirect<T, IdxT> src{};
-  src.tours = tours; src.rows = rows; src.P = P; src.L = L;
+  src.tours = tours; src.rows = rows; src.P = P; src.L = L; src.out = out;
   const int nb = (P + T - 1) / T;
   kern<<<std::min(nb, ctx->sm_count), kRThreads, smem, s>>>(g, src);
   ctx->launches++;
@@ -709,6 +709,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   ctx->d_hof.release(); ctx->d_sel_idx.release(); ctx->d_sel_tours.release(); ctx->d_sel_fit.release(); ctx->d_taken.release();
   ctx->d_state.release(); ctx->d_plan.release(); ctx->d_pos.release(); ctx->d_cum.release(); ctx->d_S4.release(); ctx->d_trace.release();
   ctx->d_pairinfo.release(); ctx->d_stepacc.release(); ctx->d_counts.release();
+  ctx->d_rowof[0].release(); ctx->d_rowof[1].release(); ctx->d_sel_rows.release(); ctx->d_row_fit.release(); ctx->d_gbar.release(); ctx->d_used.release(); ctx->d_gmin.release();
   for (auto ev : ctx->chunk_ev) cudaEventDestroy(ev);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

@@ -101,6 +101,14 @@ struct ahx_ctx {
   ahx::DevBuf<int32_t> d_plan;         // per-offspring parent/info/p/q, mutated list, count
   bool ga_x32 = false;
   int ga_T = 1;
+  bool ga_res = false;                 // persistent resident-table kernel (ahx_ga_res.cuh): d_pop[0] is a pool of 2P rows
+  int ga_G = 0, ga_nbmax = 0;
+  size_t ga_smem = 0;
+  ahx::DevBuf<int32_t> d_rowof[2], d_sel_rows;
+  ahx::DevBuf<double> d_row_fit;
+  ahx::DevBuf<unsigned int> d_gbar;           // [0] grid barrier counter, [1] hall-of-fame index scratch
+  ahx::DevBuf<unsigned char> d_used;          // 3 byte maps of referenced pool rows
+  ahx::DevBuf<unsigned long long> d_gmin;
   std::vector<int32_t> ga_active_set;  // sorted contig ids of the initial tour
   double ga_ms = 0.0;
 

@@ -26,6 +26,7 @@
 
 #include "ahx_ctx.h"
 #include "ahx_device.cuh"
+#include "ahx_resident.cuh"
 
 namespace ahx {
 
@@ -92,13 +93,17 @@ __device__ inline int tournament_pair(const double *__restrict__ fit, int P, int
       for (int m = i; m > pos; --m) chosen[m] = chosen[m - 1];
       chosen[pos] = v;
       const int id = (banned >= 0 && v >= banned) ? v + 1 : v;
-      const double f = fit[id];
+      const double f = __ldcg(fit + id);   // written by other CTAs in an earlier generation of the same launch
       if (best < 0 || f < bestfit) { best = id; bestfit = f; }
     }
     winner = best; banned = best;
   }
   return winner;
 }
+
+}  // namespace ahx
+#include "ahx_ga_res.cuh"
+namespace ahx {
 
 template <typename Coo>
 __global__ void __launch_bounds__(kBlock) ga_generation_kernel(GaDev g) {
@@ -444,8 +449,8 @@ __global__ void scatter_rows_kernel(int *__restrict__ pop, const int *__restrict
   for (int i = threadIdx.x; i < L; i += blockDim.x) dst[i] = in[static_cast<size_t>(blockIdx.x) * L + i];
 }
 // After migrants were written and scored: refresh the hall of fame from fit[0..P).
-__global__ void __launch_bounds__(1024) hof_refresh_kernel(const double *__restrict__ fit, const int *__restrict__ pop, int P, int L,
-                                                           int *hof, GaState *st, int n_new_evals) {
+__global__ void __launch_bounds__(1024) hof_refresh_kernel(const double *__restrict__ fit, const int *__restrict__ pop, const int *__restrict__ rowof,
+                                                           int P, int L, int *hof, GaState *st, int n_new_evals) {
   __shared__ double sf[32];
   __shared__ int si[32];
   __shared__ int s_best, s_improved;
@@ -468,8 +473,10 @@ __global__ void __launch_bounds__(1024) hof_refresh_kernel(const double *__restr
     if (s_improved) { st->hof_fit = bf; st->updated = st->gen; st->stop = 0; }
   }
   __syncthreads();
-  if (s_improved)
-    for (int i = tid; i < L; i += blockDim.x) hof[i] = pop[static_cast<size_t>(s_best) * L + i];
+  if (s_improved) {
+    const int row = rowof ? rowof[s_best] : s_best;
+    for (int i = tid; i < L; i += blockDim.x) hof[i] = pop[static_cast<size_t>(row) * L + i];
+  }
 }
 
 __global__ void mutate_kernel(const int *__restrict__ in, int L, int op, int p, int q, int dir, int *__restrict__ out) {
@@ -512,6 +519,104 @@ static cudaError_t launch_apply(ahx_ctx *ctx, const GaDev &g, const GaPlan &pl, 
   const int n_copy = std::min(g.P, ctx->sm_count * 4);
   kern<<<n_eval + n_copy, kBlock, smem, s>>>(g, pl, n_eval, ctx->d_sizes32.p, static_cast<int>(ctx->E_pad), ctx->d_errflag.p);
   return cudaGetLastError();
+}
+
+// ---- persistent resident GA (ahx_ga_res.cuh) ----------------------------------------
+// Usable when the evaluate kernel's resident form is (32-bit coordinates, 16-bit contig
+// indices, table + coordinates + GA scratch fit one SM's shared memory), the tour covers
+// all contigs (L == N: distinct coordinates, see res_pair_terms) and the masks fit one
+// word per thread.  T: tours per batch; G: CTAs (one per SM at most).
+struct GaResCfg { int T = 0, G = 0, nbmax = 0; size_t smem = 0; };
+
+static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double mut_prob) {
+  GaResCfg c;
+  if (const char *env = getenv("AHX_GA_RES")) if (!atoi(env)) return c;
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0 || L != ctx->N || 2 * static_cast<int64_t>(P) > 32 * kGaMaxWords) return c;
+  const double expect = std::max(1.0, P * mut_prob);
+  auto try_T = [&](int t) {
+    if (static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) return false;
+    const int G = static_cast<int>(std::min<double>(ctx->sm_count, std::max(1.0, std::ceil(1.25 * expect / t))));
+    const int nbmax = ((P + t - 1) / t + G - 1) / G;
+    const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res) + ga_res_extra_bytes(P, t, nbmax);
+    if (smem + 1024 > ctx->smem_optin) return false;
+    c.T = t; c.G = G; c.nbmax = nbmax; c.smem = smem;
+    return true;
+  };
+  int want = expect >= 4.0 * ctx->sm_count ? 4 : (expect >= 2.0 * ctx->sm_count ? 2 : 1);
+  if (const char *env = getenv("AHX_GA_T")) { const int t = atoi(env); if (t == 1 || t == 2 || t == 4) want = t; }
+  for (int t = want; t >= 1; t >>= 1)
+    if (try_T(t)) return c;
+  return c;
+}
+
+__global__ void ga_res_init_kernel(GaRes q, const int *__restrict__ init, const double *__restrict__ f0) {
+  // MakeTour = r.Tour.Clone(): PopSize copies of one tour (evaluate.go:259-262) = P references to row 0
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.P; i += gridDim.x * blockDim.x) { q.rowof[0][i] = 0; q.fit[0][i] = f0[0]; }
+  const size_t ub = 2 * static_cast<size_t>(q.P), ubp = (ub + 31) / 32 * 32;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < 3 * ubp; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    q.used[i] = (i == 0) ? 1 : 0;   // generation 0 references row 0 only
+  if (blockIdx.x == 0 && threadIdx.x < 3) q.gmin[threadIdx.x] = ~0ULL;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *q.gidx = 0x7fffffff;
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < q.L; i += blockDim.x) { q.pool[i] = init[i]; q.hof[i] = init[i]; }
+    if (threadIdx.x == 0) {
+      GaState s{};
+      s.gen = 0; s.updated = 0; s.evals = 1; s.hof_fit = f0[0];
+      s.stop = (q.max_gens <= 0 || 0 - s.updated > q.ngen) ? 1 : 0;
+      s.ticket = 0; s.best_idx = 0;
+      *q.st = s;
+    }
+  }
+}
+
+static GaRes make_res(ahx_ctx *ctx) {
+  const GaDev d = make_dev(ctx);
+  GaRes q{};
+  q.P = d.P; q.L = d.L; q.k = d.k; q.nbmax = ctx->ga_nbmax;
+  q.mut_prob = d.mut_prob; q.key0 = d.key0; q.key1 = d.key1; q.ngen = d.ngen; q.max_gens = d.max_gens;
+  q.pool = ctx->d_pop[0].p; q.rowof[0] = ctx->d_rowof[0].p; q.rowof[1] = ctx->d_rowof[1].p;
+  q.fit[0] = ctx->d_fit[0].p; q.fit[1] = ctx->d_fit[1].p; q.hof = ctx->d_hof.p; q.st = ctx->d_state.p;
+  q.gbar = ctx->d_gbar.p;
+  q.used = ctx->d_used.p; q.gmin = ctx->d_gmin.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
+  return q;
+}
+
+template <int T>
+static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
+  auto kern = ga_persist_kernel<T>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->ga_smem));
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+  ResArgs g{ctx->d_rpairs[T == 4 ? 2 : T - 1].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, ctx->ga_L, ctx->d_errflag.p};
+  GaRes q = make_res(ctx);
+  void *args[] = {&g, &q, &n_gens};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(ctx->ga_G), dim3(kRThreads), args, ctx->ga_smem, s);
+}
+
+static int launch_persist(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
+  cudaError_t e;
+  switch (ctx->ga_T) {
+    case 4: e = launch_persist_t<4>(ctx, n_gens, s); break;
+    case 2: e = launch_persist_t<2>(ctx, n_gens, s); break;
+    default: e = launch_persist_t<1>(ctx, n_gens, s); break;
+  }
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "ga_persist_kernel launch");
+  ctx->launches++;
+  return AHX_OK;
+}
+
+// rows[i] = rowof[idx[i]]: physical rows of the selected individuals
+__global__ void rows_of_kernel(const int *__restrict__ rowof, const int *__restrict__ idx, int n, int *__restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rows[i] = rowof[idx[i]];
+}
+__global__ void scatter_fit_kernel(const double *__restrict__ by_row, const int *__restrict__ rows, const int *__restrict__ idx, int n, double *__restrict__ fit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fit[idx[i]] = by_row[rows[i]];
+}
+__global__ void set_rows_kernel(int *__restrict__ rowof, const int *__restrict__ idx, const int *__restrict__ rows, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rowof[idx[i]] = rows[i];
 }
 
 static int launch_generation(ahx_ctx *ctx, const GaDev &g, cudaStream_t s) {
@@ -589,6 +694,30 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   if (!(prm->mut_prob >= 0.0 && prm->mut_prob <= 1.0) || prm->ngen < 0 || prm->max_gens < 0 || prm->log_every < 0)
     return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: bad parameter");
   ctx->ga_prm = *prm; ctx->ga_L = L;
+  {
+    const GaResCfg rc = ga_res_config(ctx, prm->npop, L, prm->mut_prob);
+    ctx->ga_res = rc.T > 0;
+    if (ctx->ga_res) { ctx->ga_T = rc.T; ctx->ga_G = rc.G; ctx->ga_nbmax = rc.nbmax; ctx->ga_smem = rc.smem; }
+  }
+  if (ctx->ga_res) {
+    const size_t PL2 = 2 * static_cast<size_t>(prm->npop) * L;
+    AHX_CUDA(ctx, ctx->d_pop[0].reserve(PL2));
+    for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); AHX_CUDA(ctx, ctx->d_rowof[i].reserve(prm->npop)); }
+    AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1)); AHX_CUDA(ctx, ctx->d_gbar.reserve(2));
+    AHX_CUDA(ctx, ctx->d_used.reserve(3 * ((2 * static_cast<size_t>(prm->npop) + 31) / 32 * 32))); AHX_CUDA(ctx, ctx->d_gmin.reserve(3));
+    AHX_CUDA(ctx, ctx->d_tours.reserve(L)); AHX_CUDA(ctx, ctx->d_scores.reserve(1));
+    ctx->ga_ms = 0.0; ctx->ga_x32 = false;
+    ctx->ga_active_set.assign(init_tour, init_tour + L);
+    std::sort(ctx->ga_active_set.begin(), ctx->ga_active_set.end());
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, init_tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_eval_m_sparse(ctx, ctx->d_tours.p, nullptr, nullptr, 1, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+    ga_res_init_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(make_res(ctx), ctx->d_tours.p, ctx->d_scores.p);
+    ctx->launches++;
+    AHX_CUDA(ctx, cudaGetLastError());
+    AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ga_active = true;
+    return AHX_OK;
+  }
   ctx->ga_x32 = use_x32(ctx, L);
   ctx->ga_T = ctx->ga_x32 ? ga_T(ctx) : 1;
   if (const char *env = getenv("AHX_GA_T")) { const int t = atoi(env); if (ctx->ga_x32 && (t == 1 || t == 2 || t == 4)) ctx->ga_T = t; }
@@ -628,7 +757,18 @@ int ahx_ga_advance(ahx_ctx *ctx, int64_t n_gens, ahx_ga_stats *stats) {
   GaState hs{};
   if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
   int64_t left = n_gens;
-  while (left > 0 && !hs.stop) {
+  while (ctx->ga_res && left > 0 && !hs.stop) {
+    const int64_t batch = std::min<int64_t>(left, 8192);  // the kernel leaves its generation loop by itself when EarlyStop fires
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    if ((rc = launch_persist(ctx, batch, ctx->stream)) != AHX_OK) return rc;
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+    float ms = 0.f;
+    AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ctx->ga_ms += ms;
+    left -= batch;
+  }
+  while (!ctx->ga_res && left > 0 && !hs.stop) {
     const int64_t batch = std::min<int64_t>(left, 256);   // one host sync per batch to poll the stop flag
     AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
     for (int64_t i = 0; i < batch; ++i)
@@ -668,7 +808,14 @@ int ahx_ga_get_elites(ahx_ctx *ctx, int32_t n, int32_t *tours, double *fitness) 
   AHX_CUDA(ctx, ctx->d_sel_tours.reserve(static_cast<size_t>(n) * L));
   AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_taken.p, 0, P, ctx->stream));
   select_extreme_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, P, n, 0, ctx->d_taken.p, ctx->d_sel_idx.p, ctx->d_sel_fit.p);
-  gather_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[cur].p, ctx->d_sel_idx.p, L, ctx->d_sel_tours.p);
+  if (ctx->ga_res) {
+    AHX_CUDA(ctx, ctx->d_sel_rows.reserve(n));
+    rows_of_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_rowof[cur].p, ctx->d_sel_idx.p, n, ctx->d_sel_rows.p);
+    gather_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[0].p, ctx->d_sel_rows.p, L, ctx->d_sel_tours.p);
+    ctx->launches++;
+  } else {
+    gather_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[cur].p, ctx->d_sel_idx.p, L, ctx->d_sel_tours.p);
+  }
   ctx->launches += 2;
   AHX_CUDA(ctx, cudaGetLastError());
   AHX_CUDA(ctx, cudaMemcpyAsync(tours, ctx->d_sel_tours.p, sizeof(int32_t) * static_cast<size_t>(n) * L, cudaMemcpyDeviceToHost, ctx->stream));
@@ -698,11 +845,46 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sel_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(n) * L, cudaMemcpyHostToDevice, ctx->stream));
   AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_taken.p, 0, P, ctx->stream));
   select_extreme_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, P, n, 1, ctx->d_taken.p, ctx->d_sel_idx.p, ctx->d_sel_fit.p);
+  if (ctx->ga_res) {
+    // individuals are references to pool rows and several may share one: a migrant takes a row that
+    // the current generation does not reference, then the replaced individual points at it
+    std::vector<int32_t> rowof(P), freerows;
+    AHX_CUDA(ctx, cudaMemcpyAsync(rowof.data(), ctx->d_rowof[cur].p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint8_t> used(2 * static_cast<size_t>(P), 0);
+    for (int32_t i = 0; i < P; ++i) used[rowof[i]] = 1;
+    for (int32_t r = 0; r < 2 * P && static_cast<int32_t>(freerows.size()) < n; ++r) if (!used[r]) freerows.push_back(r);
+    AHX_CUDA(ctx, ctx->d_sel_rows.reserve(n)); AHX_CUDA(ctx, ctx->d_row_fit.reserve(2 * static_cast<size_t>(P)));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sel_rows.p, freerows.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+      // exact reference map of the edited generation (the kernel allocates fresh rows from its complement)
+      std::vector<int32_t> worst(n);
+      AHX_CUDA(ctx, cudaMemcpyAsync(worst.data(), ctx->d_sel_idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (int32_t i = 0; i < n; ++i) rowof[worst[i]] = freerows[i];
+      const size_t ubp = (2 * static_cast<size_t>(P) + 31) / 32 * 32;
+      std::vector<uint8_t> map(ubp, 0);
+      for (int32_t i = 0; i < P; ++i) map[rowof[i]] = 1;
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_used.p + static_cast<size_t>(hs.gen % 3) * ubp, map.data(), ubp, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    scatter_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[0].p, ctx->d_sel_rows.p, L, ctx->d_sel_tours.p);
+    set_rows_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_rowof[cur].p, ctx->d_sel_idx.p, ctx->d_sel_rows.p, n);
+    ctx->launches += 3;
+    AHX_CUDA(ctx, cudaGetLastError());
+    if ((rc = launch_eval_m_sparse(ctx, ctx->d_pop[0].p, nullptr, ctx->d_sel_rows.p, n, L, ctx->d_row_fit.p, ctx->stream)) != AHX_OK) return rc;
+    scatter_fit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_row_fit.p, ctx->d_sel_rows.p, ctx->d_sel_idx.p, n, ctx->d_fit[cur].p);
+    hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[0].p, ctx->d_rowof[cur].p, P, L, ctx->d_hof.p, ctx->d_state.p, n);
+    ctx->launches += 2;
+    AHX_CUDA(ctx, cudaGetLastError());
+    AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // freerows is stack-owned
+    return AHX_OK;
+  }
   scatter_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[cur].p, ctx->d_sel_idx.p, L, ctx->d_sel_tours.p);
   ctx->launches += 2;
   AHX_CUDA(ctx, cudaGetLastError());
   if ((rc = launch_eval_m_sparse(ctx, ctx->d_pop[cur].p, nullptr, ctx->d_sel_idx.p, n, L, ctx->d_fit[cur].p, ctx->stream)) != AHX_OK) return rc;
-  hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[cur].p, P, L, ctx->d_hof.p, ctx->d_state.p, n);
+  hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[cur].p, nullptr, P, L, ctx->d_hof.p, ctx->d_state.p, n);
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

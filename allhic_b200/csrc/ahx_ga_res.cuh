@@ -1,0 +1,341 @@
+// ahx_ga_res.cuh -- CLM.GARun (evaluate.go:258-315) as ONE persistent cooperative
+// kernel: many generations per launch, the pair table resident in shared memory for
+// the whole run, one grid barrier per generation.  Included by ahx_ga.cu after the
+// Philox / tournament / mutation-plan helpers.
+//
+// Population storage.  eaopt clones every selected individual and mutates a fraction
+// MutRate of the clones.  A clone that is not mutated is an exact copy
+// of its parent, so individuals are stored by reference: rowof[g & 1][i] is the
+// physical row of individual i of generation g in a pool of 2P rows.  An un-mutated
+// offspring inherits its parent's row id and fitness (no copy); a mutated offspring
+// gets a fresh row from the rows generation g does not reference (at least P of the 2P).
+// The k-th mutated offspring (ascending index) takes the k-th free row, so the layout
+// is a pure function of the seed.
+//
+// One generation, every CTA (G = gridDim.x, 24 warps):
+//   1. bit mask of the pool rows the current generation references (from a byte map in
+//      global memory that the CTAs filled while they built that generation) + word prefix
+//   2. slot table: for the mutated offspring this CTA scores (batch b -> CTA b mod G):
+//      offspring index (select on the mutation mask), tournament parents, mutation plan,
+//      fresh row (select on the free rows)
+//   3. the CTA's share of un-mutated offspring (o = c, c + G, ...): tournament, inherit
+//   4. res_run_batches: the coordinates of T offspring at a time are built straight from
+//      the parent rows through the mutation's index remap (the child rows are written on the
+//      way), consumers score them (ahx_resident.cuh); atomicMin of the new fitness values
+//   5. mutation mask of the NEXT generation (first Philox draw of each offspring; it does not
+//      depend on fitness, so it fills the wait for the slowest CTA)
+//   6. grid barrier
+//   7. bookkeeping (evaluate.go:287-306): only a mutated offspring can beat the hall of fame,
+//      so one load of the generation's minimum decides; an improvement (rare) costs a second
+//      barrier to agree on the lowest offspring index and copy its row
+// Scores do not depend on which tours share a batch (each tour has its own accumulators
+// and a fixed summation order), tournaments and plans are functions of (seed, generation,
+// offspring): the run is bit-identical for any grid size and any T.
+#ifndef AHX_GA_RES_CUH_
+#define AHX_GA_RES_CUH_
+
+namespace ahx {
+
+struct GaRes {
+  int P, L, k, nbmax;
+  double mut_prob;
+  uint32_t key0, key1;
+  long long ngen, max_gens;
+  int *pool;            // [2P][L]
+  int *rowof[2];        // [P]
+  double *fit[2];       // [P]
+  int *hof;             // [L]
+  GaState *st;
+  unsigned int *gbar;   // grid barrier counter, zero at launch
+  unsigned char *used;  // [3][pad32(2P)] byte maps: used[g % 3][r] = 1 iff generation g references pool row r
+  unsigned long long *gmin;   // [3] order-preserving key of the best fitness evaluated while building generation g (index g % 3)
+  int *gidx;            // lowest offspring index holding that fitness (0x7fffffff when idle)
+};
+
+// One mutated offspring: where it comes from, where it goes, and its mutation as ONE
+// branch-free index remap, new[i] = parent[src(i)] (the four operators of Tour.Mutate,
+// evaluate.go:157-218, are all of this form -- no divergence between the tours of a batch):
+//   src = i;  if (i - lo <u len) src = a*i + b;  if (i == sp) src = sv;  if (i == sp2) src = sv2;
+//   if (src >= L) src -= L
+struct GaSlot { int o, parent_row, child_row, lo, len, a, b, sp, sv, sp2, sv2, pad; };
+
+__device__ __forceinline__ void remap_of(const MutPlan &mp, int L, GaSlot *s) {
+  s->lo = 0; s->len = 0; s->a = 1; s->b = 0; s->sp = -1; s->sv = 0; s->sp2 = -1; s->sv2 = 0;
+  const int p = mp.p, q = mp.q;
+  switch (mp.op) {
+    case 0: s->sp = p; s->sv = q; s->sp2 = q; s->sv2 = p; break;                       // MutPermute: swap p, q
+    case 1: s->lo = 0; s->len = L; s->b = p; break;                                    // MutSplice: new[i] = old[(i + k) mod L]
+    case 2:                                                                            // MutInsertion
+      if (p != q) {
+        if (mp.dir) { s->lo = p + 1; s->len = q - p; s->b = -1; s->sp = p; s->sv = q; }   // pop q, insert at p
+        else { s->lo = p; s->len = q - p; s->b = 1; s->sp = q; s->sv = p; }               // pop p, insert at q
+      }
+      break;
+    case 3: s->lo = p; s->len = q - p + 1; s->a = -1; s->b = p + q; break;             // MutInversion: reverse [p, q]
+    default: break;
+  }
+}
+
+constexpr int kGaMaxWords = kRThreads;   // one mask word per thread in the block scans: 2P <= 32 * kRThreads
+
+inline size_t ga_res_extra_bytes(int P, int T, int nbmax) {
+  const size_t wm = (static_cast<size_t>(P) + 31) / 32, wr = (2 * static_cast<size_t>(P) + 31) / 32;
+  return res_align16(4 * (2 * wm + 2 * wr)) + sizeof(GaSlot) * static_cast<size_t>(nbmax) * T + 4 * (kRThreads / 32 + 1) + 64;
+}
+
+// order-preserving map double -> uint64 (for atomicMin on fitness values) and back
+__device__ __forceinline__ unsigned long long fit_key(double f) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(f));
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double key_fit(unsigned long long k) {
+  return __longlong_as_double(static_cast<long long>((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k));
+}
+
+template <int T>
+struct GaSrc {
+  const int *pool; int *pool_w; const GaSlot *slots; double *fitn; unsigned long long *gmin; int L;
+  struct Cursor {
+    const int *src; int *dst; int lo, len, a, b, sp, sv, sp2, sv2, L;
+    __device__ __forceinline__ bool live() const { return src != nullptr; }
+    __device__ __forceinline__ unsigned get(int i) const {
+      int s = static_cast<unsigned>(i - lo) < static_cast<unsigned>(len) ? a * i + b : i;
+      s = i == sp ? sv : s;
+      s = i == sp2 ? sv2 : s;
+      s -= s >= L ? L : 0;
+      return static_cast<unsigned>(__ldcg(src + s));
+    }
+    __device__ __forceinline__ void get4(int i, int end, unsigned (&c)[4]) const {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[e] = i + e < end ? get(i + e) : 0xFFFFFFFFu;
+    }
+    // Tour.Clone + Tour.Mutate: the child row is the parent row through the operator's index remap
+    __device__ __forceinline__ void put4(int i, int end, const unsigned (&c)[4]) const {
+      if (i + 3 < end && (reinterpret_cast<uintptr_t>(dst + i) & 15) == 0) {
+        *reinterpret_cast<uint4 *>(dst + i) = make_uint4(c[0], c[1], c[2], c[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (i + e < end) dst[i + e] = static_cast<int>(c[e]);
+      }
+    }
+  };
+  __device__ __forceinline__ Cursor cursor(int j, int t) const {
+    const GaSlot s = slots[j * T + t];
+    if (s.o < 0) return Cursor{nullptr, nullptr, 0, 0, 1, 0, -1, 0, -1, 0, L};
+    return Cursor{pool + static_cast<size_t>(s.parent_row) * L, pool_w + static_cast<size_t>(s.child_row) * L,
+                  s.lo, s.len, s.a, s.b, s.sp, s.sv, s.sp2, s.sv2, L};
+  }
+  __device__ __forceinline__ void prefetch(int, int) const {}
+  __device__ __forceinline__ void store(int j, int t, double score) const {
+    const int o = slots[j * T + t].o;
+    if (o >= 0) { fitn[o] = score; atomicMin(gmin, fit_key(score)); }
+  }
+};
+
+// Exclusive prefix sum of one value per thread over the kRThreads threads; *total gets
+// the sum.  scratch: kRThreads / 32 + 1 words.  Ends with a block barrier.
+__device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *scratch, uint32_t *total) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += n; }
+  if (lane == 31) scratch[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < kRThreads / 32 ? scratch[lane] : 0u, wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += n; }
+    if (lane < kRThreads / 32) scratch[lane] = wi - w;
+    if (lane == 31) scratch[kRThreads / 32] = wi;
+  }
+  __syncthreads();
+  const uint32_t r = scratch[wid] + incl - v;
+  *total = scratch[kRThreads / 32];
+  __syncthreads();
+  return r;
+}
+
+// index of the m-th (0-based) set bit of a mask given the exclusive word prefix
+__device__ __forceinline__ int mask_select(const uint32_t *mask, const uint32_t *pref, int nwords, uint32_t m, bool invert, int nbits) {
+  int lo = 0, hi = nwords - 1;
+  while (lo < hi) {   // last word whose prefix is <= m
+    const int mid = (lo + hi + 1) >> 1;
+    if (pref[mid] <= m) lo = mid; else hi = mid - 1;
+  }
+  uint32_t w = invert ? ~mask[lo] : mask[lo];
+  if (invert && lo == nwords - 1 && (nbits & 31)) w &= (1u << (nbits & 31)) - 1u;
+  return lo * 32 + static_cast<int>(__fns(w, 0, static_cast<int>(m - pref[lo]) + 1));
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned int *gbar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(gbar, 1u);
+    unsigned int v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar) : "memory"); } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Mutation flags of generation `gen` (first Philox draw of every offspring: eaopt's
+// rng.Float64() < MutRate) as a bit mask + exclusive word prefix; returns the count.
+// They do not depend on fitness, so they are computed one generation ahead, before the
+// grid barrier, where fast CTAs would otherwise idle.
+__device__ __forceinline__ uint32_t ga_mutation_mask(const GaRes &q, const Philox &ph, long long gen, uint32_t *mflag, uint32_t *mpref,
+                                                     uint32_t *scan_tmp) {
+  const int tid = threadIdx.x, WM = (q.P + 31) / 32;
+  const uint32_t glo = static_cast<uint32_t>(gen), ghi = static_cast<uint32_t>(gen >> 32);
+  for (int base = 0; base < WM * 32; base += kRThreads) {   // warp w of the round covers offspring [base + 32w, +32): one word
+    const int o = base + tid;
+    bool mut = false;
+    if (o < q.P) {
+      uint32_t r[4];
+      ph(glo, ghi, static_cast<uint32_t>(o), kStreamMutate, r);
+      mut = rand_unit(r[0], r[1]) < q.mut_prob;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, mut);
+    if ((tid & 31) == 0 && (o >> 5) < WM) mflag[o >> 5] = word;
+  }
+  __syncthreads();
+  uint32_t M = 0;
+  const uint32_t e1 = block_scan_u32(tid < WM ? __popc(mflag[tid]) : 0u, scan_tmp, &M);
+  if (tid < WM) mpref[tid] = e1;
+  __syncthreads();
+  return M;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaRes q, long long n_gens) {
+  extern __shared__ __align__(128) unsigned char smem_res[];
+  const ResSmem m = res_carve<T>(smem_res, g);
+  const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
+  const int WM = (q.P + 31) / 32, WR = (2 * q.P + 31) / 32;
+  uint32_t *mflag = reinterpret_cast<uint32_t *>(m.extra), *mpref = mflag + WM, *rused = mpref + WM, *rpref = rused + WR;
+  GaSlot *slots = reinterpret_cast<GaSlot *>(m.extra + res_align16(4ull * (2 * WM + 2 * WR)));
+  uint32_t *scan_tmp = reinterpret_cast<uint32_t *>(slots + static_cast<size_t>(q.nbmax) * T);   // kRThreads/32 + 1 words
+  res_init(m, g, true);
+  int kdone = 0;
+  bool table_ready = g.E_res == 0;
+  const Philox ph{q.key0, q.key1};
+  // generation state: identical in every thread of every CTA
+  long long gen = q.st->gen, updated = q.st->updated, evals = q.st->evals;
+  double hof_fit = q.st->hof_fit;
+  int stop = q.st->stop;
+  unsigned int nsync = 0;
+  const size_t ub = (2 * static_cast<size_t>(q.P) + 31) / 32 * 32;   // bytes per row-reference map (padded)
+  uint32_t M = (n_gens > 0 && !stop) ? ga_mutation_mask(q, ph, gen, mflag, mpref, scan_tmp) : 0u;
+  for (long long it = 0; it < n_gens && !stop; ++it) {
+    const int cur = static_cast<int>(gen & 1);
+    const int *rowc = q.rowof[cur]; int *rown = q.rowof[cur ^ 1];
+    const double *fitc = q.fit[cur]; double *fitn = q.fit[cur ^ 1];
+    const uint32_t glo = static_cast<uint32_t>(gen), ghi = static_cast<uint32_t>(gen >> 32);
+    const unsigned char *used_cur = q.used + static_cast<size_t>(gen % 3) * ub;          // rows generation `gen` references
+    unsigned char *used_new = q.used + static_cast<size_t>((gen + 1) % 3) * ub;        // marked while generation gen+1 is built
+    unsigned char *used_old = q.used + static_cast<size_t>((gen + 2) % 3) * ub;        // generation gen-1's map: nobody reads it any more
+    unsigned long long *gmin_new = q.gmin + (gen + 1) % 3;
+    // ---- rows the current generation references -> free-row select structure
+    uint32_t nfree = 0;
+    {
+      uint32_t w = 0;
+      if (tid < WR) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(used_cur + static_cast<size_t>(tid) * 32);
+        const int nvalid = min(32, 2 * q.P - tid * 32);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (nvalid <= h * 16) break;
+          const uint4 v = __ldcg(src + h);                       // the map is padded to a multiple of 32 bytes
+          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) w |= ((x[i] >> (8 * b)) & 1u) << (h * 16 + i * 4 + b);
+        }
+        rused[tid] = w;
+        w = ~w;
+        if (nvalid < 32) w &= (1u << nvalid) - 1u;
+      }
+      const uint32_t e2 = block_scan_u32(tid < WR ? __popc(w) : 0u, scan_tmp, &nfree);
+      if (tid < WR) rpref[tid] = e2;
+    }
+    __syncthreads();
+    // ---- slot table of the mutated offspring this CTA scores
+    const uint32_t Mcur = M;
+    const int nb_total = (static_cast<int>(Mcur) + T - 1) / T;
+    const int nb_local = cta < nb_total ? (nb_total - cta + G - 1) / G : 0;
+    for (int s = kRThreads - 1 - tid; s < nb_local * T; s += kRThreads) {   // threads from the top of the block; the clones below start at thread 0
+      const int j = s / T, t = s % T;
+      const uint32_t mi = static_cast<uint32_t>((cta + j * G) * T + t);
+      GaSlot sl{-1, 0, 0, 0, 0, 1, 0, -1, 0, -1, 0, 0};
+      if (mi < Mcur) {
+        const int o = mask_select(mflag, mpref, WM, mi, false, q.P);
+        const MutPlan mp = plan_mutation(ph, glo, ghi, static_cast<uint32_t>(o), q.mut_prob, q.L);
+        const int parent = tournament_pair(fitc, q.P, q.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
+        remap_of(mp, q.L, &sl);
+        sl.o = o; sl.parent_row = __ldcg(rowc + parent);
+        sl.child_row = mask_select(rused, rpref, WR, mi, true, 2 * q.P);
+        rown[o] = sl.child_row;
+        used_new[sl.child_row] = 1;
+      }
+      slots[s] = sl;
+    }
+    // ---- un-mutated offspring: inherit row and fitness (eaopt keeps Evaluated = true on clones)
+    for (int o = cta + tid * G; o < q.P; o += kRThreads * G) {
+      if ((mflag[o >> 5] >> (o & 31)) & 1u) continue;
+      const int parent = tournament_pair(fitc, q.P, q.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
+      const int row = __ldcg(rowc + parent);
+      rown[o] = row;
+      used_new[row] = 1;
+      fitn[o] = __ldcg(fitc + parent);
+    }
+    // ---- housekeeping for later generations: clear generation gen-1's map (this CTA's slice), reset its minimum
+    {
+      const size_t words = ub / 4;
+      uint32_t *z = reinterpret_cast<uint32_t *>(used_old);
+      for (size_t i = static_cast<size_t>(cta) * kRThreads + tid; i < words; i += static_cast<size_t>(G) * kRThreads) z[i] = 0u;
+      if (cta == 0 && tid == 0) q.gmin[(gen + 2) % 3] = ~0ULL;
+    }
+    __syncthreads();
+    // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
+    GaSrc<T> src{q.pool, q.pool, slots, fitn, gmin_new, q.L};
+    res_run_batches<T, false>(g, m, src, 0, 1, nb_local, kdone, table_ready);
+    // ---- next generation's mutation mask (independent of fitness): hidden behind the barrier wait
+    const long long ngen_now = gen + 1;
+    const bool last = (it + 1 >= n_gens) || ngen_now >= q.max_gens;
+    __syncthreads();
+    if (!last) M = ga_mutation_mask(q, ph, ngen_now, mflag, mpref, scan_tmp);
+    ++nsync;
+    grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
+    // ---- bookkeeping (evaluate.go:287-306).  Clones are copies of individuals that already exist, so
+    // only a mutated offspring can beat the hall of fame: compare the minimum over this generation's
+    // evaluations; on a (rare) improvement the owners of that fitness agree on the lowest offspring index.
+    const unsigned long long kmin = __ldcg(gmin_new);
+    if (kmin < fit_key(hof_fit)) {          // updateHallOfFame keeps the best ever; currentBest > *best
+      hof_fit = key_fit(kmin); updated = ngen_now;
+      for (int s = tid; s < nb_local * T; s += kRThreads) {
+        const int o = slots[s].o;
+        if (o >= 0 && fit_key(__ldcg(fitn + o)) == kmin) atomicMin(q.gidx, o);
+      }
+      ++nsync;
+      grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
+      if (cta == 0) {
+        const int bi = __ldcg(q.gidx);
+        const int *best_row = q.pool + static_cast<size_t>(__ldcg(rown + bi)) * q.L;
+        for (int i = tid; i < q.L; i += kRThreads) q.hof[i] = __ldcg(best_row + i);
+        __syncthreads();
+        if (tid == 0) { q.st->best_idx = bi; *q.gidx = 0x7fffffff; }   // next use is at least one grid barrier away
+      }
+    }
+    evals += Mcur;
+    if (ngen_now - updated > q.ngen || ngen_now >= q.max_gens) stop = 1;
+    gen = ngen_now;
+  }
+  if (cta == 0 && tid == 0) {
+    q.st->gen = gen; q.st->updated = updated; q.st->evals = evals; q.st->hof_fit = hof_fit; q.st->stop = stop;
+  }
+}
+
+}  // namespace ahx
+
+#endif  // AHX_GA_RES_CUH_

@@ -49,7 +49,6 @@ struct ResArgs {
   const uint8_t *nl8;         // [E_res]
   const uint32_t *sizes32;    // [N]
   int E_res, N, L;
-  double *out;
   int *errflag;
 };
 
@@ -57,7 +56,7 @@ __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~sta
 // dynamic shared memory of the resident kernel
 inline size_t res_smem_bytes(int T, int N, long long E_res) {
   return res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res)) + 2 * res_align16(4ull * N * T) +
-         8ull * 256 + 8ull * 2 * kRC * T + 4ull * kRP * T + 8 * 8;
+         8ull * 256 + 8ull * 2 * kRC * T + res_align16(4ull * (kRC + kRP) * T) + 8 * 8;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -74,16 +73,17 @@ __device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes) {
 // ---- batch sources -------------------------------------------------------------
 // A source maps (batch, slot t) to a tour: n_batches(), out_row(batch, t) (-1: slot
 // unused, nothing to write) and cursor(batch, t), a per-lane view of that tour with
-// live(), get(i) = contig at position i, put(i, c) (lets the GA write the offspring
-// row while it is being read).
+// live(), get4(i, end, c) = contigs at positions i..i+3 and put4(i, end, c) (lets the GA
+// write the offspring row while it is being read), store(batch, t, score).
 template <int T, typename IdxT>
 struct ResDirect {
   const IdxT *tours; const int *rows; int P, L;
+  double *out;
   struct Cursor {
     const IdxT *ptr;
     __device__ __forceinline__ bool live() const { return ptr != nullptr; }
     __device__ __forceinline__ unsigned get(int i) const { return static_cast<unsigned>(ptr[i]); }
-    __device__ __forceinline__ void put(int, unsigned) const {}
+    __device__ __forceinline__ void put4(int, int, const unsigned (&)[4]) const {}
     // positions i .. i+3 (i % 4 == 0), the ones at or beyond `end` as 0xFFFFFFFF; one vector load when the row allows it
     __device__ __forceinline__ void get4(int i, int end, unsigned (&c)[4]) const {
       if (i + 3 < end && (reinterpret_cast<uintptr_t>(ptr) & (4 * sizeof(IdxT) - 1)) == 0) {
@@ -109,6 +109,10 @@ struct ResDirect {
     const int r = out_row(batch, t);
     return Cursor{r >= 0 ? tours + static_cast<size_t>(r) * L : nullptr};
   }
+  __device__ __forceinline__ void store(int batch, int t, double score) const {
+    const int r = out_row(batch, t);
+    if (r >= 0) out[r] = score;
+  }
   // asks the L2 for the rows of a later batch (called by T lanes, one row each)
   __device__ __forceinline__ void prefetch(int batch, int t) const {
     const int r = batch < n_batches() ? out_row(batch, t) : -1;
@@ -125,20 +129,22 @@ struct ResDirect {
 // the range (L2/L1 hits), prefix-sums 4 positions in the lane and the lane totals with a
 // segmented warp scan per tour, and scatters 2*cum + size = 2*mid (evaluate.go:120-126).
 // 2*sum(sizes) < 2^32 in x32 mode, so all prefix sums run in 32 bits.
-template <int T, typename Src>
+// NW warps build one batch together (the kRP producer warps in steady state, all kRC + kRP
+// warps for the first batch of a call, when nothing else can run yet); BAR: named barrier.
+template <int T, int NW, int BAR, typename Src>
 __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
-                                            uint32_t *scan_scratch /* kRP*T */, int *errflag, int ptid) {
+                                            uint32_t *scan_scratch /* NW*T */, int *errflag, int ptid) {
   constexpr int PPI = 4 * (32 / T);              // positions of one tour per warp instruction group
   constexpr int kU = 4;                          // groups in flight per lane (16 positions)
   const int lane = ptid & 31, wid = ptid >> 5;
   const int t = lane % T, sub = 4 * (lane / T);
   const auto cur = src.cursor(batch, t);
-  const int Q = ((L + kRP - 1) / kRP + PPI - 1) / PPI * PPI;
+  const int Q = ((L + NW - 1) / NW + PPI - 1) / PPI * PPI;
   const int beg = min(L, wid * Q), end = cur.live() ? min(L, beg + Q) : beg;   // dead slot: every position is "beyond the end"
   const int wend = min(L, beg + Q);                                            // warp-uniform loop bound
   bool bad = false;
   if (L < N) {   // sub-tour: contigs outside the tour must fail every window test
-    for (int i = ptid; i < N * T; i += kRPT) X[i] = kInactiveX;
+    for (int i = ptid; i < N * T; i += NW * 32) X[i] = kInactiveX;
   }
   // pass 1: sum of sizes over this warp's range, per tour
   uint32_t local = 0;
@@ -154,21 +160,20 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
 #pragma unroll
   for (int d = T; d < 32; d <<= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
   if (lane < T) scan_scratch[wid * T + lane] = local;
-  named_bar_sync(1, kRPT);
+  named_bar_sync(BAR, NW * 32);
   uint32_t carry = 0;
 #pragma unroll
-  for (int w = 0; w < kRP; ++w) carry += (w < wid) ? scan_scratch[w * T + t] : 0u;
+  for (int w = 0; w < NW; ++w) carry += (w < wid) ? scan_scratch[w * T + t] : 0u;
   // pass 2: prefix sums + scatter
   for (int p0 = beg + sub; p0 - sub < wend; p0 += PPI * kU) {
     unsigned c[kU][4]; uint32_t sz[kU][4];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) cur.get4(p0 + u * PPI, end, c[u]);
+    for (int u = 0; u < kU; ++u) { cur.get4(p0 + u * PPI, end, c[u]); cur.put4(p0 + u * PPI, end, c[u]); }
 #pragma unroll
     for (int u = 0; u < kU; ++u)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const bool on = p0 + u * PPI + e < end;
-        if (on) cur.put(p0 + u * PPI + e, c[u][e]);
         if (on && c[u][e] >= static_cast<unsigned>(N)) { bad = true; c[u][e] = 0xFFFFFFFFu; }
         sz[u][e] = c[u][e] != 0xFFFFFFFFu ? __ldg(sizes32 + c[u][e]) : 0u;
       }
@@ -188,7 +193,7 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
     }
   }
   if (bad) *errflag = 1;
-  named_bar_sync(1, kRPT);   // scan_scratch may be rewritten by the next batch; X[buf] is complete
+  named_bar_sync(BAR, NW * 32);   // scan_scratch may be rewritten by the next batch; X[buf] is complete
 }
 
 // ---- consumer: every stored pair x T tours, branch-free ----------------------------
@@ -238,95 +243,135 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
   }
 }
 
-template <int T, bool SUB, typename Src>
-__global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src src) {
-  extern __shared__ __align__(128) unsigned char smem_res[];
-  unsigned char *sp = smem_res;
-  uint32_t *table = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * g.E_res);
-  uint8_t *nl8 = sp; sp += res_align16(static_cast<size_t>(g.E_res));
-  uint32_t *X0 = reinterpret_cast<uint32_t *>(sp);
-  const size_t xstride = res_align16(4ull * g.N * T) / 4;   // words between the two X buffers
+// ---- shared-memory layout and the batch loop, shared by the evaluate kernel and the
+// ---- persistent GA kernel (ahx_ga_res.cuh) ------------------------------------------
+struct ResSmem {
+  uint32_t *table; uint8_t *nl8; uint32_t *X0; size_t xstride;
+  double *n2lut, *partial; uint64_t *full, *done, *tab; uint32_t *scan_scratch;
+  unsigned char *extra;      // first byte after the evaluate layout (GA scratch)
+};
+
+template <int T>
+__device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g) {
+  ResSmem m;
+  m.table = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * g.E_res);
+  m.nl8 = sp; sp += res_align16(static_cast<size_t>(g.E_res));
+  m.X0 = reinterpret_cast<uint32_t *>(sp);
+  m.xstride = res_align16(4ull * g.N * T) / 4;   // words between the two X buffers
   sp += 2 * res_align16(4ull * g.N * T);
-  double *n2lut = reinterpret_cast<double *>(sp); sp += 8ull * 256;                // n2lut[n] = 2n (numerators, evaluate.go:140)
-  double *partial = reinterpret_cast<double *>(sp); sp += 8ull * 2 * kRC * T;      // [buf][warp][t]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 8 * 8;                  // full[2], done[2], tab
-  uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(sp);
-  uint64_t *full = bars, *done = bars + 2, *tab = bars + 4;
+  m.n2lut = reinterpret_cast<double *>(sp); sp += 8ull * 256;                // n2lut[n] = 2n (numerators, evaluate.go:140)
+  m.partial = reinterpret_cast<double *>(sp); sp += 8ull * 2 * kRC * T;      // [buf][warp][t]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 8 * 8;            // full[2], done[2], tab
+  m.full = bars; m.done = bars + 2; m.tab = bars + 4;
+  m.scan_scratch = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * (kRC + kRP) * T);
+  m.extra = sp;
+  return m;
+}
+
+// Called by all threads once, before the first res_run_batches: barriers, the numerator
+// table, and the TMA bulk copies of the pair table (they land while the first batch's
+// coordinates are being built).  Ends with a block-wide barrier.
+__device__ __forceinline__ void res_init(const ResSmem &m, const ResArgs &g, bool load_table) {
   const int tid = threadIdx.x;
-  const int nb = src.n_batches();
-  if (tid < 256) n2lut[tid] = 2.0 * tid;
+  if (tid < 256) m.n2lut[tid] = 2.0 * tid;
   if (tid == 0) {
-    mbar_init(&full[0], kRPT); mbar_init(&full[1], kRPT);
-    mbar_init(&done[0], kRC); mbar_init(&done[1], kRC);
-    mbar_init(tab, 1);
+    mbar_init(&m.full[0], kRPT); mbar_init(&m.full[1], kRPT);
+    mbar_init(&m.done[0], kRC); mbar_init(&m.done[1], kRC);
+    mbar_init(m.tab, 1);
     mbar_init_fence();
-    if (static_cast<int>(blockIdx.x) < nb && g.E_res > 0) {
-      // the pair table streams in while the producers build the first batch
+    if (load_table && g.E_res > 0) {
       const uint32_t tb = 4u * static_cast<uint32_t>(g.E_res), nbytes = static_cast<uint32_t>(res_align16(static_cast<size_t>(g.E_res)));
-      mbar_expect_tx(tab, tb + nbytes);
+      mbar_expect_tx(m.tab, tb + nbytes);
       for (uint32_t off = 0; off < tb; off += 32768u)
-        bulk_copy_g2s(reinterpret_cast<unsigned char *>(table) + off, reinterpret_cast<const unsigned char *>(g.pairs) + off, min(32768u, tb - off), tab);
+        bulk_copy_g2s(reinterpret_cast<unsigned char *>(m.table) + off, reinterpret_cast<const unsigned char *>(g.pairs) + off, min(32768u, tb - off), m.tab);
       for (uint32_t off = 0; off < nbytes; off += 32768u)
-        bulk_copy_g2s(nl8 + off, g.nl8 + off, min(32768u, nbytes - off), tab);
+        bulk_copy_g2s(m.nl8 + off, g.nl8 + off, min(32768u, nbytes - off), m.tab);
     }
   }
   __syncthreads();
+}
+
+// Scores batches first, first + stride, ... < nb of `src`.  Called by all kRThreads
+// threads; `kdone` counts the batches this CTA has pushed through the X buffers since
+// res_init (it carries the mbarrier phases from one call to the next) and must be the
+// same in every thread.  Returns with all scores stored and both X buffers free.
+//   src.cursor(batch, t)          tour in slot t of the batch (producer side)
+//   src.prefetch(batch, t)        optional L2 prefetch of a later batch
+//   src.store(batch, t, score)    called once per slot with the finished score
+template <int T, bool SUB, typename Src>
+__device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem &m, const Src &src, int first, int stride, int nb,
+                                                int &kdone, bool &table_ready) {
+  const int tid = threadIdx.x;
+  const int k0 = kdone;
+  int k = k0;
+  // first batch of the call: nobody has anything to score yet, so all 24 warps build its coordinates
+  // (a third of the latency of the 8 producer warps); both X buffers are free here.  Producer thread
+  // p of the steady state is thread kRCT + p; in the joint build the thread index is just tid.
+  if (first < nb) res_build_x<T, kRC + kRP, 2>(src, first, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
   if (tid >= kRCT) {
     // ------------------------------------------------------------ producers
     const int ptid = tid - kRCT;
-    auto finalize = [&](int k, int batch) {
-      const int buf = k & 1;
-      mbar_wait_relaxed(&done[buf], (k >> 1) & 1);
+    auto finalize = [&](int kk, int batch) {
+      const int buf = kk & 1;
+      mbar_wait_relaxed(&m.done[buf], (kk >> 1) & 1);
       if (ptid < T) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kRC; ++w) s += partial[(buf * kRC + w) * T + ptid];
-        const int row = src.out_row(batch, ptid);
-        if (row >= 0) g.out[row] = 0.0 - s;   // score starts at +0.0 and only subtracts (evaluate.go:128,140)
+        for (int w = 0; w < kRC; ++w) s += m.partial[(buf * kRC + w) * T + ptid];
+        src.store(batch, ptid, 0.0 - s);   // score starts at +0.0 and only subtracts (evaluate.go:128,140)
       }
     };
-    int k = 0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x, ++k) {
-      if (k >= 2) finalize(k - 2, b - 2 * static_cast<int>(gridDim.x));
-      if (ptid < T) src.prefetch(b + static_cast<int>(gridDim.x), ptid);   // next batch's rows: HBM -> L2 now
-      res_build_x<T>(src, b, g.L, g.N, g.sizes32, X0 + (k & 1) * xstride, scan_scratch, g.errflag, ptid);
-      mbar_arrive(&full[k & 1]);
+    for (int b = first; b < nb; b += stride, ++k) {
+      if (k - k0 >= 2) finalize(k - 2, b - 2 * stride);
+      if (ptid < T) src.prefetch(b + stride, ptid);   // next batch's rows: HBM -> L2 now
+      if (k > k0) res_build_x<T, kRP, 1>(src, b, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
+      mbar_arrive(&m.full[k & 1]);
     }
-    for (int kk = max(0, k - 2); kk < k; ++kk) finalize(kk, static_cast<int>(blockIdx.x) + kk * static_cast<int>(gridDim.x));
+    for (int kk = max(k0, k - 2); kk < k; ++kk) finalize(kk, first + (kk - k0) * stride);
   } else {
     // ------------------------------------------------------------ consumers
     const int lane = tid & 31, wid = tid >> 5;
-    bool table_ready = g.E_res == 0;
-    int k = 0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x, ++k) {
+    for (int b = first; b < nb; b += stride, ++k) {
       const int buf = k & 1;
-      if (!table_ready) { mbar_wait(tab, 0); table_ready = true; }
-      mbar_wait(&full[buf], (k >> 1) & 1);
-      const uint32_t *X = X0 + buf * xstride;
+      if (!table_ready) { mbar_wait(m.tab, 0); table_ready = true; }
+      mbar_wait(&m.full[buf], (k >> 1) & 1);
+      const uint32_t *X = m.X0 + buf * m.xstride;
       double acc[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) acc[t] = 0.0;
       // entry j of thread tid in iteration I is stored at [(I*kRCT + tid)*4 + j]: one LDS.128 + one LDS.32
       // fetch the thread's four entries and link counts (logical order: order_pairs(), ahx_core.cu)
-      const uint4 *table4 = reinterpret_cast<const uint4 *>(table);
-      const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(nl8);
+      const uint4 *table4 = reinterpret_cast<const uint4 *>(m.table);
+      const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(m.nl8);
       for (int i = tid; i < g.E_res / kRUnroll; i += kRCT) {
         const uint4 p = table4[i];
         const uint32_t n = nl8x4[i];
-        res_pair_terms<T, SUB>(X, p.x, n2lut[n & 0xffu], acc);
-        res_pair_terms<T, SUB>(X, p.y, n2lut[(n >> 8) & 0xffu], acc);
-        res_pair_terms<T, SUB>(X, p.z, n2lut[(n >> 16) & 0xffu], acc);
-        res_pair_terms<T, SUB>(X, p.w, n2lut[n >> 24], acc);
+        res_pair_terms<T, SUB>(X, p.x, m.n2lut[n & 0xffu], acc);
+        res_pair_terms<T, SUB>(X, p.y, m.n2lut[(n >> 8) & 0xffu], acc);
+        res_pair_terms<T, SUB>(X, p.z, m.n2lut[(n >> 16) & 0xffu], acc);
+        res_pair_terms<T, SUB>(X, p.w, m.n2lut[n >> 24], acc);
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         const double s = warp_sum(acc[t]);
-        if (lane == 0) partial[(buf * kRC + wid) * T + t] = s;
+        if (lane == 0) m.partial[(buf * kRC + wid) * T + t] = s;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&done[buf]);
+      if (lane == 0) mbar_arrive(&m.done[buf]);
     }
   }
+  kdone = k;
+}
+
+template <int T, bool SUB, typename Src>
+__global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src src) {
+  extern __shared__ __align__(128) unsigned char smem_res[];
+  const ResSmem m = res_carve<T>(smem_res, g);
+  const int nb = src.n_batches();
+  res_init(m, g, static_cast<int>(blockIdx.x) < nb);
+  int kdone = 0;
+  bool table_ready = g.E_res == 0;
+  res_run_batches<T, SUB>(g, m, src, blockIdx.x, gridDim.x, nb, kdone, table_ready);
 }
 
 }  // namespace ahx

@@ -20,6 +20,7 @@
 //   4. the last CTA to finish (atomic ticket) takes the arg-min of the new
 //      generation, updates the hall of fame / generation counters / stop flag.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -528,6 +529,19 @@ static cudaError_t launch_apply(ahx_ctx *ctx, const GaDev &g, const GaPlan &pl, 
 // word per thread.  T: tours per batch; G: CTAs (one per SM at most).
 struct GaResCfg { int T = 0, G = 0, nbmax = 0; size_t smem = 0; };
 
+// X[c] = 2*cumSum + size = 2*mid of every contig of a full tour (evaluate.go:120-126), what the
+// evaluate kernel's producers compute on the device; the GA keeps one such row per pool row.
+static std::vector<uint32_t> tour_coordinates(const ahx_ctx *ctx, int32_t L, const int32_t *tour) {
+  std::vector<uint32_t> x(ctx->N, kInactiveX);
+  uint64_t cum = 0;
+  for (int32_t i = 0; i < L; ++i) {
+    const uint64_t sz = static_cast<uint64_t>(ctx->h_sizes[tour[i]]);
+    x[tour[i]] = static_cast<uint32_t>(2 * cum + sz);
+    cum += sz;
+  }
+  return x;
+}
+
 static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double mut_prob) {
   GaResCfg c;
   if (const char *env = getenv("AHX_GA_RES")) if (!atoi(env)) return c;
@@ -574,6 +588,8 @@ static GaRes make_res(ahx_ctx *ctx) {
   GaRes q{};
   q.P = d.P; q.L = d.L; q.k = d.k; q.nbmax = ctx->ga_nbmax;
   q.mut_prob = d.mut_prob; q.key0 = d.key0; q.key1 = d.key1; q.ngen = d.ngen; q.max_gens = d.max_gens;
+  q.xpool = ctx->d_xpool.p; q.sizes32 = ctx->d_sizes32.p;
+  { long long tot = 0; for (int64_t z : ctx->h_sizes) tot += z; q.total2 = static_cast<uint32_t>(2 * tot); }
   q.pool = ctx->d_pop[0].p; q.rowof[0] = ctx->d_rowof[0].p; q.rowof[1] = ctx->d_rowof[1].p;
   q.fit[0] = ctx->d_fit[0].p; q.fit[1] = ctx->d_fit[1].p; q.hof = ctx->d_hof.p; q.st = ctx->d_state.p;
   q.gbar = ctx->d_gbar.p;
@@ -711,6 +727,12 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
     std::sort(ctx->ga_active_set.begin(), ctx->ga_active_set.end());
     AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, init_tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = launch_eval_m_sparse(ctx, ctx->d_tours.p, nullptr, nullptr, 1, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+    {
+      AHX_CUDA(ctx, ctx->d_xpool.reserve(2 * static_cast<size_t>(prm->npop) * ctx->N));
+      const std::vector<uint32_t> x0 = tour_coordinates(ctx, L, init_tour);
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_xpool.p, x0.data(), sizeof(uint32_t) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // x0 is stack-owned
+    }
     ga_res_init_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(make_res(ctx), ctx->d_tours.p, ctx->d_scores.p);
     ctx->launches++;
     AHX_CUDA(ctx, cudaGetLastError());
@@ -869,6 +891,11 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
       AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     scatter_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[0].p, ctx->d_sel_rows.p, L, ctx->d_sel_tours.p);
+    for (int32_t m = 0; m < n; ++m) {   // the migrants' coordinate rows
+      const std::vector<uint32_t> xm = tour_coordinates(ctx, L, tours + static_cast<size_t>(m) * L);
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_xpool.p + static_cast<size_t>(freerows[m]) * ctx->N, xm.data(), sizeof(uint32_t) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     set_rows_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_rowof[cur].p, ctx->d_sel_idx.p, ctx->d_sel_rows.p, n);
     ctx->launches += 3;
     AHX_CUDA(ctx, cudaGetLastError());
@@ -888,6 +915,44 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AHX_OK;
+}
+
+int ahx_ga_selfcheck(ahx_ctx *ctx, int64_t *n_bad) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!ctx->ga_active || !n_bad) return fail(ctx, AHX_ERR_STATE, "ahx_ga_selfcheck: no active GA run");
+  *n_bad = 0;
+  GaState hs{};
+  if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
+  const int cur = static_cast<int>(hs.gen & 1), P = ctx->ga_prm.npop, L = ctx->ga_L, N = ctx->N;
+  std::vector<int32_t> rowof(P), tour(L);
+  std::vector<uint32_t> xrow(N);
+  std::vector<double> fit(P);
+  AHX_CUDA(ctx, cudaMemcpy(fit.data(), ctx->d_fit[cur].p, sizeof(double) * P, cudaMemcpyDeviceToHost));
+  if (ctx->ga_res) AHX_CUDA(ctx, cudaMemcpy(rowof.data(), ctx->d_rowof[cur].p, sizeof(int32_t) * P, cudaMemcpyDeviceToHost));
+  // re-score every individual's stored tour with the evaluate kernel (population laid out row by row)
+  AHX_CUDA(ctx, ctx->d_tours.reserve(static_cast<size_t>(P) * L)); AHX_CUDA(ctx, ctx->d_scores.reserve(P));
+  for (int i = 0; i < P; ++i) {
+    const int32_t *src = ctx->ga_res ? ctx->d_pop[0].p + static_cast<size_t>(rowof[i]) * L : ctx->d_pop[cur].p + static_cast<size_t>(i) * L;
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p + static_cast<size_t>(i) * L, src, sizeof(int32_t) * L, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if ((rc = launch_eval_m_sparse(ctx, ctx->d_tours.p, nullptr, nullptr, P, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+  std::vector<double> again(P);
+  AHX_CUDA(ctx, cudaMemcpyAsync(again.data(), ctx->d_scores.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = finish_checked(ctx, "ahx_ga_selfcheck")) != AHX_OK) return rc;
+  for (int i = 0; i < P; ++i) {
+    bool bad = !(std::fabs(again[i] - fit[i]) <= 1e-12 * std::fabs(again[i]));
+    AHX_CUDA(ctx, cudaMemcpy(tour.data(), ctx->d_tours.p + static_cast<size_t>(i) * L, sizeof(int32_t) * L, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> sorted(tour);
+    std::sort(sorted.begin(), sorted.end());
+    if (sorted != ctx->ga_active_set) bad = true;                       // bit-exact validity: a permutation of the active contigs
+    if (ctx->ga_res && !bad) {
+      AHX_CUDA(ctx, cudaMemcpy(xrow.data(), ctx->d_xpool.p + static_cast<size_t>(rowof[i]) * N, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+      if (xrow != tour_coordinates(ctx, L, tour.data())) bad = true;    // stored coordinates == coordinates of the stored tour
+    }
+    if (bad) ++*n_bad;
+  }
   return AHX_OK;
 }
 

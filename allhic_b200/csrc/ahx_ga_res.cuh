@@ -41,7 +41,10 @@ struct GaRes {
   double mut_prob;
   uint32_t key0, key1;
   long long ngen, max_gens;
-  int *pool;            // [2P][L]
+  int *pool;            // [2P][L]   tours
+  uint32_t *xpool;      // [2P][N]   coordinates 2*mid of every contig in that tour (N == L)
+  const uint32_t *sizes32;
+  uint32_t total2;      // 2 * sum(sizes)
   int *rowof[2];        // [P]
   double *fit[2];       // [P]
   int *hof;             // [L]
@@ -52,26 +55,58 @@ struct GaRes {
   int *gidx;            // lowest offspring index holding that fitness (0x7fffffff when idle)
 };
 
-// One mutated offspring: where it comes from, where it goes, and its mutation as ONE
-// branch-free index remap, new[i] = parent[src(i)] (the four operators of Tour.Mutate,
-// evaluate.go:157-218, are all of this form -- no divergence between the tours of a batch):
-//   src = i;  if (i - lo <u len) src = a*i + b;  if (i == sp) src = sv;  if (i == sp2) src = sv2;
-//   if (src >= L) src -= L
-struct GaSlot { int o, parent_row, child_row, lo, len, a, b, sp, sv, sp2, sv2, pad; };
+// One mutated offspring: where it comes from, where it goes, and its mutation in two
+// branch-free forms (the four operators of Tour.Mutate, evaluate.go:157-218, fit both --
+// no divergence between the tours of a batch):
+//   tour:         new[i] = parent[src(i)],
+//                 src = i; if (i - lo <u len) src = a*i + b; if (i == sp) src = sv; if (i == sp2) src = sv2;
+//                 if (src >= L) src -= L
+//   coordinates:  X = 2*mid (evaluate.go:120-126) of contig c in the parent, uint32 arithmetic mod 2^32,
+//                 X' = (X - xlo <u xlen) ? xa*X + xb : X + xb0;  if (c == m1) X' = v1;  if (c == m2) X' = v2
+// because every operator moves whole segments: contigs between the two cut points shift by
+// a constant (swap, insertion, rotation) or are mirrored (inversion), the one or two moved
+// contigs get explicit values.  So a child's coordinates are an elementwise map of its
+// parent's stored coordinates: no prefix sum, no size lookups, no scatter.
+struct GaSlot {
+  int o, parent_row, child_row;
+  int lo, len, a, b, sp, sv, sp2, sv2;
+  uint32_t xlo, xlen, xa, xb, xb0, v1, v2;
+  int m1, m2;
+};
 
-__device__ __forceinline__ void remap_of(const MutPlan &mp, int L, GaSlot *s) {
+// pt / px: the parent's tour row and coordinate row; s32: contig sizes; total2 = 2 * sum(sizes)
+__device__ __forceinline__ void remap_of(const MutPlan &mp, int L, const int *pt, const uint32_t *px, const uint32_t *__restrict__ s32,
+                                         uint32_t total2, GaSlot *s) {
   s->lo = 0; s->len = 0; s->a = 1; s->b = 0; s->sp = -1; s->sv = 0; s->sp2 = -1; s->sv2 = 0;
+  s->xlo = 0; s->xlen = 0; s->xa = 1; s->xb = 0; s->xb0 = 0; s->m1 = -1; s->v1 = 0; s->m2 = -1; s->v2 = 0;
   const int p = mp.p, q = mp.q;
+  if (mp.op < 0 || (mp.op != 1 && p == q)) return;                 // randomTwoInts may return p == q: every operator is then a no-op
+  const int cp = __ldcg(pt + p), cq = __ldcg(pt + (mp.op == 1 ? p : q));
+  const uint32_t Xp = __ldcg(px + cp), Xq = __ldcg(px + cq), zp = __ldg(s32 + cp), zq = __ldg(s32 + cq);
   switch (mp.op) {
-    case 0: s->sp = p; s->sv = q; s->sp2 = q; s->sv2 = p; break;                       // MutPermute: swap p, q
-    case 1: s->lo = 0; s->len = L; s->b = p; break;                                    // MutSplice: new[i] = old[(i + k) mod L]
-    case 2:                                                                            // MutInsertion
-      if (p != q) {
-        if (mp.dir) { s->lo = p + 1; s->len = q - p; s->b = -1; s->sp = p; s->sv = q; }   // pop q, insert at p
-        else { s->lo = p; s->len = q - p; s->b = 1; s->sp = q; s->sv = p; }               // pop p, insert at q
+    case 0:                                                         // MutPermute: swap positions p < q
+      s->sp = p; s->sv = q; s->sp2 = q; s->sv2 = p;
+      s->xlo = Xp + 1; s->xlen = Xq - Xp - 1; s->xb = 2u * (zq - zp);            // everything in between shifts by size_q - size_p
+      s->m1 = cq; s->v1 = Xp - zp + zq;                                           // q's contig now starts where p's did
+      s->m2 = cp; s->v2 = Xq + zq - zp;                                           // p's contig now ends where q's did
+      break;
+    case 1:                                                         // MutSplice: new = old[k:] ++ old[:k], k = p
+      s->lo = 0; s->len = L; s->b = p;
+      s->xlo = Xp; s->xlen = 0u - Xp; s->xb = 0u - (Xp - zp); s->xb0 = total2 - (Xp - zp);   // tail moves to the front, head behind it
+      break;
+    case 2:                                                         // MutInsertion
+      if (mp.dir) {                                                 // pop q, insert at p: [p, q) shifts right by size_q
+        s->lo = p + 1; s->len = q - p; s->b = -1; s->sp = p; s->sv = q;
+        s->xlo = Xp; s->xlen = Xq - Xp; s->xb = 2u * zq; s->m1 = cq; s->v1 = Xp - zp + zq;
+      } else {                                                      // pop p, insert at q: (p, q] shifts left by size_p
+        s->lo = p; s->len = q - p; s->b = 1; s->sp = q; s->sv = p;
+        s->xlo = Xp + 1; s->xlen = Xq - Xp; s->xb = 0u - 2u * zp; s->m1 = cp; s->v1 = Xq + zq - zp;
       }
       break;
-    case 3: s->lo = p; s->len = q - p + 1; s->a = -1; s->b = p + q; break;             // MutInversion: reverse [p, q]
+    case 3:                                                         // MutInversion: reverse [p, q] -> mirror image of the segment
+      s->lo = p; s->len = q - p + 1; s->a = -1; s->b = p + q;
+      s->xlo = Xp; s->xlen = Xq - Xp + 1; s->xa = 0xFFFFFFFFu; s->xb = (Xp - zp) + (Xq + zq);
+      break;
     default: break;
   }
 }
@@ -94,36 +129,50 @@ __device__ __forceinline__ double key_fit(unsigned long long k) {
 
 template <int T>
 struct GaSrc {
-  const int *pool; int *pool_w; const GaSlot *slots; double *fitn; unsigned long long *gmin; int L;
-  struct Cursor {
-    const int *src; int *dst; int lo, len, a, b, sp, sv, sp2, sv2, L;
-    __device__ __forceinline__ bool live() const { return src != nullptr; }
-    __device__ __forceinline__ unsigned get(int i) const {
-      int s = static_cast<unsigned>(i - lo) < static_cast<unsigned>(len) ? a * i + b : i;
-      s = i == sp ? sv : s;
-      s = i == sp2 ? sv2 : s;
-      s -= s >= L ? L : 0;
-      return static_cast<unsigned>(__ldcg(src + s));
-    }
-    __device__ __forceinline__ void get4(int i, int end, unsigned (&c)[4]) const {
+  const int *pool; int *pool_w; const uint32_t *xpool; uint32_t *xpool_w; const GaSlot *slots; double *fitn; unsigned long long *gmin;
+  // Lane l works on tour t = l mod T and on contig (then position) base + l / T: 32/T consecutive
+  // elements of each tour per warp instruction (one 32-byte sector per tour), and the coordinate
+  // store X[c*T + t] of a warp is 32 consecutive words.
+  template <int NW, int BAR>
+  __device__ __forceinline__ void build(int j, int L, int N, const uint32_t *__restrict__, uint32_t *X, uint32_t *, int *, int gtid) const {
+    constexpr int CPI = 32 / T, kU = 4;
+    const int lane = gtid & 31, wid = gtid >> 5, t = lane % T, sub = lane / T;
+    const GaSlot s = slots[j * T + t];
+    const bool live = s.o >= 0;
+    const uint32_t *px = xpool + static_cast<size_t>(s.parent_row) * N;
+    uint32_t *cx = xpool_w + static_cast<size_t>(s.child_row) * N;
+    for (int c0 = wid * CPI + sub; c0 - sub < N; c0 += NW * CPI * kU) {
+      uint32_t x[kU];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) c[e] = i + e < end ? get(i + e) : 0xFFFFFFFFu;
-    }
-    // Tour.Clone + Tour.Mutate: the child row is the parent row through the operator's index remap
-    __device__ __forceinline__ void put4(int i, int end, const unsigned (&c)[4]) const {
-      if (i + 3 < end && (reinterpret_cast<uintptr_t>(dst + i) & 15) == 0) {
-        *reinterpret_cast<uint4 *>(dst + i) = make_uint4(c[0], c[1], c[2], c[3]);
-      } else {
+      for (int u = 0; u < kU; ++u) { const int c = c0 + u * NW * CPI; x[u] = (live && c < N) ? __ldcg(px + c) : 0u; }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (i + e < end) dst[i + e] = static_cast<int>(c[e]);
+      for (int u = 0; u < kU; ++u) {
+        const int c = c0 + u * NW * CPI;
+        uint32_t y = (x[u] - s.xlo < s.xlen) ? s.xa * x[u] + s.xb : x[u] + s.xb0;
+        y = c == s.m1 ? s.v1 : y;
+        y = c == s.m2 ? s.v2 : y;
+        if (c < N) { X[static_cast<size_t>(c) * T + t] = y; if (live) cx[c] = y; }
       }
     }
-  };
-  __device__ __forceinline__ Cursor cursor(int j, int t) const {
-    const GaSlot s = slots[j * T + t];
-    if (s.o < 0) return Cursor{nullptr, nullptr, 0, 0, 1, 0, -1, 0, -1, 0, L};
-    return Cursor{pool + static_cast<size_t>(s.parent_row) * L, pool_w + static_cast<size_t>(s.child_row) * L,
-                  s.lo, s.len, s.a, s.b, s.sp, s.sv, s.sp2, s.sv2, L};
+    // Tour.Clone + Tour.Mutate: the child row is the parent row through the operator's index remap
+    const int *pt = pool + static_cast<size_t>(s.parent_row) * L;
+    int *ct = pool_w + static_cast<size_t>(s.child_row) * L;
+    if (live)
+      for (int i0 = wid * CPI + sub; i0 < L; i0 += NW * CPI * kU) {
+        int v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int i = i0 + u * NW * CPI;
+          int src = static_cast<unsigned>(i - s.lo) < static_cast<unsigned>(s.len) ? s.a * i + s.b : i;
+          src = i == s.sp ? s.sv : src;
+          src = i == s.sp2 ? s.sv2 : src;
+          src -= src >= L ? L : 0;
+          v[u] = i < L ? __ldcg(pt + src) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { const int i = i0 + u * NW * CPI; if (i < L) ct[i] = v[u]; }
+      }
+    named_bar_sync(BAR, NW * 32);   // X[buf] is complete
   }
   __device__ __forceinline__ void prefetch(int, int) const {}
   __device__ __forceinline__ void store(int j, int t, double score) const {
@@ -267,13 +316,15 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     for (int s = kRThreads - 1 - tid; s < nb_local * T; s += kRThreads) {   // threads from the top of the block; the clones below start at thread 0
       const int j = s / T, t = s % T;
       const uint32_t mi = static_cast<uint32_t>((cta + j * G) * T + t);
-      GaSlot sl{-1, 0, 0, 0, 0, 1, 0, -1, 0, -1, 0, 0};
+      GaSlot sl{};
+      sl.o = -1;
       if (mi < Mcur) {
         const int o = mask_select(mflag, mpref, WM, mi, false, q.P);
         const MutPlan mp = plan_mutation(ph, glo, ghi, static_cast<uint32_t>(o), q.mut_prob, q.L);
         const int parent = tournament_pair(fitc, q.P, q.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
-        remap_of(mp, q.L, &sl);
-        sl.o = o; sl.parent_row = __ldcg(rowc + parent);
+        sl.parent_row = __ldcg(rowc + parent);
+        remap_of(mp, q.L, q.pool + static_cast<size_t>(sl.parent_row) * q.L, q.xpool + static_cast<size_t>(sl.parent_row) * g.N, q.sizes32, q.total2, &sl);
+        sl.o = o;
         sl.child_row = mask_select(rused, rpref, WR, mi, true, 2 * q.P);
         rown[o] = sl.child_row;
         used_new[sl.child_row] = 1;
@@ -298,7 +349,7 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     }
     __syncthreads();
     // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
-    GaSrc<T> src{q.pool, q.pool, slots, fitn, gmin_new, q.L};
+    GaSrc<T> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
     res_run_batches<T, false>(g, m, src, 0, 1, nb_local, kdone, table_ready);
     // ---- next generation's mutation mask (independent of fitness): hidden behind the barrier wait
     const long long ngen_now = gen + 1;

@@ -70,11 +70,18 @@ __device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes) {
   if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(static_cast<uint32_t>(e - a)) : "memory");
 }
 
+template <int T, int NW, int BAR, typename Src>
+__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
+                                            uint32_t *scan_scratch, int *errflag, int ptid);
+
 // ---- batch sources -------------------------------------------------------------
-// A source maps (batch, slot t) to a tour: n_batches(), out_row(batch, t) (-1: slot
-// unused, nothing to write) and cursor(batch, t), a per-lane view of that tour with
-// live(), get4(i, end, c) = contigs at positions i..i+3 and put4(i, end, c) (lets the GA
-// write the offspring row while it is being read), store(batch, t, score).
+// A source turns a batch into coordinates and takes the scores back:
+//   build<NW, BAR>(batch, ..., X, ...)  called by NW warps: fill X[c*T + t] for the T tours of the batch
+//   prefetch(batch, t)                   optional L2 prefetch of a later batch
+//   store(batch, t, score)               called once per slot with the finished score
+// ResDirect reads tours from a P x L array and prefix-sums the sizes (res_build_x, through
+// cursor(batch, t): live(), get4(i, end, c) = contigs at positions i..i+3); the GA's source
+// (ahx_ga_res.cuh) transforms the parent's stored coordinates instead.
 template <int T, typename IdxT>
 struct ResDirect {
   const IdxT *tours; const int *rows; int P, L;
@@ -83,7 +90,6 @@ struct ResDirect {
     const IdxT *ptr;
     __device__ __forceinline__ bool live() const { return ptr != nullptr; }
     __device__ __forceinline__ unsigned get(int i) const { return static_cast<unsigned>(ptr[i]); }
-    __device__ __forceinline__ void put4(int, int, const unsigned (&)[4]) const {}
     // positions i .. i+3 (i % 4 == 0), the ones at or beyond `end` as 0xFFFFFFFF; one vector load when the row allows it
     __device__ __forceinline__ void get4(int i, int end, unsigned (&c)[4]) const {
       if (i + 3 < end && (reinterpret_cast<uintptr_t>(ptr) & (4 * sizeof(IdxT) - 1)) == 0) {
@@ -112,6 +118,11 @@ struct ResDirect {
   __device__ __forceinline__ void store(int batch, int t, double score) const {
     const int r = out_row(batch, t);
     if (r >= 0) out[r] = score;
+  }
+  template <int NW, int BAR>
+  __device__ __forceinline__ void build(int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X, uint32_t *scratch,
+                                        int *errflag, int gtid) const {
+    res_build_x<T, NW, BAR>(*this, batch, L, N, sizes32, X, scratch, errflag, gtid);
   }
   // asks the L2 for the rows of a later batch (called by T lanes, one row each)
   __device__ __forceinline__ void prefetch(int batch, int t) const {
@@ -168,7 +179,7 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
   for (int p0 = beg + sub; p0 - sub < wend; p0 += PPI * kU) {
     unsigned c[kU][4]; uint32_t sz[kU][4];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) { cur.get4(p0 + u * PPI, end, c[u]); cur.put4(p0 + u * PPI, end, c[u]); }
+    for (int u = 0; u < kU; ++u) cur.get4(p0 + u * PPI, end, c[u]);
 #pragma unroll
     for (int u = 0; u < kU; ++u)
 #pragma unroll
@@ -307,7 +318,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
   // first batch of the call: nobody has anything to score yet, so all 24 warps build its coordinates
   // (a third of the latency of the 8 producer warps); both X buffers are free here.  Producer thread
   // p of the steady state is thread kRCT + p; in the joint build the thread index is just tid.
-  if (first < nb) res_build_x<T, kRC + kRP, 2>(src, first, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
+  if (first < nb) src.template build<kRC + kRP, 2>(first, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
   if (tid >= kRCT) {
     // ------------------------------------------------------------ producers
     const int ptid = tid - kRCT;
@@ -324,7 +335,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
     for (int b = first; b < nb; b += stride, ++k) {
       if (k - k0 >= 2) finalize(k - 2, b - 2 * stride);
       if (ptid < T) src.prefetch(b + stride, ptid);   // next batch's rows: HBM -> L2 now
-      if (k > k0) res_build_x<T, kRP, 1>(src, b, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
+      if (k > k0) src.template build<kRP, 1>(b, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
       mbar_arrive(&m.full[k & 1]);
     }
     for (int kk = max(k0, k - 2); kk < k; ++kk) finalize(kk, first + (kk - k0) * stride);

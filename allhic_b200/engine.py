@@ -174,6 +174,12 @@ class Engine:
         t = np.ascontiguousarray(tours, np.int32)
         self._ck(self._l.ahx_ga_put_migrants(self.h, t.shape[0], _ptr(t)))
 
+    def ga_selfcheck(self):
+        """Number of individuals of the current generation whose stored state is inconsistent (0 = sound)."""
+        n = C.c_int64()
+        self._ck(self._l.ahx_ga_selfcheck(self.h, C.byref(n)))
+        return n.value
+
     def ga_end(self):
         self._ck(self._l.ahx_ga_end(self.h))
 

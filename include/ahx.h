@@ -193,6 +193,10 @@ int ahx_ga_get_elites(ahx_ctx *ctx, int32_t n, int32_t *tours /* n*L */, double 
 /* Replace the n worst individuals by migrants (tours validated as permutations
  * of the active set; fitness re-evaluated on the device). */
 int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours /* n*L */);
+/* Test hook: re-derives every individual of the current generation from its stored tour
+ * (permutation of the active contigs, fitness within 1e-12 of a fresh Tour.Evaluate, stored
+ * coordinates equal to the tour's) and counts the individuals that fail. */
+int ahx_ga_selfcheck(ahx_ctx *ctx, int64_t *n_bad);
 int ahx_ga_end(ahx_ctx *ctx);
 
 /* One mutation operator applied to one tour on the device (test hook for

@@ -709,7 +709,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   ctx->d_hof.release(); ctx->d_sel_idx.release(); ctx->d_sel_tours.release(); ctx->d_sel_fit.release(); ctx->d_taken.release();
   ctx->d_state.release(); ctx->d_plan.release(); ctx->d_pos.release(); ctx->d_cum.release(); ctx->d_S4.release(); ctx->d_trace.release();
   ctx->d_pairinfo.release(); ctx->d_stepacc.release(); ctx->d_counts.release();
-  ctx->d_rowof[0].release(); ctx->d_rowof[1].release(); ctx->d_sel_rows.release(); ctx->d_row_fit.release(); ctx->d_gbar.release(); ctx->d_used.release(); ctx->d_gmin.release(); ctx->d_xpool.release();
+  ctx->d_rowof[0].release(); ctx->d_rowof[1].release(); ctx->d_sel_rows.release(); ctx->d_row_fit.release(); ctx->d_gbar.release(); ctx->d_used.release(); ctx->d_gmin.release(); ctx->d_xpool.release(); ctx->d_gmask.release();
   for (auto ev : ctx->chunk_ev) cudaEventDestroy(ev);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

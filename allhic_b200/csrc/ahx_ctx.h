@@ -109,6 +109,7 @@ struct ahx_ctx {
   ahx::DevBuf<unsigned int> d_gbar;           // [0] grid barrier counter, [1] hall-of-fame index scratch
   ahx::DevBuf<unsigned char> d_used;          // 3 byte maps of referenced pool rows
   ahx::DevBuf<unsigned long long> d_gmin;
+  ahx::DevBuf<uint32_t> d_gmask;              // mutation masks of two generations
   ahx::DevBuf<uint32_t> d_xpool;              // coordinate row of every pool row
   std::vector<int32_t> ga_active_set;  // sorted contig ids of the initial tour
   double ga_ms = 0.0;

@@ -593,7 +593,7 @@ static GaRes make_res(ahx_ctx *ctx) {
   q.pool = ctx->d_pop[0].p; q.rowof[0] = ctx->d_rowof[0].p; q.rowof[1] = ctx->d_rowof[1].p;
   q.fit[0] = ctx->d_fit[0].p; q.fit[1] = ctx->d_fit[1].p; q.hof = ctx->d_hof.p; q.st = ctx->d_state.p;
   q.gbar = ctx->d_gbar.p;
-  q.used = ctx->d_used.p; q.gmin = ctx->d_gmin.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
+  q.used = ctx->d_used.p; q.gmin = ctx->d_gmin.p; q.gmask = ctx->d_gmask.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
   return q;
 }
 
@@ -720,7 +720,7 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
     AHX_CUDA(ctx, ctx->d_pop[0].reserve(PL2));
     for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); AHX_CUDA(ctx, ctx->d_rowof[i].reserve(prm->npop)); }
     AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1)); AHX_CUDA(ctx, ctx->d_gbar.reserve(2));
-    AHX_CUDA(ctx, ctx->d_used.reserve(3 * ((2 * static_cast<size_t>(prm->npop) + 31) / 32 * 32))); AHX_CUDA(ctx, ctx->d_gmin.reserve(3));
+    AHX_CUDA(ctx, ctx->d_used.reserve(3 * ((2 * static_cast<size_t>(prm->npop) + 31) / 32 * 32))); AHX_CUDA(ctx, ctx->d_gmin.reserve(3)); AHX_CUDA(ctx, ctx->d_gmask.reserve(2 * ((static_cast<size_t>(prm->npop) + 31) / 32)));
     AHX_CUDA(ctx, ctx->d_tours.reserve(L)); AHX_CUDA(ctx, ctx->d_scores.reserve(1));
     ctx->ga_ms = 0.0; ctx->ga_x32 = false;
     ctx->ga_active_set.assign(init_tour, init_tour + L);

@@ -22,9 +22,9 @@
 //   4. res_run_batches: the coordinates of T offspring at a time are built straight from
 //      the parent rows through the mutation's index remap (the child rows are written on the
 //      way), consumers score them (ahx_resident.cuh); atomicMin of the new fitness values
-//   5. mutation mask of the NEXT generation (first Philox draw of each offspring; it does not
-//      depend on fitness, so it fills the wait for the slowest CTA)
-//   6. grid barrier
+//   5. (during 2-3) this CTA's words of the NEXT generation's mutation mask (first Philox draw
+//      of each offspring; independent of fitness) to global memory
+//   6. grid barrier; load the whole mask, word prefix
 //   7. bookkeeping (evaluate.go:287-306): only a mutated offspring can beat the hall of fame,
 //      so one load of the generation's minimum decides; an improvement (rare) costs a second
 //      barrier to agree on the lowest offspring index and copy its row
@@ -53,6 +53,7 @@ struct GaRes {
   unsigned char *used;  // [3][pad32(2P)] byte maps: used[g % 3][r] = 1 iff generation g references pool row r
   unsigned long long *gmin;   // [3] order-preserving key of the best fitness evaluated while building generation g (index g % 3)
   int *gidx;            // lowest offspring index holding that fitness (0x7fffffff when idle)
+  uint32_t *gmask;      // [2][ceil(P/32)] mutation masks of generations g (index g & 1), filled one generation ahead
 };
 
 // One mutated offspring: where it comes from, where it goes, and its mutation in two
@@ -135,7 +136,7 @@ struct GaSrc {
   // store X[c*T + t] of a warp is 32 consecutive words.
   template <int NW, int BAR>
   __device__ __forceinline__ void build(int j, int L, int N, const uint32_t *__restrict__, uint32_t *X, uint32_t *, int *, int gtid) const {
-    constexpr int CPI = 32 / T, kU = 4;
+    constexpr int CPI = 32 / T, kU = 8;
     const int lane = gtid & 31, wid = gtid >> 5, t = lane % T, sub = lane / T;
     const GaSlot s = slots[j * T + t];
     const bool live = s.o >= 0;
@@ -229,15 +230,15 @@ __device__ __forceinline__ void grid_barrier(unsigned int *gbar, unsigned int ta
 }
 
 // Mutation flags of generation `gen` (first Philox draw of every offspring: eaopt's
-// rng.Float64() < MutRate) as a bit mask + exclusive word prefix; returns the count.
-// They do not depend on fitness, so they are computed one generation ahead, before the
-// grid barrier, where fast CTAs would otherwise idle.
-__device__ __forceinline__ uint32_t ga_mutation_mask(const GaRes &q, const Philox &ph, long long gen, uint32_t *mflag, uint32_t *mpref,
-                                                     uint32_t *scan_tmp) {
-  const int tid = threadIdx.x, WM = (q.P + 31) / 32;
+// rng.Float64() < MutRate) as a bit mask.  They do not depend on fitness, so they are
+// produced one generation ahead: CTA c computes the words w = c, c + G, ... of the next
+// generation's mask while it builds the current one (ga_publish_mask, before the grid
+// barrier) and every CTA reads the whole mask back after the barrier (ga_load_mask).
+__device__ __forceinline__ void ga_publish_mask(const GaRes &q, const Philox &ph, long long gen, uint32_t *gmask, int cta, int G) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, WM = (q.P + 31) / 32;
   const uint32_t glo = static_cast<uint32_t>(gen), ghi = static_cast<uint32_t>(gen >> 32);
-  for (int base = 0; base < WM * 32; base += kRThreads) {   // warp w of the round covers offspring [base + 32w, +32): one word
-    const int o = base + tid;
+  for (int w = cta + warp * G; w < WM; w += (kRThreads / 32) * G) {   // one warp per word
+    const int o = w * 32 + lane;
     bool mut = false;
     if (o < q.P) {
       uint32_t r[4];
@@ -245,11 +246,16 @@ __device__ __forceinline__ uint32_t ga_mutation_mask(const GaRes &q, const Philo
       mut = rand_unit(r[0], r[1]) < q.mut_prob;
     }
     const uint32_t word = __ballot_sync(0xffffffffu, mut);
-    if ((tid & 31) == 0 && (o >> 5) < WM) mflag[o >> 5] = word;
+    if (lane == 0) gmask[w] = word;
   }
-  __syncthreads();
+}
+// returns the number of mutated offspring; mflag / mpref: the mask and its exclusive word prefix
+__device__ __forceinline__ uint32_t ga_load_mask(const GaRes &q, const uint32_t *gmask, uint32_t *mflag, uint32_t *mpref, uint32_t *scan_tmp) {
+  const int tid = threadIdx.x, WM = (q.P + 31) / 32;
+  const uint32_t w = tid < WM ? __ldcg(gmask + tid) : 0u;
+  if (tid < WM) mflag[tid] = w;
   uint32_t M = 0;
-  const uint32_t e1 = block_scan_u32(tid < WM ? __popc(mflag[tid]) : 0u, scan_tmp, &M);
+  const uint32_t e1 = block_scan_u32(__popc(w), scan_tmp, &M);
   if (tid < WM) mpref[tid] = e1;
   __syncthreads();
   return M;
@@ -274,7 +280,11 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
   int stop = q.st->stop;
   unsigned int nsync = 0;
   const size_t ub = (2 * static_cast<size_t>(q.P) + 31) / 32 * 32;   // bytes per row-reference map (padded)
-  uint32_t M = (n_gens > 0 && !stop) ? ga_mutation_mask(q, ph, gen, mflag, mpref, scan_tmp) : 0u;
+  // the first generation of this launch: every CTA publishes its share of the mask, one extra barrier
+  if (n_gens > 0 && !stop) ga_publish_mask(q, ph, gen, q.gmask + static_cast<size_t>(gen & 1) * WM, cta, G);
+  ++nsync;
+  grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
+  uint32_t M = (n_gens > 0 && !stop) ? ga_load_mask(q, q.gmask + static_cast<size_t>(gen & 1) * WM, mflag, mpref, scan_tmp) : 0u;
   for (long long it = 0; it < n_gens && !stop; ++it) {
     const int cur = static_cast<int>(gen & 1);
     const int *rowc = q.rowof[cur]; int *rown = q.rowof[cur ^ 1];
@@ -340,7 +350,9 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
       used_new[row] = 1;
       fitn[o] = __ldcg(fitc + parent);
     }
-    // ---- housekeeping for later generations: clear generation gen-1's map (this CTA's slice), reset its minimum
+    // ---- housekeeping for later generations: this CTA's words of the next generation's mutation mask,
+    // clear generation gen-1's row map (this CTA's slice), reset its minimum
+    ga_publish_mask(q, ph, gen + 1, q.gmask + static_cast<size_t>((gen + 1) & 1) * WM, cta, G);
     {
       const size_t words = ub / 4;
       uint32_t *z = reinterpret_cast<uint32_t *>(used_old);
@@ -351,13 +363,10 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
     GaSrc<T> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
     res_run_batches<T, false>(g, m, src, 0, 1, nb_local, kdone, table_ready);
-    // ---- next generation's mutation mask (independent of fitness): hidden behind the barrier wait
     const long long ngen_now = gen + 1;
-    const bool last = (it + 1 >= n_gens) || ngen_now >= q.max_gens;
-    __syncthreads();
-    if (!last) M = ga_mutation_mask(q, ph, ngen_now, mflag, mpref, scan_tmp);
     ++nsync;
     grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
+    M = ga_load_mask(q, q.gmask + static_cast<size_t>(ngen_now & 1) * WM, mflag, mpref, scan_tmp);
     // ---- bookkeeping (evaluate.go:287-306).  Clones are copies of individuals that already exist, so
     // only a mutated offspring can beat the hall of fame: compare the minimum over this generation's
     // evaluations; on a (rare) improvement the owners of that fitness agree on the lowest offspring index.

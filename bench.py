@@ -35,8 +35,8 @@ try:
 except Exception:
     pass
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the evaluate kernel, from the committed
-# ncu --set full capture of (workload, P) -- profiles/r1b_ncu_full_summary.txt
-NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64232192 + 669952}
+# ncu --set full capture of (workload, P) -- profiles/r1k_ncu_full_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64208128 + 754688}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 
@@ -267,13 +267,19 @@ def main():
     e2e_v = world * P * args.steps / e2e_s
     kern_s = dev_ms * 1e-3 / args.steps
     terms_per_s = P * e_act / kern_s                       # per GPU (roofline is a per-kernel figure)
-    # Roofline of the dominant kernel: per tour, E window tests each gathering two
-    # 4-byte coordinates from shared memory, E_act in-window pairs each one fp64 divide + add, and
-    # 4*L + 8 bytes of HBM.  The slowest leg at its measured/derived peak is the bound.
+    # Roofline of the dominant kernel.  eval_m_res_kernel evaluates EVERY stored pair of every
+    # tour branch-free (the window test only masks the reciprocal seed), so per tour the algorithmic work is
+    #   fp64: E terms x 5 fp64-pipe instructions (exact u32->f64, 3 FMA of the cubic reciprocal step, 1 FMA to
+    #         accumulate) = 10 flop per stored pair, against the measured DFMA peak;
+    #   smem: E x two 4-byte coordinate gathers from shared memory, against 128 B/clk/SM;
+    #   hbm : 4*L + 8 bytes (the tour in, the score out), against MEASURED_PEAKS.json.
+    # The slowest leg at its peak is the bound.
     sm_mhz = clocks.peak_mhz()
     smem_peak = 128.0 * eng.sm_count() * sm_mhz * 1e6 / 1e9                      # GB/s: 128 B/clk/SM
+    kind, tpb = eng.eval_m_kernel(P, L)
+    flop_per_pair = 10.0 if kind == 2 else 2.0 * e_act / max(E, 1)               # the streaming kernels divide in-window pairs only
     legs = {"smem": (P * 8.0 * E / kern_s / 1e9, smem_peak, "GB/s"),
-            "fp64": (terms_per_s / 1e9, ddiv_g, "Gdiv+add/s"),
+            "fp64": (P * E * flop_per_pair / kern_s / 1e12, dfma_tflops, "TFLOP/s"),
             "hbm": (P * (4.0 * L + 8.0) / kern_s / 1e9, HBM_PEAK, "GB/s")}
     bound = max(legs, key=lambda k: legs[k][0] / legs[k][1])
     roof = {"bound": bound, "achieved": legs[bound][0], "peak": legs[bound][1], "unit": legs[bound][2],
@@ -281,10 +287,15 @@ def main():
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, P)),
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel (profiles/), bytes per launch",
             "peak_source": {"smem": "128 B/clk/SM x %d SMs x %.0f MHz (SM clock sampled during the timed region)" % (eng.sm_count(), sm_mhz),
-                            "fp64": "dependent-free fp64 divide+add microbenchmark measured live by this run (ahx_probe_fp64)",
+                            "fp64": "DFMA microbenchmark measured live by this run (ahx_probe_fp64; MEASURED_PEAKS.json has no fp64 figure)",
                             "hbm": "MEASURED_PEAKS.json hbm_gbs"}[bound],
-            "kernel": {2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[eng.eval_m_kernel(P, L)[0]], "tours_per_batch": eng.eval_m_kernel(P, L)[1],
-            "algorithmic_per_tour": {"window_tests_E": E, "smem_gather_bytes": 8 * E, "in_window_pairs_E_act": e_act, "hbm_bytes": 4 * L + 8},
+            "kernel": {2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[kind], "tours_per_batch": tpb,
+            "algorithmic_per_tour": {"stored_pairs_E": E, "fp64_flop": flop_per_pair * E, "smem_gather_bytes": 8 * E,
+                                     "in_window_pairs_E_act": e_act, "hbm_bytes": 4 * L + 8},
+            "issue_model": {"issue_cycles_per_pair_term": 18.3, "note": "SASS of the consumer loop: 5 fp64 (2 issue cycles each, term_probe.cu) + 8.3 other instructions per (pair, tour); "
+                            "frac = terms/s x cycles / (SMs x 4 schedulers x clock)",
+                            "frac": P * E * 18.3 / 32.0 / kern_s / (eng.sm_count() * 4 * sm_mhz * 1e6)},
+            "measured_div_add_peak_per_s": ddiv_g * 1e9,
             "legs": {k: {"achieved": v[0], "peak": v[1], "unit": v[2], "frac": v[0] / v[1]} for k, v in legs.items()},
             "dense_equivalent": {"window_pairs_per_tour": w_dense, "bytes_per_tour": 4 * w_dense + 12 * L,
                                  "algorithmic_GBs": P * (4 * w_dense + 12 * L) / kern_s / 1e9, "hbm_peak_GBs": HBM_PEAK,
@@ -341,6 +352,22 @@ def main():
                      "evals_per_s_inside_ga": float(ev.item()) / ga_s if world == 1 else None, "best_score": best,
                      "model": "islands, all-gather of 2 elites every 50 generations over NCCL" if world > 1 else "single population"}
 
+    # ---- orientation phase (CLM.EvaluateQ batched over sign vectors; one flipOne pass), for the record
+    if not args.no_ga and rank == 0:
+        rng = np.random.default_rng(7)
+        nq = 1024
+        signs = np.where(rng.random((nq, n)) < 0.5, ord('+'), ord('-')).astype(np.uint8)
+        eng.eval_q(tours[0], signs[:8])
+        t0 = time.perf_counter(); reps = 5
+        for _ in range(reps):
+            eng.eval_q(tours[0], signs)
+        q_s = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        s2, *_ = eng.flip_one(tours[0], signs[0])
+        f_s = time.perf_counter() - t0
+        out["orientation"] = {"eval_q_per_s_e2e": nq / q_s, "batch": nq, "flip_one_pass_ms_e2e": f_s * 1e3, "tour_length": int(L),
+                              "note": "host buffers through ahx_eval_q / ahx_flip_one; the reference does 1 + L full EvaluateQ per flipOne pass"}
+
     out["clocks"] = clocks.stop()
     # ---- CPU baseline beside it (rank 0, N == 1 only)
     if rank == 0 and world == 1:
@@ -348,6 +375,16 @@ def main():
         v, reps, dt = cpu_population_evals(ids, clmf, tours, args.cpu_seconds, threads)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "the same %d-tour population x %d passes (%.1f s), C restatement of Tour.Evaluate + eaopt ParallelEval chunking, %d threads" % (P, reps, dt, threads)}
+        if not args.no_ga:
+            # the same GA on the CPU restatement (eaopt emulation, ParallelEval over all threads), bounded to a few seconds
+            from oracle_lib import OracleCLM
+            orc = OracleCLM(clmf, ids)
+            orc.set_tour(tours[0].astype(np.int64))
+            t0 = time.perf_counter()
+            r = orc.ga_run(npop=P, ngen=1 << 30, mutprob=0.2, seed=42, max_gens=1 << 30, max_seconds=min(6.0, args.cpu_seconds), nthreads=threads)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"]["ga_generations_per_s"] = r.generations / dt
+            out["cpu_baseline"]["ga_sample"] = "%d generations of the same GA (npop %d) in %.1f s" % (r.generations, P, dt)
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:

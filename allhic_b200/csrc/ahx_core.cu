@@ -416,28 +416,36 @@ static cudaError_t launch_x32_c(ahx_ctx *ctx, const IdxT *tours, const int32_t *
 // Usable when the coordinates fit 32 bits, contig indices fit 16 bits and the
 // packed table + two X buffers fit one SM's shared memory.  T: as many tours per
 // batch as still leave one batch per SM.
-int resident_T(const ahx_ctx *ctx, int32_t P) {
-  if (const char *env = getenv("AHX_EVAL_RES")) if (!atoi(env)) return 0;
-  if (const char *env = getenv("AHX_EVAL_FP64")) if (atoi(env)) return 0;
-  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0) return 0;
-  auto fits = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res) + 1024 <= ctx->smem_optin && static_cast<uint64_t>(ctx->N) * 4u * t <= 65535u; };
-  if (const char *env = getenv("AHX_EVAL_T")) {
-    const int t = atoi(env);
-    if (t == 1 || t == 2 || t == 4) return fits(t) ? t : 0;
+// Which form of the persistent kernel can score P tours: T tours per batch, table resident
+// in shared memory or streamed (T = 0: neither -- fall back to the x32 / fp64 kernels).
+ResPlan resident_plan(const ahx_ctx *ctx, int32_t P) {
+  ResPlan pl;
+  if (const char *env = getenv("AHX_EVAL_RES")) if (!atoi(env)) return pl;
+  if (const char *env = getenv("AHX_EVAL_FP64")) if (atoi(env)) return pl;
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0) return pl;
+  auto fits_res = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res) + 1024 <= ctx->smem_optin && static_cast<uint64_t>(ctx->N) * 4u * t <= 65535u; };
+  auto fits_str = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res, true) + 1024 <= ctx->smem_optin; };
+  int forced = 0;
+  if (const char *env = getenv("AHX_EVAL_T")) { const int t = atoi(env); if (t == 1 || t == 2 || t == 4) forced = t; }
+  const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
+  const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
+  for (int t : {4, 2, 1}) {
+    if (forced && t != forced) continue;
+    if (!forced && t > 1 && (P + t - 1) / t < ctx->sm_count) continue;   // keep one batch per SM
+    if (!only_stream && fits_res(t)) { pl.T = t; pl.stream = false; return pl; }
+    if (!no_stream && fits_str(t)) { pl.T = t; pl.stream = true; return pl; }
   }
-  for (int t : {4, 2})
-    if (fits(t) && (P + t - 1) / t >= ctx->sm_count) return t;
-  if (fits(1)) return 1;
-  return 0;
+  return pl;
 }
+int resident_T(const ahx_ctx *ctx, int32_t P) { return resident_plan(ctx, P).T; }
 
-template <int T, typename IdxT>
+template <int T, bool STREAM, typename IdxT>
 static cudaError_t launch_res_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
-  auto kern = L < ctx->N ? eval_m_res_kernel<T, true, ResDirect<T, IdxT>> : eval_m_res_kernel<T, false, ResDirect<T, IdxT>>;
-  const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res);
+  auto kern = L < ctx->N ? eval_m_res_kernel<T, true, STREAM, ResDirect<T, IdxT>> : eval_m_res_kernel<T, false, STREAM, ResDirect<T, IdxT>>;
+  const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res, STREAM);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  ResArgs g{ctx->d_rpairs[T == 4 ? 2 : T - 1].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, ctx->d_errflag.p};
+  ResArgs g{ctx->d_rpairs[STREAM ? 3 : (T == 4 ? 2 : T - 1)].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, ctx->d_errflag.p};
   ResDirect<T, IdxT> src{};
   src.tours = tours; src.rows = rows; src.P = P; src.L = L; src.out = out;
   const int nb = (P + T - 1) / T;
@@ -447,11 +455,18 @@ static cudaError_t launch_res_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *
 }
 
 template <typename IdxT>
-static cudaError_t launch_res(ahx_ctx *ctx, int T, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
-  switch (T) {
-    case 4: return launch_res_t<4, IdxT>(ctx, tours, rows, P, L, out, s);
-    case 2: return launch_res_t<2, IdxT>(ctx, tours, rows, P, L, out, s);
-    default: return launch_res_t<1, IdxT>(ctx, tours, rows, P, L, out, s);
+static cudaError_t launch_res(ahx_ctx *ctx, const ResPlan &pl, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
+  if (pl.stream) {
+    switch (pl.T) {
+      case 4: return launch_res_t<4, true, IdxT>(ctx, tours, rows, P, L, out, s);
+      case 2: return launch_res_t<2, true, IdxT>(ctx, tours, rows, P, L, out, s);
+      default: return launch_res_t<1, true, IdxT>(ctx, tours, rows, P, L, out, s);
+    }
+  }
+  switch (pl.T) {
+    case 4: return launch_res_t<4, false, IdxT>(ctx, tours, rows, P, L, out, s);
+    case 2: return launch_res_t<2, false, IdxT>(ctx, tours, rows, P, L, out, s);
+    default: return launch_res_t<1, false, IdxT>(ctx, tours, rows, P, L, out, s);
   }
 }
 
@@ -466,8 +481,8 @@ int launch_eval_m_sparse(ahx_ctx *ctx, const int32_t *d_tours, const uint16_t *d
                          int32_t P, int32_t L, double *d_out, cudaStream_t s) {
   if (P == 0) return AHX_OK;
   cudaError_t e;
-  if (const int rt = resident_T(ctx, P)) {
-    e = d_tours16 ? launch_res<uint16_t>(ctx, rt, d_tours16, d_rows, P, L, d_out, s) : launch_res<int32_t>(ctx, rt, d_tours, d_rows, P, L, d_out, s);
+  if (const ResPlan pl = resident_plan(ctx, P); pl.T) {
+    e = d_tours16 ? launch_res<uint16_t>(ctx, pl, d_tours16, d_rows, P, L, d_out, s) : launch_res<int32_t>(ctx, pl, d_tours, d_rows, P, L, d_out, s);
   } else if (use_x32(ctx, L)) {
     if (d_tours16) e = ctx->coo16 ? launch_x32_c<Coo16, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s) : launch_x32_c<Coo32, uint16_t>(ctx, d_tours16, d_rows, P, L, d_out, s);
     else e = ctx->coo16 ? launch_x32_c<Coo16, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s) : launch_x32_c<Coo32, int32_t>(ctx, d_tours, d_rows, P, L, d_out, s);
@@ -829,6 +844,11 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
           AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs[ti].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
           AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // rp is reused
         }
+        // the same list as plain contig indices a | b << 16 for the streamed-table mode (any N <= 65535, any T)
+        for (size_t i = 0; i < er; ++i) rp[phys(i)] = ra[i] | (rb[i] << 16);
+        AHX_CUDA(ctx, ctx->d_rpairs[3].reserve(er));
+        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs[3].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
+        AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->E_res = static_cast<int64_t>(er);
       }
     }
@@ -933,7 +953,7 @@ int ahx_pop_scores(ahx_ctx *ctx, double *out) {
 int ahx_eval_m_kernel(const ahx_ctx *ctx, int32_t P, int32_t L, int32_t *tours_per_batch) {
   if (!ctx || !ctx->loaded) return AHX_ERR_STATE;
   int kind = 0, T = 1;
-  if (const int rt = resident_T(ctx, P)) { kind = 2; T = rt; }
+  if (const ResPlan pl = resident_plan(ctx, P); pl.T) { kind = pl.stream ? 3 : 2; T = pl.T; }
   else if (use_x32(ctx, L)) { kind = 1; T = pick_T32(ctx, P, L); }
   else if (eval_m_smem_bytes(1, ctx->N, L) + 1024 <= ctx->smem_optin) T = pick_T(ctx, P, L);
   if (tours_per_batch) *tours_per_batch = T;

@@ -65,7 +65,7 @@ struct ahx_ctx {
   // resident-table kernel (ahx_resident.cuh): per entry the byte offsets of the two contigs in X,
   // (a*4T) | (b*4T) << 16, one table per T = 1, 2, 4, and an 8-bit link count (pairs with more than
   // 255 links are split over several entries); bank-conflict-free order, padded with (0, 1, 0)
-  ahx::DevBuf<uint32_t> d_rpairs[3];
+  ahx::DevBuf<uint32_t> d_rpairs[4];   // [3]: plain contig indices a | b << 16 (streamed-table mode)
   ahx::DevBuf<uint8_t> d_rnl8;
   int64_t E_res = 0;                      // multiple of kRPad (0 when E == 0)
   bool x32_ok = false;                    // 2*sum(sizes) + 2*LIMIT + 2 < 2^32
@@ -102,6 +102,7 @@ struct ahx_ctx {
   bool ga_x32 = false;
   int ga_T = 1;
   bool ga_res = false;                 // persistent resident-table kernel (ahx_ga_res.cuh): d_pop[0] is a pool of 2P rows
+  bool ga_stream = false;              // ... with the pair table streamed through a ring
   int ga_G = 0, ga_nbmax = 0;
   size_t ga_smem = 0;
   ahx::DevBuf<int32_t> d_rowof[2], d_sel_rows;
@@ -139,7 +140,10 @@ int validate_tour(ahx_ctx *ctx, int32_t L, const int32_t *tour, const char *who)
 size_t eval_m_smem_bytes(int T, int32_t N, int32_t L);
 size_t eval_x32_smem_bytes(int T, bool coo16, int32_t N, int32_t L);
 bool use_x32(const ahx_ctx *ctx, int32_t L);
-// Tours per batch of the resident-table kernel for a population of P tours (0: not usable).
+// Tours per batch of the persistent evaluate kernel for a population of P tours (0: not usable)
+// and whether the pair table is streamed through a ring instead of resident in shared memory.
+struct ResPlan { int T = 0; bool stream = false; };
+ResPlan resident_plan(const ahx_ctx *ctx, int32_t P);
 int resident_T(const ahx_ctx *ctx, int32_t P);
 }  // namespace ahx
 

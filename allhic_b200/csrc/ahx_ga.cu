@@ -527,7 +527,7 @@ static cudaError_t launch_apply(ahx_ctx *ctx, const GaDev &g, const GaPlan &pl, 
 // indices, table + coordinates + GA scratch fit one SM's shared memory), the tour covers
 // all contigs (L == N: distinct coordinates, see res_pair_terms) and the masks fit one
 // word per thread.  T: tours per batch; G: CTAs (one per SM at most).
-struct GaResCfg { int T = 0, G = 0, nbmax = 0; size_t smem = 0; };
+struct GaResCfg { int T = 0, G = 0, nbmax = 0; size_t smem = 0; bool stream = false; };
 
 // X[c] = 2*cumSum + size = 2*mid of every contig of a full tour (evaluate.go:120-126), what the
 // evaluate kernel's producers compute on the device; the GA keeps one such row per pool row.
@@ -547,14 +547,20 @@ static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double m
   if (const char *env = getenv("AHX_GA_RES")) if (!atoi(env)) return c;
   if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0 || L != ctx->N || 2 * static_cast<int64_t>(P) > 32 * kGaMaxWords) return c;
   const double expect = std::max(1.0, P * mut_prob);
+  const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
+  const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
   auto try_T = [&](int t) {
-    if (static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) return false;
     const int G = static_cast<int>(std::min<double>(ctx->sm_count, std::max(1.0, std::ceil(1.25 * expect / t))));
     const int nbmax = ((P + t - 1) / t + G - 1) / G;
-    const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res) + ga_res_extra_bytes(P, t, nbmax);
-    if (smem + 1024 > ctx->smem_optin) return false;
-    c.T = t; c.G = G; c.nbmax = nbmax; c.smem = smem;
-    return true;
+    for (int stream = 0; stream < 2; ++stream) {   // table resident in shared memory if it fits, streamed otherwise
+      if (stream ? no_stream : only_stream) continue;
+      if (!stream && static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) continue;
+      const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res, stream != 0) + ga_res_extra_bytes(P, t, nbmax);
+      if (smem + 1024 > ctx->smem_optin) continue;
+      c.T = t; c.G = G; c.nbmax = nbmax; c.smem = smem; c.stream = stream != 0;
+      return true;
+    }
+    return false;
   };
   int want = expect >= 4.0 * ctx->sm_count ? 4 : (expect >= 2.0 * ctx->sm_count ? 2 : 1);
   if (const char *env = getenv("AHX_GA_T")) { const int t = atoi(env); if (t == 1 || t == 2 || t == 4) want = t; }
@@ -597,13 +603,13 @@ static GaRes make_res(ahx_ctx *ctx) {
   return q;
 }
 
-template <int T>
+template <int T, bool STREAM>
 static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
-  auto kern = ga_persist_kernel<T>;
+  auto kern = ga_persist_kernel<T, STREAM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->ga_smem));
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
-  ResArgs g{ctx->d_rpairs[T == 4 ? 2 : T - 1].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, ctx->ga_L, ctx->d_errflag.p};
+  ResArgs g{ctx->d_rpairs[STREAM ? 3 : (T == 4 ? 2 : T - 1)].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, ctx->ga_L, ctx->d_errflag.p};
   GaRes q = make_res(ctx);
   void *args[] = {&g, &q, &n_gens};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(ctx->ga_G), dim3(kRThreads), args, ctx->ga_smem, s);
@@ -611,10 +617,18 @@ static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t
 
 static int launch_persist(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
   cudaError_t e;
-  switch (ctx->ga_T) {
-    case 4: e = launch_persist_t<4>(ctx, n_gens, s); break;
-    case 2: e = launch_persist_t<2>(ctx, n_gens, s); break;
-    default: e = launch_persist_t<1>(ctx, n_gens, s); break;
+  if (ctx->ga_stream) {
+    switch (ctx->ga_T) {
+      case 4: e = launch_persist_t<4, true>(ctx, n_gens, s); break;
+      case 2: e = launch_persist_t<2, true>(ctx, n_gens, s); break;
+      default: e = launch_persist_t<1, true>(ctx, n_gens, s); break;
+    }
+  } else {
+    switch (ctx->ga_T) {
+      case 4: e = launch_persist_t<4, false>(ctx, n_gens, s); break;
+      case 2: e = launch_persist_t<2, false>(ctx, n_gens, s); break;
+      default: e = launch_persist_t<1, false>(ctx, n_gens, s); break;
+    }
   }
   if (e != cudaSuccess) return cuda_fail(ctx, e, "ga_persist_kernel launch");
   ctx->launches++;
@@ -713,7 +727,7 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   {
     const GaResCfg rc = ga_res_config(ctx, prm->npop, L, prm->mut_prob);
     ctx->ga_res = rc.T > 0;
-    if (ctx->ga_res) { ctx->ga_T = rc.T; ctx->ga_G = rc.G; ctx->ga_nbmax = rc.nbmax; ctx->ga_smem = rc.smem; }
+    if (ctx->ga_res) { ctx->ga_T = rc.T; ctx->ga_G = rc.G; ctx->ga_nbmax = rc.nbmax; ctx->ga_smem = rc.smem; ctx->ga_stream = rc.stream; }
   }
   if (ctx->ga_res) {
     const size_t PL2 = 2 * static_cast<size_t>(prm->npop) * L;

@@ -261,16 +261,16 @@ __device__ __forceinline__ uint32_t ga_load_mask(const GaRes &q, const uint32_t 
   return M;
 }
 
-template <int T>
+template <int T, bool STREAM>
 __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaRes q, long long n_gens) {
   extern __shared__ __align__(128) unsigned char smem_res[];
-  const ResSmem m = res_carve<T>(smem_res, g);
+  const ResSmem m = res_carve<T, STREAM>(smem_res, g);
   const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
   const int WM = (q.P + 31) / 32, WR = (2 * q.P + 31) / 32;
   uint32_t *mflag = reinterpret_cast<uint32_t *>(m.extra), *mpref = mflag + WM, *rused = mpref + WM, *rpref = rused + WR;
   GaSlot *slots = reinterpret_cast<GaSlot *>(m.extra + res_align16(4ull * (2 * WM + 2 * WR)));
   uint32_t *scan_tmp = reinterpret_cast<uint32_t *>(slots + static_cast<size_t>(q.nbmax) * T);   // kRThreads/32 + 1 words
-  res_init(m, g, true);
+  res_init<STREAM>(m, g, true);
   int kdone = 0;
   bool table_ready = g.E_res == 0;
   const Philox ph{q.key0, q.key1};
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     __syncthreads();
     // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
     GaSrc<T> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
-    res_run_batches<T, false>(g, m, src, 0, 1, nb_local, kdone, table_ready);
+    res_run_batches<T, false, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
     const long long ngen_now = gen + 1;
     ++nsync;
     grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));

@@ -43,6 +43,13 @@ constexpr int kRPT = kRP * 32;                // producer threads
 constexpr int kRThreads = kRCT + kRPT;
 constexpr int kRUnroll = 4;                   // pairs per consumer lane per iteration (one uint4 of the table)
 constexpr int kRPad = kRCT * kRUnroll;        // E_res is a multiple of this
+// STREAM mode (the pair table does not fit next to the coordinates): the table is streamed
+// from L2 for every batch through a ring of kRStages tiles of kRPad entries (4 B offsets
+// + 1 B link counts each) filled by TMA bulk copies; the last producer warp becomes the
+// loader, the other kRP - 1 build coordinates.
+constexpr int kRStages = 4;
+constexpr int kRTileBytes = 5 * kRPad;
+template <bool STREAM> struct ResRoles { static constexpr int NB = STREAM ? kRP - 1 : kRP; };   // warps that build X
 
 struct ResArgs {
   const uint32_t *pairs;      // [E_res]
@@ -54,8 +61,9 @@ struct ResArgs {
 
 __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 // dynamic shared memory of the resident kernel
-inline size_t res_smem_bytes(int T, int N, long long E_res) {
-  return res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res)) + 2 * res_align16(4ull * N * T) +
+inline size_t res_smem_bytes(int T, int N, long long E_res, bool stream = false) {
+  return (stream ? static_cast<size_t>(kRStages) * kRTileBytes : res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res))) +
+         2 * res_align16(4ull * N * T) + (stream ? 8ull * 2 * kRStages : 0) +
          8ull * 256 + 8ull * 2 * kRC * T + res_align16(4ull * (kRC + kRP) * T) + 8 * 8;
 }
 
@@ -233,13 +241,20 @@ __device__ __forceinline__ double rcp_pos(double x) {
 //   d - 1 < 2 LIMIT (unsigned).
 // Issue-slot model measured with profiles/microbench/term_probe.cu: an fp64 instruction
 // costs 2 issue cycles, anything else 1.
-template <int T, bool SUB>
+// SCALED: p holds byte offsets (resident tables); otherwise contig indices a | b << 16 (the
+// streamed table of large groups, where N * 4T can exceed 16 bits).
+template <int T, bool SUB, bool SCALED>
 __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, double n2, double (&acc)[T]) {
   using V = typename XVec<T>::type;
   uint32_t xa[T], xb[T];
   const unsigned char *Xb = reinterpret_cast<const unsigned char *>(X);
-  x_unpack(*reinterpret_cast<const V *>(Xb + (p & 0xffffu)), xa);
-  x_unpack(*reinterpret_cast<const V *>(Xb + (p >> 16)), xb);
+  if constexpr (SCALED) {
+    x_unpack(*reinterpret_cast<const V *>(Xb + (p & 0xffffu)), xa);
+    x_unpack(*reinterpret_cast<const V *>(Xb + (p >> 16)), xb);
+  } else {
+    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p & 0xffffu) * T), xa);
+    x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p >> 16) * T), xb);
+  }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const uint32_t d = __usad(xa[t], xb[t], 0u);
@@ -258,15 +273,21 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
 // ---- persistent GA kernel (ahx_ga_res.cuh) ------------------------------------------
 struct ResSmem {
   uint32_t *table; uint8_t *nl8; uint32_t *X0; size_t xstride;
-  double *n2lut, *partial; uint64_t *full, *done, *tab; uint32_t *scan_scratch;
+  double *n2lut, *partial; uint64_t *full, *done, *tab, *tfull, *tempty; uint32_t *scan_scratch;
+  unsigned char *ring;       // STREAM: kRStages tiles
   unsigned char *extra;      // first byte after the evaluate layout (GA scratch)
 };
 
-template <int T>
+template <int T, bool STREAM = false>
 __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g) {
   ResSmem m;
-  m.table = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * g.E_res);
-  m.nl8 = sp; sp += res_align16(static_cast<size_t>(g.E_res));
+  m.table = nullptr; m.nl8 = nullptr; m.ring = nullptr; m.tfull = m.tempty = nullptr;
+  if constexpr (STREAM) {
+    m.ring = sp; sp += static_cast<size_t>(kRStages) * kRTileBytes;
+  } else {
+    m.table = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * g.E_res);
+    m.nl8 = sp; sp += res_align16(static_cast<size_t>(g.E_res));
+  }
   m.X0 = reinterpret_cast<uint32_t *>(sp);
   m.xstride = res_align16(4ull * g.N * T) / 4;   // words between the two X buffers
   sp += 2 * res_align16(4ull * g.N * T);
@@ -274,6 +295,7 @@ __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g
   m.partial = reinterpret_cast<double *>(sp); sp += 8ull * 2 * kRC * T;      // [buf][warp][t]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 8 * 8;            // full[2], done[2], tab
   m.full = bars; m.done = bars + 2; m.tab = bars + 4;
+  if constexpr (STREAM) { m.tfull = reinterpret_cast<uint64_t *>(sp); m.tempty = m.tfull + kRStages; sp += 8ull * 2 * kRStages; }
   m.scan_scratch = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * (kRC + kRP) * T);
   m.extra = sp;
   return m;
@@ -282,15 +304,18 @@ __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g
 // Called by all threads once, before the first res_run_batches: barriers, the numerator
 // table, and the TMA bulk copies of the pair table (they land while the first batch's
 // coordinates are being built).  Ends with a block-wide barrier.
+template <bool STREAM = false>
 __device__ __forceinline__ void res_init(const ResSmem &m, const ResArgs &g, bool load_table) {
   const int tid = threadIdx.x;
   if (tid < 256) m.n2lut[tid] = 2.0 * tid;
   if (tid == 0) {
-    mbar_init(&m.full[0], kRPT); mbar_init(&m.full[1], kRPT);
+    mbar_init(&m.full[0], ResRoles<STREAM>::NB * 32); mbar_init(&m.full[1], ResRoles<STREAM>::NB * 32);
     mbar_init(&m.done[0], kRC); mbar_init(&m.done[1], kRC);
     mbar_init(m.tab, 1);
+    if constexpr (STREAM)
+      for (int i = 0; i < kRStages; ++i) { mbar_init(&m.tfull[i], 1); mbar_init(&m.tempty[i], kRC); }
     mbar_init_fence();
-    if (load_table && g.E_res > 0) {
+    if (!STREAM && load_table && g.E_res > 0) {
       const uint32_t tb = 4u * static_cast<uint32_t>(g.E_res), nbytes = static_cast<uint32_t>(res_align16(static_cast<size_t>(g.E_res)));
       mbar_expect_tx(m.tab, tb + nbytes);
       for (uint32_t off = 0; off < tb; off += 32768u)
@@ -309,17 +334,36 @@ __device__ __forceinline__ void res_init(const ResSmem &m, const ResArgs &g, boo
 //   src.cursor(batch, t)          tour in slot t of the batch (producer side)
 //   src.prefetch(batch, t)        optional L2 prefetch of a later batch
 //   src.store(batch, t, score)    called once per slot with the finished score
-template <int T, bool SUB, typename Src>
+template <int T, bool SUB, bool STREAM, typename Src>
 __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem &m, const Src &src, int first, int stride, int nb,
                                                 int &kdone, bool &table_ready) {
+  constexpr int NB = ResRoles<STREAM>::NB;
   const int tid = threadIdx.x;
   const int k0 = kdone;
   int k = k0;
-  // first batch of the call: nobody has anything to score yet, so all 24 warps build its coordinates
-  // (a third of the latency of the 8 producer warps); both X buffers are free here.  Producer thread
-  // p of the steady state is thread kRCT + p; in the joint build the thread index is just tid.
-  if (first < nb) src.template build<kRC + kRP, 2>(first, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
-  if (tid >= kRCT) {
+  const bool loader = STREAM && tid >= kRCT + NB * 32;
+  const int ntiles = g.E_res / kRPad;
+  // first batch of the call: nobody has anything to score yet, so all consumer and build warps fill its
+  // coordinates together (a third of the latency of the build warps alone); both X buffers are free here.
+  // Build thread p of the steady state is thread kRCT + p; in the joint build the thread index is just tid.
+  if (first < nb && !loader) src.template build<kRC + NB, 2>(first, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
+  if (loader) {
+    // ------------------------------------------------------------ table loader (STREAM)
+    if (tid == kRCT + NB * 32) {
+      for (int b = first; b < nb; b += stride, ++k)
+        for (int tile = 0; tile < ntiles; ++tile) {
+          const long long c = static_cast<long long>(k) * ntiles + tile;          // tiles pushed through the ring since res_init
+          const int st = static_cast<int>(c % kRStages);
+          if (c >= kRStages) mbar_wait(&m.tempty[st], static_cast<uint32_t>((c / kRStages - 1) & 1));
+          unsigned char *dst = m.ring + static_cast<size_t>(st) * kRTileBytes;
+          mbar_expect_tx(&m.tfull[st], kRTileBytes);
+          bulk_copy_g2s(dst, reinterpret_cast<const unsigned char *>(g.pairs) + static_cast<size_t>(tile) * 4 * kRPad, 4 * kRPad, &m.tfull[st]);
+          bulk_copy_g2s(dst + 4 * kRPad, g.nl8 + static_cast<size_t>(tile) * kRPad, kRPad, &m.tfull[st]);
+        }
+    } else {
+      for (int b = first; b < nb; b += stride) ++k;
+    }
+  } else if (tid >= kRCT) {
     // ------------------------------------------------------------ producers
     const int ptid = tid - kRCT;
     auto finalize = [&](int kk, int batch) {
@@ -335,7 +379,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
     for (int b = first; b < nb; b += stride, ++k) {
       if (k - k0 >= 2) finalize(k - 2, b - 2 * stride);
       if (ptid < T) src.prefetch(b + stride, ptid);   // next batch's rows: HBM -> L2 now
-      if (k > k0) src.template build<kRP, 1>(b, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
+      if (k > k0) src.template build<NB, 1>(b, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
       mbar_arrive(&m.full[k & 1]);
     }
     for (int kk = max(k0, k - 2); kk < k; ++kk) finalize(kk, first + (kk - k0) * stride);
@@ -344,7 +388,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
     const int lane = tid & 31, wid = tid >> 5;
     for (int b = first; b < nb; b += stride, ++k) {
       const int buf = k & 1;
-      if (!table_ready) { mbar_wait(m.tab, 0); table_ready = true; }
+      if (!STREAM && !table_ready) { mbar_wait(m.tab, 0); table_ready = true; }
       mbar_wait(&m.full[buf], (k >> 1) & 1);
       const uint32_t *X = m.X0 + buf * m.xstride;
       double acc[T];
@@ -352,15 +396,32 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
       for (int t = 0; t < T; ++t) acc[t] = 0.0;
       // entry j of thread tid in iteration I is stored at [(I*kRCT + tid)*4 + j]: one LDS.128 + one LDS.32
       // fetch the thread's four entries and link counts (logical order: order_pairs(), ahx_core.cu)
-      const uint4 *table4 = reinterpret_cast<const uint4 *>(m.table);
-      const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(m.nl8);
-      for (int i = tid; i < g.E_res / kRUnroll; i += kRCT) {
-        const uint4 p = table4[i];
-        const uint32_t n = nl8x4[i];
-        res_pair_terms<T, SUB>(X, p.x, m.n2lut[n & 0xffu], acc);
-        res_pair_terms<T, SUB>(X, p.y, m.n2lut[(n >> 8) & 0xffu], acc);
-        res_pair_terms<T, SUB>(X, p.z, m.n2lut[(n >> 16) & 0xffu], acc);
-        res_pair_terms<T, SUB>(X, p.w, m.n2lut[n >> 24], acc);
+      if constexpr (!STREAM) {
+        const uint4 *table4 = reinterpret_cast<const uint4 *>(m.table);
+        const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(m.nl8);
+        for (int i = tid; i < g.E_res / kRUnroll; i += kRCT) {
+          const uint4 p = table4[i];
+          const uint32_t n = nl8x4[i];
+          res_pair_terms<T, SUB, true>(X, p.x, m.n2lut[n & 0xffu], acc);
+          res_pair_terms<T, SUB, true>(X, p.y, m.n2lut[(n >> 8) & 0xffu], acc);
+          res_pair_terms<T, SUB, true>(X, p.z, m.n2lut[(n >> 16) & 0xffu], acc);
+          res_pair_terms<T, SUB, true>(X, p.w, m.n2lut[n >> 24], acc);
+        }
+      } else {
+        for (int tile = 0; tile < ntiles; ++tile) {
+          const long long c = static_cast<long long>(k) * ntiles + tile;
+          const int st = static_cast<int>(c % kRStages);
+          mbar_wait(&m.tfull[st], static_cast<uint32_t>((c / kRStages) & 1));
+          const unsigned char *src_tile = m.ring + static_cast<size_t>(st) * kRTileBytes;
+          const uint4 p = reinterpret_cast<const uint4 *>(src_tile)[tid];
+          const uint32_t n = reinterpret_cast<const uint32_t *>(src_tile + 4 * kRPad)[tid];
+          res_pair_terms<T, SUB, false>(X, p.x, m.n2lut[n & 0xffu], acc);
+          res_pair_terms<T, SUB, false>(X, p.y, m.n2lut[(n >> 8) & 0xffu], acc);
+          res_pair_terms<T, SUB, false>(X, p.z, m.n2lut[(n >> 16) & 0xffu], acc);
+          res_pair_terms<T, SUB, false>(X, p.w, m.n2lut[n >> 24], acc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&m.tempty[st]);   // this warp is done with the stage
+        }
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -374,15 +435,15 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
   kdone = k;
 }
 
-template <int T, bool SUB, typename Src>
+template <int T, bool SUB, bool STREAM, typename Src>
 __global__ void __launch_bounds__(kRThreads, 1) eval_m_res_kernel(ResArgs g, Src src) {
   extern __shared__ __align__(128) unsigned char smem_res[];
-  const ResSmem m = res_carve<T>(smem_res, g);
+  const ResSmem m = res_carve<T, STREAM>(smem_res, g);
   const int nb = src.n_batches();
-  res_init(m, g, static_cast<int>(blockIdx.x) < nb);
+  res_init<STREAM>(m, g, static_cast<int>(blockIdx.x) < nb);
   int kdone = 0;
   bool table_ready = g.E_res == 0;
-  res_run_batches<T, SUB>(g, m, src, blockIdx.x, gridDim.x, nb, kdone, table_ready);
+  res_run_batches<T, SUB, STREAM>(g, m, src, blockIdx.x, gridDim.x, nb, kdone, table_ready);
 }
 
 }  // namespace ahx

@@ -199,6 +199,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -277,7 +278,7 @@ def main():
     sm_mhz = clocks.peak_mhz()
     smem_peak = 128.0 * eng.sm_count() * sm_mhz * 1e6 / 1e9                      # GB/s: 128 B/clk/SM
     kind, tpb = eng.eval_m_kernel(P, L)
-    flop_per_pair = 10.0 if kind == 2 else 2.0 * e_act / max(E, 1)               # the streaming kernels divide in-window pairs only
+    flop_per_pair = 10.0 if kind >= 2 else 2.0 * e_act / max(E, 1)               # the streaming kernels divide in-window pairs only
     legs = {"smem": (P * 8.0 * E / kern_s / 1e9, smem_peak, "GB/s"),
             "fp64": (P * E * flop_per_pair / kern_s / 1e12, dfma_tflops, "TFLOP/s"),
             "hbm": (P * (4.0 * L + 8.0) / kern_s / 1e9, HBM_PEAK, "GB/s")}
@@ -289,7 +290,7 @@ def main():
             "peak_source": {"smem": "128 B/clk/SM x %d SMs x %.0f MHz (SM clock sampled during the timed region)" % (eng.sm_count(), sm_mhz),
                             "fp64": "DFMA microbenchmark measured live by this run (ahx_probe_fp64; MEASURED_PEAKS.json has no fp64 figure)",
                             "hbm": "MEASURED_PEAKS.json hbm_gbs"}[bound],
-            "kernel": {2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[kind], "tours_per_batch": tpb,
+            "kernel": {3: "eval_m_res_kernel (table streamed)", 2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[kind], "tours_per_batch": tpb,
             "algorithmic_per_tour": {"stored_pairs_E": E, "fp64_flop": flop_per_pair * E, "smem_gather_bytes": 8 * E,
                                      "in_window_pairs_E_act": e_act, "hbm_bytes": 4 * L + 8},
             "issue_model": {"issue_cycles_per_pair_term": 18.3, "note": "SASS of the consumer loop: 5 fp64 (2 issue cycles each, term_probe.cu) + 8.3 other instructions per (pair, tour); "

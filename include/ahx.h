@@ -140,8 +140,9 @@ int ahx_pop_set(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours);
 int ahx_pop_eval_m(ahx_ctx *ctx, int32_t kind, int32_t repeat, float *elapsed_ms);
 int ahx_pop_scores(ahx_ctx *ctx, double *out /* P */);
 /* Which kernel ahx_eval_m / ahx_pop_eval_m(kind 0) would launch for P tours of length L:
- * 2 eval_m_res_kernel (pair table resident in shared memory), 1 eval_m_x32_kernel (32-bit
- * coordinates, table streamed), 0 eval_m_sparse_kernel (fp64 coordinates).
+ * 2 eval_m_res_kernel with the pair table resident in shared memory, 3 the same kernel with
+ * the table streamed through a ring (large groups), 1 eval_m_x32_kernel (32-bit coordinates,
+ * one CTA per T tours), 0 eval_m_sparse_kernel (fp64 coordinates).
  * *tours_per_batch (optional) receives the tours one CTA scores together. */
 int ahx_eval_m_kernel(const ahx_ctx *ctx, int32_t P, int32_t L, int32_t *tours_per_batch);
 /* Writes `bytes` of device memory (> L2) to evict the L2 between timed runs. */

@@ -67,16 +67,20 @@ def test_eval_m_population_fixture(fix, P):
     assert close(eng.eval_m(tours.astype(np.uint16)), want)
 
 
-@pytest.mark.parametrize("path", ["resident", "stream32", "fp64"])
+@pytest.mark.parametrize("path", ["resident", "resident-streamed", "stream32", "fp64"])
 @pytest.mark.parametrize("T", ["1", "2", "4"])
 def test_eval_m_tours_per_cta(syn, T, path, monkeypatch):
-    """All three formulations of the contig-space kernel (persistent kernel with the
-    pair table resident in shared memory; 32-bit coordinates + TMA-streamed pair
-    table; fp64 coordinates fallback) at every tours-per-batch setting."""
+    """All formulations of the contig-space kernel (persistent kernel with the pair
+    table resident in shared memory or streamed through a TMA ring; one-CTA-per-batch
+    kernel with 32-bit coordinates; fp64 coordinates fallback) at every
+    tours-per-batch setting, full tours and sub-tours."""
     eng, clm, orc = syn
     monkeypatch.setenv("AHX_EVAL_T", T)
-    monkeypatch.setenv("AHX_EVAL_RES", "1" if path == "resident" else "0")
+    monkeypatch.setenv("AHX_EVAL_RES", "1" if path.startswith("resident") else "0")
+    monkeypatch.setenv("AHX_EVAL_STREAM", "1" if path == "resident-streamed" else "0")
     monkeypatch.setenv("AHX_EVAL_FP64", "1" if path == "fp64" else "0")
+    if path.startswith("resident"):
+        assert eng.eval_m_kernel(203) == (3 if path == "resident-streamed" else 2, int(T))
     rng = np.random.default_rng(int(T))
     tours = np.stack([rng.permutation(clm.N) for _ in range(203)]).astype(np.int32)
     tours[0] = np.arange(clm.N); tours[1] = np.arange(clm.N)[::-1]
@@ -84,6 +88,8 @@ def test_eval_m_tours_per_cta(syn, T, path, monkeypatch):
     got = eng.eval_m(tours)
     assert close(got, want)
     assert (got == eng.eval_m(tours)).all()          # fixed-shape reductions: bit-reproducible
+    sub = np.stack([rng.permutation(clm.N)[: clm.N // 3] for _ in range(37)]).astype(np.int32)
+    assert close(eng.eval_m(sub), orc.population_evaluate(sub.astype(np.int64), nthreads=4))
 
 
 def test_eval_m_limit_window_and_subtours(syn):
@@ -275,7 +281,7 @@ def test_ga_elites_and_migrants(fix):
     eng.ga_end()
 
 
-@pytest.mark.parametrize("path", ["persistent", "two-kernel", "fp64"])
+@pytest.mark.parametrize("path", ["persistent", "persistent-streamed", "two-kernel", "fp64"])
 @pytest.mark.parametrize("gaT", ["1", "2", "4"])
 def test_ga_population_is_consistent_on_every_path(syn, path, gaT, monkeypatch):
     """After many generations every individual must still be what its stored state says:
@@ -284,8 +290,9 @@ def test_ga_population_is_consistent_on_every_path(syn, path, gaT, monkeypatch):
     (they are derived by per-operator transforms, never recomputed).  Same seed => the
     three implementations of CLM.GARun follow the same trajectory."""
     eng, clm, orc = syn
-    if path != "persistent":
+    if not path.startswith("persistent"):
         monkeypatch.setenv("AHX_GA_RES", "0")
+    monkeypatch.setenv("AHX_EVAL_STREAM", "1" if path == "persistent-streamed" else "0")
     if path == "fp64":
         monkeypatch.setenv("AHX_EVAL_FP64", "1")
         monkeypatch.setenv("AHX_EVAL_RES", "0")

@@ -422,30 +422,41 @@ ResPlan resident_plan(const ahx_ctx *ctx, int32_t P) {
   ResPlan pl;
   if (const char *env = getenv("AHX_EVAL_RES")) if (!atoi(env)) return pl;
   if (const char *env = getenv("AHX_EVAL_FP64")) if (atoi(env)) return pl;
-  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0) return pl;
-  auto fits_res = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res) + 1024 <= ctx->smem_optin && static_cast<uint64_t>(ctx->N) * 4u * t <= 65535u; };
-  auto fits_str = [&](int t) { return res_smem_bytes(t, ctx->N, ctx->E_res, true) + 1024 <= ctx->smem_optin; };
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res[0] <= 0) return pl;
+  auto fits = [&](int t, bool stream, bool sizes) {
+    if (!stream && static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) return false;
+    return res_smem_bytes(t, ctx->N, ctx->E_res[res_ti(t)], stream, sizes) + 1024 <= ctx->smem_optin;
+  };
   int forced = 0;
   if (const char *env = getenv("AHX_EVAL_T")) { const int t = atoi(env); if (t == 1 || t == 2 || t == 4) forced = t; }
   const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
   const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
-  for (int t : {4, 2, 1}) {
-    if (forced && t != forced) continue;
-    if (!forced && t > 1 && (P + t - 1) / t < ctx->sm_count) continue;   // keep one batch per SM
-    if (!only_stream && fits_res(t)) { pl.T = t; pl.stream = false; return pl; }
-    if (!no_stream && fits_str(t)) { pl.T = t; pl.stream = true; return pl; }
+  const bool no_sizes = getenv("AHX_EVAL_SIZES") && !atoi(getenv("AHX_EVAL_SIZES"));
+  // preference: the table resident, then the largest T; the contig sizes staged in shared memory whenever
+  // they fit next to the rest (the producers' size gathers from global memory cost as many LSU cycles as
+  // all of the consumers' shared-memory traffic) -- for a streamed table even at the price of a smaller T
+  for (int stream = 0; stream < 2; ++stream) {
+    if (stream ? no_stream : only_stream) continue;
+    for (int pass = 0; pass < 2; ++pass)          // streamed: first insist on staged sizes, then take any T
+      for (int t : {4, 2, 1}) {
+        if (forced && t != forced) continue;
+        if (!forced && t > 1 && (P + t - 1) / t < ctx->sm_count) continue;   // keep one batch per SM
+        const bool sz = !no_sizes && fits(t, stream != 0, true);
+        if (stream && pass == 0 && !sz && !no_sizes) continue;
+        if (sz || fits(t, stream != 0, false)) { pl.T = t; pl.stream = stream != 0; pl.sizes = sz; return pl; }
+      }
   }
   return pl;
 }
 int resident_T(const ahx_ctx *ctx, int32_t P) { return resident_plan(ctx, P).T; }
 
 template <int T, bool STREAM, typename IdxT>
-static cudaError_t launch_res_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
+static cudaError_t launch_res_t(ahx_ctx *ctx, bool sizes, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
   auto kern = L < ctx->N ? eval_m_res_kernel<T, true, STREAM, ResDirect<T, IdxT>> : eval_m_res_kernel<T, false, STREAM, ResDirect<T, IdxT>>;
-  const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res, STREAM);
+  const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res[res_ti(T)], STREAM, sizes);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  ResArgs g{ctx->d_rpairs[STREAM ? 3 : (T == 4 ? 2 : T - 1)].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, L, ctx->d_errflag.p};
+  ResArgs g{(STREAM ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, L, ctx->d_errflag.p, sizes ? 1 : 0};
   ResDirect<T, IdxT> src{};
   src.tours = tours; src.rows = rows; src.P = P; src.L = L; src.out = out;
   const int nb = (P + T - 1) / T;
@@ -458,15 +469,15 @@ template <typename IdxT>
 static cudaError_t launch_res(ahx_ctx *ctx, const ResPlan &pl, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
   if (pl.stream) {
     switch (pl.T) {
-      case 4: return launch_res_t<4, true, IdxT>(ctx, tours, rows, P, L, out, s);
-      case 2: return launch_res_t<2, true, IdxT>(ctx, tours, rows, P, L, out, s);
-      default: return launch_res_t<1, true, IdxT>(ctx, tours, rows, P, L, out, s);
+      case 4: return launch_res_t<4, true, IdxT>(ctx, pl.sizes, tours, rows, P, L, out, s);
+      case 2: return launch_res_t<2, true, IdxT>(ctx, pl.sizes, tours, rows, P, L, out, s);
+      default: return launch_res_t<1, true, IdxT>(ctx, pl.sizes, tours, rows, P, L, out, s);
     }
   }
   switch (pl.T) {
-    case 4: return launch_res_t<4, false, IdxT>(ctx, tours, rows, P, L, out, s);
-    case 2: return launch_res_t<2, false, IdxT>(ctx, tours, rows, P, L, out, s);
-    default: return launch_res_t<1, false, IdxT>(ctx, tours, rows, P, L, out, s);
+    case 4: return launch_res_t<4, false, IdxT>(ctx, pl.sizes, tours, rows, P, L, out, s);
+    case 2: return launch_res_t<2, false, IdxT>(ctx, pl.sizes, tours, rows, P, L, out, s);
+    default: return launch_res_t<1, false, IdxT>(ctx, pl.sizes, tours, rows, P, L, out, s);
   }
 }
 
@@ -584,31 +595,35 @@ static int validate_tours(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours,
 // (a mod 8, b mod 8) buckets, largest bucket first); blocks that cannot be
 // filled are padded with (0,0,0) entries, which contribute nothing (d = 0).
 // The order of the terms only changes the (fixed) summation order.
-void order_pairs(int64_t E, const int32_t *pa, const int32_t *pb, std::vector<int64_t> *order /* -1 = padding */) {
-  std::vector<std::vector<int64_t>> bucket(64);
-  for (int64_t e = E - 1; e >= 0; --e) bucket[(pa[e] & 7) * 8 + (pb[e] & 7)].push_back(e);   // pop_back yields ascending e
+// W: lanes that are served together by one shared-memory wavefront of the coordinate gather =
+// 32 / T (a contig's T coordinates are 4T bytes: 8 lanes x 16 B, 16 x 8 B or 32 x 4 B per 128 B);
+// within every aligned group of W entries all `a mod W` and all `b mod W` are distinct.
+void order_pairs(int64_t E, const int32_t *pa, const int32_t *pb, std::vector<int64_t> *order /* -1 = padding */, int W) {
+  std::vector<std::vector<int64_t>> bucket(static_cast<size_t>(W) * W);
+  for (int64_t e = E - 1; e >= 0; --e) bucket[static_cast<size_t>(pa[e] % W) * W + (pb[e] % W)].push_back(e);   // pop_back yields ascending e
   order->clear();
   order->reserve(static_cast<size_t>(E + E / 8 + 512));
   int64_t left = E;
   int rot = 0;
+  std::vector<char> used_b(W);
   while (left > 0) {
-    bool used_b[8] = {false, false, false, false, false, false, false, false};
+    std::fill(used_b.begin(), used_b.end(), 0);
     int filled = 0;
-    for (int i = 0; i < 8; ++i) {
-      const int r = (i + rot) & 7;
+    for (int i = 0; i < W; ++i) {
+      const int r = (i + rot) % W;
       int best = -1; size_t best_n = 0;
-      for (int c = 0; c < 8; ++c) {
-        const size_t n = bucket[r * 8 + c].size();
-        if (!used_b[c] && n > best_n) { best = c; best_n = n; }
+      for (int cc = 0; cc < W; ++cc) {
+        const size_t n = bucket[static_cast<size_t>(r) * W + cc].size();
+        if (!used_b[cc] && n > best_n) { best = cc; best_n = n; }
       }
       if (best >= 0) {
-        order->push_back(bucket[r * 8 + best].back());
-        bucket[r * 8 + best].pop_back();
-        used_b[best] = true; --left; ++filled;
+        order->push_back(bucket[static_cast<size_t>(r) * W + best].back());
+        bucket[static_cast<size_t>(r) * W + best].pop_back();
+        used_b[best] = 1; --left; ++filled;
       }
     }
-    for (; filled < 8; ++filled) order->push_back(-1);
-    rot = (rot + 1) & 7;
+    for (; filled < W; ++filled) order->push_back(-1);
+    rot = (rot + 1) % W;
   }
   while (order->size() % kBlock) order->push_back(-1);
 }
@@ -716,7 +731,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); for (auto &b : ctx->d_rpairs) b.release(); ctx->d_rnl8.release(); ctx->d_pa.release(); ctx->d_pb.release();
+  ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); for (auto &b : ctx->d_rpairs) b.release(); for (auto &b : ctx->d_rraw) b.release(); for (auto &b : ctx->d_rnl8) b.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
   ctx->d_tours.release(); ctx->d_res_tours.release(); ctx->d_res_scores.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();
   ctx->d_flush.release(); ctx->d_errflag.release();
@@ -793,7 +808,7 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
     AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes32.p, s32.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
     AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<int64_t> ord;
-    order_pairs(E, pa, pb, &ord);
+    order_pairs(E, pa, pb, &ord, 8);
     ctx->E_pad = static_cast<int64_t>(ord.size());
     if (ctx->coo16) {
       std::vector<uint2> o16(ord.size());
@@ -810,46 +825,44 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
     }
     // resident-table form (ahx_resident.cuh): 8-bit link counts, so a pair with more
     // than 255 links becomes several entries; ordered and padded like the list above
-    ctx->E_res = 0;
+    for (auto &er : ctx->E_res) er = 0;
     if (ctx->coo16 && E > 0) {
       std::vector<int32_t> xa, xb, xn;
       xa.reserve(E); xb.reserve(E); xn.reserve(E);
       for (int64_t e = 0; e < E; ++e)
         for (int32_t left = nl[e]; left > 0; left -= 255) { xa.push_back(pa[e]); xb.push_back(pb[e]); xn.push_back(std::min(left, 255)); }
-      if (xa.size() <= static_cast<size_t>(8) * E + 4096) {   // absurd link counts: leave it to the streaming kernels
+      // storage order: consumer thread tid reads its kRUnroll entries of iteration I as one vector, so the
+      // logical entry I*kRPad + j*kRCT + tid lives at (I*kRCT + tid)*kRUnroll + j
+      auto phys = [](size_t i) { const size_t I = i / kRPad, r = i % kRPad; return (I * kRCT + r % kRCT) * kRUnroll + r / kRCT; };
+      for (int ti = 0; ti < 3 && xa.size() <= static_cast<size_t>(8) * E + 4096; ++ti) {   // (absurd link counts: leave it to the fallback kernels)
+        // one ordering per tours-per-batch T = 1, 2, 4: conflict-free groups of 32 / T lanes
+        const uint32_t T = 1u << ti, stride = 4u * T;
         std::vector<int64_t> rord;
-        order_pairs(static_cast<int64_t>(xa.size()), xa.data(), xb.data(), &rord);
+        order_pairs(static_cast<int64_t>(xa.size()), xa.data(), xb.data(), &rord, static_cast<int>(32u / T));
         const size_t er = (rord.size() + kRPad - 1) / kRPad * kRPad;
-        std::vector<uint8_t> r8(er + 16, 0);
+        std::vector<uint8_t> r8p(er + 16, 0);
         std::vector<uint32_t> ra(er, 0u), rb(er, N > 1 ? 1u : 0u);   // padding: contigs (0, 1) with 0 links
         for (size_t i = 0; i < rord.size(); ++i) {
           if (rord[i] < 0) continue;
           const int64_t x = rord[i];
           ra[i] = static_cast<uint32_t>(xa[x]); rb[i] = static_cast<uint32_t>(xb[x]);
-          r8[i] = static_cast<uint8_t>(xn[x]);
+          r8p[phys(i)] = static_cast<uint8_t>(xn[x]);
         }
-        // storage order: consumer thread tid reads its kRUnroll entries of iteration I as one vector, so the
-        // logical entry I*kRPad + j*kRCT + tid lives at (I*kRCT + tid)*kRUnroll + j
-        auto phys = [](size_t i) { const size_t I = i / kRPad, r = i % kRPad; return (I * kRCT + r % kRCT) * kRUnroll + r / kRCT; };
-        std::vector<uint8_t> r8p(er + 16, 0);
-        for (size_t i = 0; i < er; ++i) r8p[phys(i)] = r8[i];
-        AHX_CUDA(ctx, ctx->d_rnl8.reserve(er + 16));
-        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8.p, r8p.data(), er + 16, cudaMemcpyHostToDevice, ctx->stream));
+        AHX_CUDA(ctx, ctx->d_rnl8[ti].reserve(er + 16));
+        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rnl8[ti].p, r8p.data(), er + 16, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<uint32_t> rp(er);
-        for (int ti = 0; ti < 3; ++ti) {   // one table per tours-per-batch T = 1, 2, 4: entries are byte offsets into X
-          const uint32_t stride = 4u << ti;
-          if (static_cast<uint64_t>(N) * stride > 65535u) continue;
+        if (static_cast<uint64_t>(N) * stride <= 65535u) {   // resident mode: entries are byte offsets into X
           for (size_t i = 0; i < er; ++i) rp[phys(i)] = (ra[i] * stride) | ((rb[i] * stride) << 16);
           AHX_CUDA(ctx, ctx->d_rpairs[ti].reserve(er));
           AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs[ti].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
           AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // rp is reused
         }
-        // the same list as plain contig indices a | b << 16 for the streamed-table mode (any N <= 65535, any T)
+        // streamed mode: plain contig indices a | b << 16 (N * 4T may exceed 16 bits)
         for (size_t i = 0; i < er; ++i) rp[phys(i)] = ra[i] | (rb[i] << 16);
-        AHX_CUDA(ctx, ctx->d_rpairs[3].reserve(er));
-        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rpairs[3].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
+        AHX_CUDA(ctx, ctx->d_rraw[ti].reserve(er));
+        AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_rraw[ti].p, rp.data(), 4 * er, cudaMemcpyHostToDevice, ctx->stream));
         AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->E_res = static_cast<int64_t>(er);
+        ctx->E_res[ti] = static_cast<int64_t>(er);
       }
     }
   }

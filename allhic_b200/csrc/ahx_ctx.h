@@ -65,9 +65,11 @@ struct ahx_ctx {
   // resident-table kernel (ahx_resident.cuh): per entry the byte offsets of the two contigs in X,
   // (a*4T) | (b*4T) << 16, one table per T = 1, 2, 4, and an 8-bit link count (pairs with more than
   // 255 links are split over several entries); bank-conflict-free order, padded with (0, 1, 0)
-  ahx::DevBuf<uint32_t> d_rpairs[4];   // [3]: plain contig indices a | b << 16 (streamed-table mode)
-  ahx::DevBuf<uint8_t> d_rnl8;
-  int64_t E_res = 0;                      // multiple of kRPad (0 when E == 0)
+  // index ti = log2(T): every T has its own bank-conflict-free ordering (groups of 32 / T lanes)
+  ahx::DevBuf<uint32_t> d_rpairs[3];   // resident mode: byte offsets into X (only when N * 4T < 64 KB)
+  ahx::DevBuf<uint32_t> d_rraw[3];     // streamed mode: contig indices a | b << 16
+  ahx::DevBuf<uint8_t> d_rnl8[3];
+  int64_t E_res[3] = {0, 0, 0};           // entries, multiple of kRPad (0 when E == 0)
   bool x32_ok = false;                    // 2*sum(sizes) + 2*LIMIT + 2 < 2^32
   ahx::DevBuf<int32_t> d_pa, d_pb, d_slots, d_hist, d_M;
   bool dense_ready = false;
@@ -142,9 +144,10 @@ size_t eval_x32_smem_bytes(int T, bool coo16, int32_t N, int32_t L);
 bool use_x32(const ahx_ctx *ctx, int32_t L);
 // Tours per batch of the persistent evaluate kernel for a population of P tours (0: not usable)
 // and whether the pair table is streamed through a ring instead of resident in shared memory.
-struct ResPlan { int T = 0; bool stream = false; };
+struct ResPlan { int T = 0; bool stream = false; bool sizes = false; };
 ResPlan resident_plan(const ahx_ctx *ctx, int32_t P);
 int resident_T(const ahx_ctx *ctx, int32_t P);
+inline int res_ti(int T) { return T == 4 ? 2 : T - 1; }
 }  // namespace ahx
 
 #define AHX_CUDA(ctx, call)                                              \

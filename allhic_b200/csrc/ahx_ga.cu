@@ -545,7 +545,7 @@ static std::vector<uint32_t> tour_coordinates(const ahx_ctx *ctx, int32_t L, con
 static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double mut_prob) {
   GaResCfg c;
   if (const char *env = getenv("AHX_GA_RES")) if (!atoi(env)) return c;
-  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res <= 0 || L != ctx->N || 2 * static_cast<int64_t>(P) > 32 * kGaMaxWords) return c;
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res[0] <= 0 || L != ctx->N || 2 * static_cast<int64_t>(P) > 32 * kGaMaxWords) return c;
   const double expect = std::max(1.0, P * mut_prob);
   const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
   const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
@@ -555,7 +555,7 @@ static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double m
     for (int stream = 0; stream < 2; ++stream) {   // table resident in shared memory if it fits, streamed otherwise
       if (stream ? no_stream : only_stream) continue;
       if (!stream && static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) continue;
-      const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res, stream != 0) + ga_res_extra_bytes(P, t, nbmax);
+      const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res[res_ti(t)], stream != 0) + ga_res_extra_bytes(P, t, nbmax);
       if (smem + 1024 > ctx->smem_optin) continue;
       c.T = t; c.G = G; c.nbmax = nbmax; c.smem = smem; c.stream = stream != 0;
       return true;
@@ -609,7 +609,7 @@ static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->ga_smem));
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
-  ResArgs g{ctx->d_rpairs[STREAM ? 3 : (T == 4 ? 2 : T - 1)].p, ctx->d_rnl8.p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res), ctx->N, ctx->ga_L, ctx->d_errflag.p};
+  ResArgs g{(STREAM ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, ctx->ga_L, ctx->d_errflag.p, 0};
   GaRes q = make_res(ctx);
   void *args[] = {&g, &q, &n_gens};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(ctx->ga_G), dim3(kRThreads), args, ctx->ga_smem, s);

@@ -57,12 +57,13 @@ struct ResArgs {
   const uint32_t *sizes32;    // [N]
   int E_res, N, L;
   int *errflag;
+  int sizes_in_smem;          // the contig sizes are staged in shared memory (4N bytes) instead of gathered from global memory
 };
 
 __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 // dynamic shared memory of the resident kernel
-inline size_t res_smem_bytes(int T, int N, long long E_res, bool stream = false) {
-  return (stream ? static_cast<size_t>(kRStages) * kRTileBytes : res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res))) +
+inline size_t res_smem_bytes(int T, int N, long long E_res, bool stream = false, bool sizes = false) {
+  return (sizes ? res_align16(4ull * N) : 0) + (stream ? static_cast<size_t>(kRStages) * kRTileBytes : res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res))) +
          2 * res_align16(4ull * N * T) + (stream ? 8ull * 2 * kRStages : 0) +
          8ull * 256 + 8ull * 2 * kRC * T + res_align16(4ull * (kRC + kRP) * T) + 8 * 8;
 }
@@ -79,7 +80,7 @@ __device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes) {
 }
 
 template <int T, int NW, int BAR, typename Src>
-__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
+__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *sizes32, uint32_t *X,
                                             uint32_t *scan_scratch, int *errflag, int ptid);
 
 // ---- batch sources -------------------------------------------------------------
@@ -128,7 +129,7 @@ struct ResDirect {
     if (r >= 0) out[r] = score;
   }
   template <int NW, int BAR>
-  __device__ __forceinline__ void build(int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X, uint32_t *scratch,
+  __device__ __forceinline__ void build(int batch, int L, int N, const uint32_t *sizes32, uint32_t *X, uint32_t *scratch,
                                         int *errflag, int gtid) const {
     res_build_x<T, NW, BAR>(*this, batch, L, N, sizes32, X, scratch, errflag, gtid);
   }
@@ -151,7 +152,7 @@ struct ResDirect {
 // NW warps build one batch together (the kRP producer warps in steady state, all kRC + kRP
 // warps for the first batch of a call, when nothing else can run yet); BAR: named barrier.
 template <int T, int NW, int BAR, typename Src>
-__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *__restrict__ sizes32, uint32_t *X,
+__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *sizes32, uint32_t *X,
                                             uint32_t *scan_scratch /* NW*T */, int *errflag, int ptid) {
   constexpr int PPI = 4 * (32 / T);              // positions of one tour per warp instruction group
   constexpr int kU = 4;                          // groups in flight per lane (16 positions)
@@ -174,7 +175,7 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
 #pragma unroll
     for (int u = 0; u < kU; ++u)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) local += c[u][e] < static_cast<unsigned>(N) ? __ldg(sizes32 + c[u][e]) : 0u;
+      for (int e = 0; e < 4; ++e) local += c[u][e] < static_cast<unsigned>(N) ? sizes32[c[u][e]] : 0u;
   }
 #pragma unroll
   for (int d = T; d < 32; d <<= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
@@ -194,7 +195,7 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
       for (int e = 0; e < 4; ++e) {
         const bool on = p0 + u * PPI + e < end;
         if (on && c[u][e] >= static_cast<unsigned>(N)) { bad = true; c[u][e] = 0xFFFFFFFFu; }
-        sz[u][e] = c[u][e] != 0xFFFFFFFFu ? __ldg(sizes32 + c[u][e]) : 0u;
+        sz[u][e] = c[u][e] != 0xFFFFFFFFu ? sizes32[c[u][e]] : 0u;
       }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -241,6 +242,14 @@ __device__ __forceinline__ double rcp_pos(double x) {
 //   d - 1 < 2 LIMIT (unsigned).
 // Issue-slot model measured with profiles/microbench/term_probe.cu: an fp64 instruction
 // costs 2 issue cycles, anything else 1.
+// numerator 2n as a double: from the 256-entry table (one LDS.64; T = 4, where instruction issue is the
+// limit) or computed (one DADD; T <= 2, where the shared-memory pipe is: fewer gathers per table entry)
+template <int T>
+__device__ __forceinline__ double res_n2(const double *n2lut, uint32_t n8) {
+  if constexpr (T >= 4) return n2lut[n8];
+  else return u32_to_double(2u * n8);
+}
+
 // SCALED: p holds byte offsets (resident tables); otherwise contig indices a | b << 16 (the
 // streamed table of large groups, where N * 4T can exceed 16 bits).
 template <int T, bool SUB, bool SCALED>
@@ -275,6 +284,7 @@ struct ResSmem {
   uint32_t *table; uint8_t *nl8; uint32_t *X0; size_t xstride;
   double *n2lut, *partial; uint64_t *full, *done, *tab, *tfull, *tempty; uint32_t *scan_scratch;
   unsigned char *ring;       // STREAM: kRStages tiles
+  const uint32_t *sizes;     // contig sizes: shared-memory copy, or the global array
   unsigned char *extra;      // first byte after the evaluate layout (GA scratch)
 };
 
@@ -297,6 +307,8 @@ __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g
   m.full = bars; m.done = bars + 2; m.tab = bars + 4;
   if constexpr (STREAM) { m.tfull = reinterpret_cast<uint64_t *>(sp); m.tempty = m.tfull + kRStages; sp += 8ull * 2 * kRStages; }
   m.scan_scratch = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * (kRC + kRP) * T);
+  m.sizes = g.sizes32;
+  if (g.sizes_in_smem) { m.sizes = reinterpret_cast<const uint32_t *>(sp); sp += res_align16(4ull * g.N); }
   m.extra = sp;
   return m;
 }
@@ -308,6 +320,8 @@ template <bool STREAM = false>
 __device__ __forceinline__ void res_init(const ResSmem &m, const ResArgs &g, bool load_table) {
   const int tid = threadIdx.x;
   if (tid < 256) m.n2lut[tid] = 2.0 * tid;
+  if (g.sizes_in_smem)
+    for (int i = tid; i < g.N; i += kRThreads) const_cast<uint32_t *>(m.sizes)[i] = __ldg(g.sizes32 + i);
   if (tid == 0) {
     mbar_init(&m.full[0], ResRoles<STREAM>::NB * 32); mbar_init(&m.full[1], ResRoles<STREAM>::NB * 32);
     mbar_init(&m.done[0], kRC); mbar_init(&m.done[1], kRC);
@@ -346,7 +360,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
   // first batch of the call: nobody has anything to score yet, so all consumer and build warps fill its
   // coordinates together (a third of the latency of the build warps alone); both X buffers are free here.
   // Build thread p of the steady state is thread kRCT + p; in the joint build the thread index is just tid.
-  if (first < nb && !loader) src.template build<kRC + NB, 2>(first, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
+  if (first < nb && !loader) src.template build<kRC + NB, 2>(first, g.L, g.N, m.sizes, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, tid);
   if (loader) {
     // ------------------------------------------------------------ table loader (STREAM)
     if (tid == kRCT + NB * 32) {
@@ -379,7 +393,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
     for (int b = first; b < nb; b += stride, ++k) {
       if (k - k0 >= 2) finalize(k - 2, b - 2 * stride);
       if (ptid < T) src.prefetch(b + stride, ptid);   // next batch's rows: HBM -> L2 now
-      if (k > k0) src.template build<NB, 1>(b, g.L, g.N, g.sizes32, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
+      if (k > k0) src.template build<NB, 1>(b, g.L, g.N, m.sizes, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
       mbar_arrive(&m.full[k & 1]);
     }
     for (int kk = max(k0, k - 2); kk < k; ++kk) finalize(kk, first + (kk - k0) * stride);
@@ -396,31 +410,58 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
       for (int t = 0; t < T; ++t) acc[t] = 0.0;
       // entry j of thread tid in iteration I is stored at [(I*kRCT + tid)*4 + j]: one LDS.128 + one LDS.32
       // fetch the thread's four entries and link counts (logical order: order_pairs(), ahx_core.cu)
+      // UI table vectors (4 entries each) per thread are in flight at once, so that 16 independent
+      // reciprocal chains hide the MUFU/fp64 latency whatever T is
+      constexpr int UI = T >= 4 ? 1 : (T == 2 ? 2 : 4);
       if constexpr (!STREAM) {
         const uint4 *table4 = reinterpret_cast<const uint4 *>(m.table);
         const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(m.nl8);
-        for (int i = tid; i < g.E_res / kRUnroll; i += kRCT) {
-          const uint4 p = table4[i];
-          const uint32_t n = nl8x4[i];
-          res_pair_terms<T, SUB, true>(X, p.x, m.n2lut[n & 0xffu], acc);
-          res_pair_terms<T, SUB, true>(X, p.y, m.n2lut[(n >> 8) & 0xffu], acc);
-          res_pair_terms<T, SUB, true>(X, p.z, m.n2lut[(n >> 16) & 0xffu], acc);
-          res_pair_terms<T, SUB, true>(X, p.w, m.n2lut[n >> 24], acc);
+        const int nvec = g.E_res / kRUnroll;
+        for (int i = tid; i < nvec; i += UI * kRCT) {
+          uint4 p[UI]; uint32_t n[UI];
+#pragma unroll
+          for (int u = 0; u < UI; ++u) {
+            const int iu = min(i + u * kRCT, nvec - 1);
+            p[u] = table4[iu]; n[u] = i + u * kRCT < nvec ? nl8x4[iu] : 0u;   // beyond the end: zero link counts
+          }
+#pragma unroll
+          for (int u = 0; u < UI; ++u) {
+            res_pair_terms<T, SUB, true>(X, p[u].x, res_n2<T>(m.n2lut, n[u] & 0xffu), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].y, res_n2<T>(m.n2lut, (n[u] >> 8) & 0xffu), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].z, res_n2<T>(m.n2lut, (n[u] >> 16) & 0xffu), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].w, res_n2<T>(m.n2lut, n[u] >> 24), acc);
+          }
         }
       } else {
-        for (int tile = 0; tile < ntiles; ++tile) {
-          const long long c = static_cast<long long>(k) * ntiles + tile;
-          const int st = static_cast<int>(c % kRStages);
-          mbar_wait(&m.tfull[st], static_cast<uint32_t>((c / kRStages) & 1));
-          const unsigned char *src_tile = m.ring + static_cast<size_t>(st) * kRTileBytes;
-          const uint4 p = reinterpret_cast<const uint4 *>(src_tile)[tid];
-          const uint32_t n = reinterpret_cast<const uint32_t *>(src_tile + 4 * kRPad)[tid];
-          res_pair_terms<T, SUB, false>(X, p.x, m.n2lut[n & 0xffu], acc);
-          res_pair_terms<T, SUB, false>(X, p.y, m.n2lut[(n >> 8) & 0xffu], acc);
-          res_pair_terms<T, SUB, false>(X, p.z, m.n2lut[(n >> 16) & 0xffu], acc);
-          res_pair_terms<T, SUB, false>(X, p.w, m.n2lut[n >> 24], acc);
+        constexpr int US = UI > 2 ? 2 : UI;   // at most half of the ring's stages in use, the other half loading
+        for (int tile = 0; tile < ntiles; tile += US) {
+          uint4 p[US]; uint32_t n[US];
+#pragma unroll
+          for (int u = 0; u < US; ++u) {
+            if (tile + u < ntiles) {
+              const long long c = static_cast<long long>(k) * ntiles + tile + u;
+              const int st = static_cast<int>(c % kRStages);
+              mbar_wait(&m.tfull[st], static_cast<uint32_t>((c / kRStages) & 1));
+              const unsigned char *src_tile = m.ring + static_cast<size_t>(st) * kRTileBytes;
+              p[u] = reinterpret_cast<const uint4 *>(src_tile)[tid];
+              n[u] = reinterpret_cast<const uint32_t *>(src_tile + 4 * kRPad)[tid];
+            } else {
+              p[u] = make_uint4(0x10000u, 0x10000u, 0x10000u, 0x10000u); n[u] = 0u;   // contigs (0, 1), zero links
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < US; ++u) {
+            res_pair_terms<T, SUB, false>(X, p[u].x, res_n2<T>(m.n2lut, n[u] & 0xffu), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].y, res_n2<T>(m.n2lut, (n[u] >> 8) & 0xffu), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].z, res_n2<T>(m.n2lut, (n[u] >> 16) & 0xffu), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].w, res_n2<T>(m.n2lut, n[u] >> 24), acc);
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&m.tempty[st]);   // this warp is done with the stage
+          if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < US; ++u)
+              if (tile + u < ntiles) mbar_arrive(&m.tempty[static_cast<int>((static_cast<long long>(k) * ntiles + tile + u) % kRStages)]);   // done with the stage
+          }
         }
       }
 #pragma unroll

@@ -652,6 +652,7 @@ static int eval_m_host(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours, do
   AHX_CUDA(ctx, ctx->d_scores.reserve(P));
   // ~4 MB per chunk, at most 16 chunks, chunk sizes multiple of 4 tours
   int nchunk = static_cast<int>(std::min<size_t>(16, std::max<size_t>(1, total * sizeof(IdxT) / (4u << 20))));
+  if (const char *env = getenv("AHX_EVAL_CHUNKS")) nchunk = std::max(1, std::min(64, atoi(env)));
   int32_t per = ((P + nchunk - 1) / nchunk + 3) & ~3;
   nchunk = (P + per - 1) / per;
   while (static_cast<int>(ctx->chunk_ev.size()) < nchunk) {

@@ -905,10 +905,10 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
       AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     scatter_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[0].p, ctx->d_sel_rows.p, L, ctx->d_sel_tours.p);
-    for (int32_t m = 0; m < n; ++m) {   // the migrants' coordinate rows
-      const std::vector<uint32_t> xm = tour_coordinates(ctx, L, tours + static_cast<size_t>(m) * L);
-      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_xpool.p + static_cast<size_t>(freerows[m]) * ctx->N, xm.data(), sizeof(uint32_t) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
-      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::vector<uint32_t>> xrows(n);   // the migrants' coordinate rows (kept alive until the stream is drained below)
+    for (int32_t m = 0; m < n; ++m) {
+      xrows[m] = tour_coordinates(ctx, L, tours + static_cast<size_t>(m) * L);
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_xpool.p + static_cast<size_t>(freerows[m]) * ctx->N, xrows[m].data(), sizeof(uint32_t) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
     }
     set_rows_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_rowof[cur].p, ctx->d_sel_idx.p, ctx->d_sel_rows.p, n);
     ctx->launches += 3;

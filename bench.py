@@ -41,6 +41,18 @@ METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 
 
+_JSON_FD = None
+
+
+def emit(obj):
+    """The bench's one JSON line, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def workload(name):
     from allhic_b200 import synth
     cfg = synth.CONFIGS[name]
@@ -169,12 +181,12 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     v = args.steps * S / dt
     sample = "%d of the %d tours per step x %d steps, oracle/allhic_oracle.c orc_population_evaluate, %d threads" % (S, P, args.steps, threads)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": desc, "n_contigs": n, "population": P, "sample_per_step": S},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def main():
@@ -190,6 +202,12 @@ def main():
     ap.add_argument("--no-dense", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: native libraries (NCCL prints its version banner
+    # to fd 1) and stray prints are sent to stderr; the line itself is written to the saved descriptor.
+    sys.stdout.flush()
+    global _JSON_FD
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -389,7 +407,7 @@ def main():
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     pin_t.close(); pin_o.close(); eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -134,3 +134,29 @@ def test_synth_is_deterministic():
     a, b = synth.generate(120, 5), synth.generate(120, 5)
     assert (a["sizes"] == b["sizes"]).all() and (a["pa"] == b["pa"]).all() and all((x == y).all() for x, y in zip(a["dists"], b["dists"]))
     assert len(a["pa"]) > 120 and (a["pa"] < a["pb"]).all()
+
+
+def test_farm_runs_every_group_once_largest_first(tmp_path):
+    """One linkage group per GPU (allhic.go:170-173): the farm hands groups out
+    longest-processing-time-first to whichever device is free; a stand-in for the
+    host binary records what it was asked to do."""
+    import stat
+    from allhic_b200 import farm
+    fake = tmp_path / "fake-allhic"
+    fake.write_text("#!/bin/sh\n# optimize <refile> <clmfile> --device <d>\n"
+                    "echo \"Current iteration GA2-500: max_score=0.5$5\"\necho \"$2 $5\" >> %s/calls.log\necho 'NOTICE Success' >&2\n" % tmp_path)
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    groups = []
+    for g, n in enumerate([5, 50, 20, 35]):
+        ids = tmp_path / ("g%d.ids" % g)
+        ids.write_text("#Contig\tRECounts\tLength\n" + "".join("t%d\t1\t100\n" % i for i in range(n)))
+        (tmp_path / ("g%d.clm" % g)).write_text("")
+        groups.append((str(ids), str(tmp_path / ("g%d.clm" % g))))
+    res = farm.optimize_groups(groups, devices=[0, 1], binary=str(fake))
+    assert [r["group"] for r in res] == [0, 1, 2, 3] and all(r["ok"] for r in res)
+    assert [r["n_contigs"] for r in res] == [5, 50, 20, 35]
+    assert all(r["final_score"] is not None and r["device"] in (0, 1) for r in res)
+    calls = (tmp_path / "calls.log").read_text().split("\n")
+    assert sorted(c.split()[0] for c in calls if c) == sorted(g[0] for g in groups)   # each group exactly once
+    first_two = {c.split()[0] for c in calls[:2]}
+    assert str(tmp_path / "g1.ids") in first_two                                        # the largest group starts first

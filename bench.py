@@ -386,6 +386,19 @@ def main():
         f_s = time.perf_counter() - t0
         out["orientation"] = {"eval_q_per_s_e2e": nq / q_s, "batch": nq, "flip_one_pass_ms_e2e": f_s * 1e3, "tour_length": int(L),
                               "note": "host buffers through ahx_eval_q / ahx_flip_one; the reference does 1 + L full EvaluateQ per flipOne pass"}
+        if world == 1 and args.cpu_seconds > 0:
+            # the CPU restatement beside it: EvaluateQ as the reference does it (dense 96*N^2-byte Q() rebuilt per call,
+            # orientation.go:137-193) and with the map lookup that avoids Q(); a flipOne pass = (1 + L) such calls
+            from oracle_lib import OracleCLM
+            orc = OracleCLM(clmf, ids)
+            orc.set_tour(tours[0].astype(np.int64)); orc.set_signs(signs[0])
+            t0 = time.perf_counter(); orc.evaluate_q(literal=False); lk = time.perf_counter() - t0
+            lit = None
+            if 96.0 * n * n < 2e9:
+                t0 = time.perf_counter(); orc.evaluate_q(literal=True); lit = time.perf_counter() - t0
+            out["orientation"]["cpu_restatement"] = {"eval_q_lookup_per_s": 1.0 / lk, "eval_q_literal_per_s": (1.0 / lit) if lit else None,
+                                                      "flip_one_pass_ms_estimate": (1 + L) * (lit or lk) * 1e3, "cores": 1,
+                                                      "note": "one call each; flipOne estimated as (1 + L) x the literal EvaluateQ (lookup variant where dense Q is infeasible)"}
 
     out["clocks"] = clocks.stop()
     # ---- CPU baseline beside it (rank 0, N == 1 only)

@@ -395,4 +395,18 @@ def test_config3_size_properties(built_lib):
     orc.set_tour(tours[0])
     for k in range(3):
         orc.set_signs(sg[k]); assert close(q[k], orc.evaluate_q())
+    assert (s == eng.eval_m(tours)).all()                           # bit-reproducible run to run
+    # the device-resident GA at the full size: every one of the 8000 individuals stays consistent with
+    # its stored tour (permutation, fitness, coordinates) and the best-ever score never decreases
+    eng.ga_begin(tours[0], eng.ga_params(npop=P, ngen=1 << 30, max_gens=1 << 40, seed=11))
+    last = -np.inf
+    for _ in range(3):
+        st = eng.ga_advance(40)
+        assert st.best_score >= last
+        last = st.best_score
+    assert st.generations == 120 and eng.ga_selfcheck() == 0
+    best, score = eng.ga_best()
+    assert sorted(best.tolist()) == list(range(n)) and close(score, -orc.evaluate(best.astype(np.int64)))
+    assert score > -s[0] * 1.5                                      # 120 generations improve a random tour a lot
+    eng.ga_end()
     eng.close()

@@ -285,6 +285,12 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
   ++nsync;
   grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
   uint32_t M = (n_gens > 0 && !stop) ? ga_load_mask(q, q.gmask + static_cast<size_t>(gen & 1) * WM, mflag, mpref, scan_tmp) : 0u;
+#ifdef AHX_GA_TIMING   // make EXTRA_NVFLAGS=-DAHX_GA_TIMING: per-phase clock64 totals of the first and last CTA, printed at exit
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define AHX_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); tph[i] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define AHX_TICK(i) do { } while (0)
+#endif
   for (long long it = 0; it < n_gens && !stop; ++it) {
     const int cur = static_cast<int>(gen & 1);
     const int *rowc = q.rowof[cur]; int *rown = q.rowof[cur ^ 1];
@@ -319,6 +325,7 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
       if (tid < WR) rpref[tid] = e2;
     }
     __syncthreads();
+    AHX_TICK(0);   // row map -> free-row select
     // ---- slot table of the mutated offspring this CTA scores
     const uint32_t Mcur = M;
     const int nb_total = (static_cast<int>(Mcur) + T - 1) / T;
@@ -360,12 +367,16 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
       if (cta == 0 && tid == 0) q.gmin[(gen + 2) % 3] = ~0ULL;
     }
     __syncthreads();
+    AHX_TICK(1);   // slots + clones
     // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
     GaSrc<T> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
     res_run_batches<T, false, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
     const long long ngen_now = gen + 1;
+    __syncthreads();
+    AHX_TICK(2);   // build + score
     ++nsync;
     grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
+    AHX_TICK(3);   // grid barrier
     M = ga_load_mask(q, q.gmask + static_cast<size_t>(ngen_now & 1) * WM, mflag, mpref, scan_tmp);
     // ---- bookkeeping (evaluate.go:287-306).  Clones are copies of individuals that already exist, so
     // only a mutated offspring can beat the hall of fame: compare the minimum over this generation's
@@ -390,7 +401,13 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     evals += Mcur;
     if (ngen_now - updated > q.ngen || ngen_now >= q.max_gens) stop = 1;
     gen = ngen_now;
+    AHX_TICK(4);   // mask load + hall of fame
   }
+#ifdef AHX_GA_TIMING
+  if (tid == 0 && (cta == 0 || cta == G - 1))
+    printf("cta %d (%d batches/gen at the end): rowmap %lld  slots %lld  build+score %lld  barrier %lld  mask+hof %lld cycles over %lld generations\n",
+           cta, 0, tph[0], tph[1], tph[2], tph[3], tph[4], n_gens);
+#endif
   if (cta == 0 && tid == 0) {
     q.st->gen = gen; q.st->updated = updated; q.st->evals = evals; q.st->hof_fit = hof_fit; q.st->stop = stop;
   }

@@ -47,6 +47,7 @@ constexpr int kRPad = kRCT * kRUnroll;        // E_res is a multiple of this
 // from L2 for every batch through a ring of kRStages tiles of kRPad entries (4 B offsets
 // + 1 B link counts each) filled by TMA bulk copies; the last producer warp becomes the
 // loader, the other kRP - 1 build coordinates.
+constexpr double kResFlush = 1e-30;          // sums below this consist of masked-out terms only: written as +0
 constexpr int kRStages = 4;
 constexpr int kRTileBytes = 5 * kRPad;
 template <bool STREAM> struct ResRoles { static constexpr int NB = STREAM ? kRP - 1 : kRP; };   // warps that build X
@@ -233,9 +234,14 @@ __device__ __forceinline__ double rcp_pos(double x) {
 //   n2 = 2 * nlinks of the entry as a double (from the 256-entry table in shared memory)
 //   d  = |X_a - X_b| = 2 dist;  inside the window  <=>  0 < d <= 2 LIMIT  (evaluate.go:135-137)
 //   term = (2 nlinks) / d                                                  (evaluate.go:140)
-// The window mask is applied to the 32-bit reciprocal SEED: with r0 = 0 the cubic step
-// gives e = 1, r = 0 (0 * 2 + 0), so the term is exactly +0 whatever d is -- one SEL
-// instead of selects on 64-bit operands, and d = 0 (inf from MUFU) never propagates.
+// The window mask rides on the uint32 -> double conversion: the exact conversion is
+// (2^52 + d) - 2^52, i.e. a double with high word 0x43300000 and low word d, minus 2^52;
+// outside the window the high word is 0x4B300000 instead (one SEL replaces the constant's
+// MOV), which makes x ~ 2^180: the term becomes ~1e-52 instead of exactly 0, no inf/NaN can
+// arise (d = 0 included), and no operand needs a 64-bit select.  Every genuine term is
+// >= 2 / (2 LIMIT) = 1e-7, so the masked terms (< 1e-46 in total) can never change a
+// non-empty sum, and a sum below kResFlush is an empty one and is written as exactly +0
+// (Go's score starts from +0.0, evaluate.go:128).
 // SUB = false (full tours, L == N): all X are distinct and padding entries are
 //   (0, 1, n = 0), so d >= 1 and the test is d <= 2 LIMIT.
 // SUB = true  (sub-tour): inactive contigs share X = 0xFFFFFFFF, d can be 0: the test is
@@ -268,13 +274,14 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
   for (int t = 0; t < T; ++t) {
     const uint32_t d = __usad(xa[t], xb[t], 0u);
     const bool in = SUB ? (d - 1u < kLimit2) : (d <= kLimit2);
-    const double x = u32_to_double(d);
+    // exact uint32 -> double is (2^52 + d) - 2^52 with the high word 0x43300000; outside the window the
+    // high word is 0x4B300000 instead, so x ~ 2^180 and the term is ~1e-52 (see kResFlush)
+    const double x = __hiloint2double(in ? 0x43300000 : 0x4B300000, static_cast<int>(d)) - 4503599627370496.0;
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));                 // MUFU.RCP64H: high word, relative error 2^-20
-    const double r = __hiloint2double(in ? __double2hiint(r0) : 0, 0);
-    double e = fma(-x, r, 1.0);
+    double e = fma(-x, r0, 1.0);
     e = fma(e, e, e);
-    acc[t] = fma(n2, fma(r, e, r), acc[t]);                                 // r (1 + e + e^2): <= 1 ulp of 1/x (rcp_probe.cu V1)
+    acc[t] = fma(n2, fma(r0, e, r0), acc[t]);                               // r0 (1 + e + e^2): <= 1 ulp of 1/x (rcp_probe.cu V1)
   }
 }
 
@@ -387,7 +394,7 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < kRC; ++w) s += m.partial[(buf * kRC + w) * T + ptid];
-        src.store(batch, ptid, 0.0 - s);   // score starts at +0.0 and only subtracts (evaluate.go:128,140)
+        src.store(batch, ptid, 0.0 - (s < kResFlush ? 0.0 : s));   // score starts at +0.0 and only subtracts (evaluate.go:128,140)
       }
     };
     for (int b = first; b < nb; b += stride, ++k) {

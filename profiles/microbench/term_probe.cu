@@ -34,6 +34,15 @@ template <int V> __device__ __forceinline__ void term(double &acc, uint32_t d, d
     const bool in = d <= LIM;
     const double x = u32_to_double(d);
     acc = fma(__hiloint2double(in ? n2hi : 0, 0), cubic(x, rcp64h(x)), acc);
+  } else if (V == 6) {   // window mask through the exponent of the converted distance: out-of-window x ~ 2^180, 1/x negligible
+    const bool in = d <= LIM;
+    const double x = __hiloint2double(in ? 0x43300000 : 0x4B300000, (int)d) - 4503599627370496.0;
+    acc = fma(n2, cubic(x, rcp64h(x)), acc);
+  } else if (V == 7) {   // V6 + the seed's low word is the distance itself (any low word keeps the seed within 2^-19)
+    const bool in = d <= LIM;
+    const double x = __hiloint2double(in ? 0x43300000 : 0x4B300000, (int)d) - 4503599627370496.0;
+    const double r0 = __hiloint2double(__double2hiint(rcp64h(x)), (int)d);
+    acc = fma(n2, cubic(x, r0), acc);
   } else if (V == 5) {   // V4 + seed low word from x
     const bool in = d <= LIM;
     const double x = u32_to_double(d);
@@ -78,6 +87,6 @@ template <int V> void run(double *buf, double clk_khz) {
 int main() {
   double *buf; cudaMalloc(&buf, 148 * 1024 * 8);
   int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
-  run<0>(buf, clk); run<1>(buf, clk); run<2>(buf, clk); run<3>(buf, clk); run<4>(buf, clk); run<5>(buf, clk);
+  run<0>(buf, clk); run<4>(buf, clk); run<6>(buf, clk); run<7>(buf, clk);
   return 0;
 }

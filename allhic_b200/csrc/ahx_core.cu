@@ -1,9 +1,12 @@
 // ahx_core.cu -- context, upload, and the batched Tour.Evaluate / EvaluateQ kernels.
 //
-// Kernels in this file (all sm_100a, no tensor cores: the path is gather +
-// fp64 divide/log + reduction):
-//   eval_m_sparse_kernel  Tour.Evaluate (evaluate.go:116-143) in contig space:
-//                         one CTA scores T tours against the nonzero pairs of M
+// Kernels (all sm_100a, no tensor cores: the path is gather + fp64 reciprocal/log +
+// reduction):
+//   eval_m_res_kernel     (ahx_resident.cuh) Tour.Evaluate (evaluate.go:116-143), the product
+//                         path: persistent, warp-specialised, pair table resident in shared
+//                         memory or streamed through a TMA ring
+//   eval_m_x32_kernel     fallback, 32-bit coordinates, one CTA per T tours, table streamed
+//   eval_m_sparse_kernel  fallback, fp64 coordinates (groups longer than 2.1 Gb, N > 65535)
 //   eval_m_dense_kernel   the same score in position space, gathering dense M
 //                         (north_star's literal formulation; one CTA per tour)
 //   eval_q_kernel         CLM.EvaluateQ (orientation.go:159-193), one CTA per

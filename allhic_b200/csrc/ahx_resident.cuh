@@ -1,34 +1,39 @@
 // ahx_resident.cuh -- Tour.Evaluate (evaluate.go:116-143) as a persistent,
-// warp-specialised kernel with the pair table RESIDENT in shared memory.
+// warp-specialised kernel; the building blocks are shared with the persistent GA
+// kernel (ahx_ga_res.cuh).
 //
-// One CTA per SM (kRThreads = 640 threads, up to ~200 KB of shared memory):
+// One CTA per SM (kRThreads = 768 threads, up to ~215 KB of shared memory):
 //   table   uint32[E_res]   nonzero pairs of M as the byte offsets of the two contigs in X,
 //                           (a*4T) | (b*4T) << 16 (N*4T < 64 KB whenever X fits), in the
-//                           bank-conflict-free order of order_pairs(), padded with
-//                           (0, 1, nlinks 0) entries to a multiple of kRCT * kRUnroll;
-//                           loaded ONCE per CTA by TMA bulk copies
-//   n2lut   double[256]     2n for n = 0..255 (the numerators)
+//                           bank-conflict-free order of order_pairs() for this T, padded
+//                           with (0, 1, nlinks 0) entries to a multiple of kRCT * kRUnroll
+//                           and stored so that a thread's 4 entries of an iteration are one
+//                           LDS.128; loaded ONCE per CTA by TMA bulk copies -- or, STREAM
+//                           mode, streamed for every batch through a ring of kRStages tiles
 //   nl8     uint8[E_res]    nlinks of the entry (a pair with more than 255 links is split
 //                           over several entries: sum_i n_i / d == n / d up to rounding)
+//   n2lut   double[256]     2n for n = 0..255 (the numerators)
 //   X[2]    uint32[N*T]     2*mid of contig c in tour t at X[c*T + t], double buffered
+//   sizes   uint32[N]       contig sizes, staged here when they fit (else read from global)
 // Roles:
-//   4 producer warps  build X[buf] for batch k+1 (T tours: read the rows, prefix-sum
-//                     the sizes, scatter 2*cum+size to contig space) while the
-//                     consumers work on batch k; they also fold the 16 per-warp
-//                     partial sums of a finished batch in a fixed order and write
+//   8 producer warps  build X[buf] for batch k+1 (T tours: vector loads of the rows,
+//                     two-pass prefix sum of the sizes, scatter 2*cum+size to contig
+//                     space) while the consumers work on batch k; they also fold the 16
+//                     per-warp partial sums of a finished batch in a fixed order and write
 //                     the scores.  full[buf] / done[buf] mbarriers hand the buffers over.
+//                     (STREAM: the last of them is the table loader.)
 //   16 consumer warps each owns 1/16 of the pair table and evaluates EVERY stored pair
-//                     for the T tours of the batch, branch-free: the window test
-//                     (integer pipe) only selects the numerator (nlinks or 0), the
-//                     reciprocal is MUFU.RCP64H + one cubic correction (<= 1 ulp).  The
-//                     cost is data independent -- random and converged tours run at the
-//                     same rate -- and bound by the fp64/XU pipes (profiles/microbench/
-//                     rcp_probe.cu: 16.3 SMSP-cycles per warp-term); filtering in-window
-//                     pairs first (the r1a/r1b design: ballot compaction into per-warp
-//                     queues, re-gather, divide) cost more than the divides it saved.
-// Batches are assigned round-robin (batch b -> CTA b mod gridDim.x) and every
-// reduction has a fixed shape, so a score depends only on the tours that share
-// its batch, never on scheduling: bit-reproducible run to run.
+//                     for the T tours of the batch, branch-free: the window test only
+//                     changes the exponent of the converted distance (res_pair_terms),
+//                     the reciprocal is MUFU.RCP64H + one cubic correction (<= 1 ulp).
+//                     The cost is data independent -- random and converged tours run at
+//                     the same rate -- and bound by instruction issue (an fp64 instruction
+//                     takes 2 issue cycles; profiles/microbench/term_probe.cu); filtering
+//                     in-window pairs first (the r1a/r1b design: ballot compaction into
+//                     per-warp queues, re-gather, divide) cost more than the divides it saved.
+// Batches are assigned round-robin (batch b -> CTA b mod gridDim.x); every tour has its
+// own accumulators and every reduction a fixed shape, so a score depends neither on the
+// tours that share its batch nor on scheduling: bit-reproducible.
 #ifndef AHX_RESIDENT_CUH_
 #define AHX_RESIDENT_CUH_
 

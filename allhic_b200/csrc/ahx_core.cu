@@ -919,7 +919,10 @@ int ahx_eval_q(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours, int32_t
   AHX_CUDA(ctx, ctx->d_scores.reserve(P));
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tours, sizeof(int32_t) * static_cast<size_t>(PT) * L, cudaMemcpyHostToDevice, ctx->stream));
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_signs.p, signs, static_cast<size_t>(P) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = launch_eval_q(ctx, ctx->d_tours.p, shared_tour, ctx->d_signs.p, P, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+  if (shared_tour && static_cast<size_t>(ctx->N) + 1024 <= ctx->smem_optin) {
+    // one tour, many sign vectors (flipWhole / flipAll / batched orientation search): logs once, then lookups
+    if ((rc = eval_q_shared_tour(ctx, P, L, tours, ctx->d_signs.p, ctx->d_scores.p)) != AHX_OK) return rc;
+  } else if ((rc = launch_eval_q(ctx, ctx->d_tours.p, shared_tour, ctx->d_signs.p, P, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
   AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AHX_OK;

@@ -137,6 +137,7 @@ int launch_eval_m_sparse(ahx_ctx *ctx, const int32_t *d_tours, const uint16_t *d
 int launch_eval_m_dense(ahx_ctx *ctx, const int32_t *d_tours, int32_t P, int32_t L, double *d_out, cudaStream_t s);
 int launch_eval_q(ahx_ctx *ctx, const int32_t *d_tours, int shared_tour, const uint8_t *d_signs, int32_t P, int32_t L,
                   double *d_out, cudaStream_t s);
+int eval_q_shared_tour(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tour, const uint8_t *d_signs, double *d_out);
 int finish_checked(ahx_ctx *ctx, const char *who);
 int validate_tour(ahx_ctx *ctx, int32_t L, const int32_t *tour, const char *who);
 size_t eval_m_smem_bytes(int T, int32_t N, int32_t L);

@@ -124,6 +124,23 @@ __global__ void __launch_bounds__(32) flip_one_kernel(const int *__restrict__ to
   if (lane == 0) { counts[0] = n_acc; counts[1] = n_rej; *final_score = score; }
 }
 
+// EvaluateQ for many sign vectors on ONE tour: the 12 logarithms per pair depend on the
+// tour only, so they are computed once (pair_scores_kernel) and each individual is a
+// table lookup per stored pair.  One CTA per individual; shared memory: sign codes, N bytes.
+__global__ void __launch_bounds__(kBlock) eval_q_lookup_kernel(int N, int E, const unsigned char *__restrict__ signs, const int *__restrict__ pa,
+                                                               const int *__restrict__ pb, const double *__restrict__ S4,
+                                                               const unsigned char *__restrict__ info, double *__restrict__ out) {
+  extern __shared__ unsigned char sg[];
+  __shared__ double red_scratch[kWarps];
+  const int tid = threadIdx.x, p = blockIdx.x;
+  for (int i = tid; i < N; i += kBlock) sg[i] = sign_code(signs[static_cast<size_t>(p) * N + i]);
+  __syncthreads();
+  double acc = 0.0;
+  for (int e = tid; e < E; e += kBlock) acc += pair_term(S4, info, e, sg[pa[e]], sg[pb[e]]);
+  const double s = block_sum(acc, red_scratch, tid);
+  if (tid == 0) out[p] = 0.0 - s;
+}
+
 static int upload_tour_index(ahx_ctx *ctx, int32_t L, const int32_t *tour) {
   // pos = inverse permutation, cum = cumsize (orientation.go:165-170)
   std::vector<int32_t> pos(ctx->N, -1);
@@ -134,6 +151,24 @@ static int upload_tour_index(ahx_ctx *ctx, int32_t L, const int32_t *tour) {
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos.p, pos.data(), sizeof(int32_t) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_cum.p, cum.data(), sizeof(long long) * L, cudaMemcpyHostToDevice, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // pos/cum are stack-owned
+  return AHX_OK;
+}
+
+// d_signs: P x N sign bytes on the device; d_out: P scores.  Used by ahx_eval_q(shared_tour != 0).
+int eval_q_shared_tour(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tour, const uint8_t *d_signs, double *d_out) {
+  int rc = upload_tour_index(ctx, L, tour);
+  if (rc != AHX_OK) return rc;
+  const int E = static_cast<int>(ctx->E);
+  AHX_CUDA(ctx, ctx->d_S4.reserve(static_cast<size_t>(std::max(E, 1)) * 4)); AHX_CUDA(ctx, ctx->d_pairinfo.reserve(std::max(E, 1)));
+  if (E > 0) {
+    pair_scores_kernel<<<(E + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pa.p, ctx->d_pb.p, ctx->d_slots.p, ctx->d_hist.p, E, ctx->d_pos.p,
+                                                                 ctx->d_cum.p, ctx->d_S4.p, ctx->d_pairinfo.p);
+    ctx->launches++;
+  }
+  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_q_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->N));
+  eval_q_lookup_kernel<<<P, kBlock, ctx->N, ctx->stream>>>(ctx->N, E, d_signs, ctx->d_pa.p, ctx->d_pb.p, ctx->d_S4.p, ctx->d_pairinfo.p, d_out);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
   return AHX_OK;
 }
 

@@ -413,7 +413,7 @@ def main():
             orc = OracleCLM(clmf, ids)
             orc.set_tour(tours[0].astype(np.int64))
             t0 = time.perf_counter()
-            r = orc.ga_run(npop=P, ngen=1 << 30, mutprob=0.2, seed=42, max_gens=1 << 30, max_seconds=min(6.0, args.cpu_seconds), nthreads=threads)
+            r = orc.ga_run(npop=P, ngen=1 << 30, mutprob=0.2, seed=42, max_gens=1 << 30, max_seconds=min(6.0, max(0.5, args.cpu_seconds)), nthreads=threads)   # 0 would mean no time limit
             dt = time.perf_counter() - t0
             out["cpu_baseline"]["ga_generations_per_s"] = r.generations / dt
             out["cpu_baseline"]["ga_sample"] = "%d generations of the same GA (npop %d) in %.1f s" % (r.generations, P, dt)

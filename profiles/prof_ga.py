@@ -17,6 +17,8 @@ clm = A.CLM(clmf, ids)
 eng = A.Engine(0)
 eng.load(clm)
 n, P = cfg["n"], cfg["npop"]
+if "--npop" in sys.argv:
+    P = int(sys.argv[sys.argv.index("--npop") + 1])
 rng = np.random.default_rng(1000)
 init = rng.permutation(n).astype(np.int32)
 eng.ga_begin(init, eng.ga_params(npop=P, ngen=1 << 30, max_gens=1 << 40, seed=42))

@@ -867,11 +867,16 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
   if (n < 0 || n > ctx->ga_prm.npop || (n > 0 && !tours)) return fail(ctx, AHX_ERR_ARG, "ahx_ga_put_migrants: bad argument");
   if (n == 0) return AHX_OK;
   const int P = ctx->ga_prm.npop, L = ctx->ga_L;
-  std::vector<int32_t> tmp(L);
-  for (int32_t m = 0; m < n; ++m) {   // bit-exact validity: a migrant must be a permutation of the active set
-    std::copy(tours + static_cast<size_t>(m) * L, tours + static_cast<size_t>(m + 1) * L, tmp.begin());
-    std::sort(tmp.begin(), tmp.end());
-    if (tmp != ctx->ga_active_set) return fail(ctx, AHX_ERR_ARG, "ahx_ga_put_migrants: migrant is not a permutation of the active contigs");
+  {   // bit-exact validity: a migrant must be a permutation of the active set (one marking pass per migrant)
+    std::vector<int32_t> stamp(ctx->N, -2);
+    for (int32_t c : ctx->ga_active_set) stamp[c] = -1;
+    for (int32_t m = 0; m < n; ++m)
+      for (int32_t i = 0; i < L; ++i) {
+        const int32_t c = tours[static_cast<size_t>(m) * L + i];
+        if (c < 0 || c >= ctx->N || stamp[c] == -2 || stamp[c] == m)
+          return fail(ctx, AHX_ERR_ARG, "ahx_ga_put_migrants: migrant is not a permutation of the active contigs");
+        stamp[c] = m;
+      }
   }
   GaState hs{};
   if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;

@@ -36,22 +36,25 @@ class IslandGA:
         self.exchanges = 0
         self.eng.ga_begin(np.ascontiguousarray(init_tour, np.int32), params)
 
-    def exchange(self):
-        """All-gather elites; replace this island's worst by everyone else's best."""
+    def exchange(self, stopped=0):
+        """All-gather elites (and this island's EarlyStop flag, so the stop decision costs no second
+        collective); replace this island's worst by everyone else's best.  Returns (fitness of all
+        elites [world, n_elite], True when every island has stopped)."""
         tours, fit = self.eng.ga_get_elites(self.n_elite)
-        payload = torch.empty(self.n_elite, self.L + 2, dtype=torch.int32)
+        payload = torch.empty(self.n_elite, self.L + 3, dtype=torch.int32)
         payload[:, : self.L] = torch.from_numpy(tours)
-        payload[:, self.L:] = torch.from_numpy(fit.view(np.int32).reshape(self.n_elite, 2))   # f64 bits as 2 x int32
+        payload[:, self.L:self.L + 2] = torch.from_numpy(fit.view(np.int32).reshape(self.n_elite, 2))   # f64 bits as 2 x int32
+        payload[:, self.L + 2] = int(stopped)
         payload = payload.to(self.dev)
-        gathered = torch.empty(self.world * self.n_elite, self.L + 2, dtype=torch.int32, device=self.dev)
+        gathered = torch.empty(self.world * self.n_elite, self.L + 3, dtype=torch.int32, device=self.dev)
         dist.all_gather_into_tensor(gathered, payload, group=self.group)
-        g = gathered.cpu().numpy().reshape(self.world, self.n_elite, self.L + 2)
+        g = gathered.cpu().numpy().reshape(self.world, self.n_elite, self.L + 3)
         others = np.concatenate([g[r, :, : self.L] for r in range(self.world) if r != self.rank], axis=0) if self.world > 1 else None
         if others is not None and len(others):
             self.eng.ga_put_migrants(np.ascontiguousarray(others, np.int32))
         self.exchanges += 1
-        fits = np.ascontiguousarray(g[:, :, self.L:]).view(np.float64).reshape(self.world, self.n_elite)
-        return fits
+        fits = np.ascontiguousarray(g[:, :, self.L:self.L + 2]).view(np.float64).reshape(self.world, self.n_elite)
+        return fits, bool(np.all(g[:, 0, self.L + 2] != 0))
 
     def run(self, max_gens, on_exchange=None):
         """Advance all islands in lock step until every island's EarlyStop fired or
@@ -63,13 +66,12 @@ class IslandGA:
             st = self.eng.ga_advance(n)
             done += n
             if self.world > 1:
-                fits = self.exchange()
+                fits, all_stopped = self.exchange(st.stopped)
                 if on_exchange:
                     on_exchange(done, fits)
-                st = self.eng.ga_advance(0)
-            flag = torch.tensor([int(st.stopped)], dtype=torch.int32, device=self.dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            if int(flag.item()) == 1:
+            else:
+                all_stopped = bool(st.stopped)
+            if all_stopped:
                 break
         tour, score = self.eng.ga_best()
         best = torch.tensor([score], dtype=torch.float64, device=self.dev)
@@ -78,6 +80,8 @@ class IslandGA:
         owner = int(torch.argmax(allbest).item())
         t = torch.from_numpy(np.ascontiguousarray(tour, np.int32)).to(self.dev)
         dist.broadcast(t, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner, group=self.group)
+        if self.world > 1:
+            st = self.eng.ga_advance(0)      # statistics after the last migrants
         return t.cpu().numpy(), float(allbest[owner].item()), st
 
     def close(self):

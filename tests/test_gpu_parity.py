@@ -200,6 +200,53 @@ def test_eval_q_general_slot_table(engine, tmp_path):
     eng.close()
 
 
+def test_group_without_contacts_and_heavy_pairs(built_lib, tmp_path):
+    """Edge inputs the reference accepts: (1) a CLM that names none of the REfile's contigs --
+    M is all zero, every score is +0.0 (Go's score starts from +0.0 and nothing is subtracted),
+    the GA still returns a permutation, flips REJECT; (2) pairs with hundreds / thousands of links
+    (the resident table stores 8-bit counts and splits such pairs over several entries)."""
+    import allhic_b200 as A
+    rng = np.random.default_rng(12)
+    n = 40
+    ids = tmp_path / "e.ids"; clmf = tmp_path / "e.clm"
+    ids.write_text("".join("c%d\t1\t%d\n" % (i, rng.integers(1000, 90000)) for i in range(n)))
+    clmf.write_text("x1+ x2+\t3\t5 6 7\n")                                # unknown contigs: skipped (clm.go:211-218)
+    clm = A.CLM(str(clmf), str(ids)); eng = A.Engine(0); eng.load(clm)
+    tours = np.stack([rng.permutation(n) for _ in range(7)]).astype(np.int32)
+    for kind in ("sparse", "dense"):
+        s = eng.eval_m(tours, kind=kind)
+        assert (s == 0).all() and not np.signbit(s).any()
+    signs = rand_signs(rng, n)
+    assert eng.eval_q(tours[0], signs)[0] == 0
+    best, st = eng.ga_run(tours[0], eng.ga_params(npop=32, ngen=20, max_gens=200, seed=1))
+    assert sorted(best.tolist()) == list(range(n)) and st.best_score == 0 and st.generations == 21
+    s2, acc, a, b = eng.flip_whole(tours[0], signs)
+    assert not acc and (s2 == signs).all()                                 # newScore <= score: REJECT (orientation.go:78)
+    s3, any_acc, na, nr, *_ = eng.flip_one(tours[0], signs)
+    assert not any_acc and na == 0 and nr == n and (s3 == signs).all()
+    eng.close()
+    # (2) heavy pairs: 255, 256, 700 and 2600 links
+    lines = []
+    for (a, b), cnt in zip([(0, 1), (1, 2), (2, 5), (3, 9)], [255, 256, 700, 2600]):
+        d = rng.integers(1, 200000, cnt)
+        for ao, bo in ("++", "+-", "-+", "--"):
+            lines.append("c%d%s c%d%s\t%d\t%s\n" % (a, ao, b, bo, cnt, " ".join(map(str, d))))
+    for _ in range(60):
+        a, b = sorted(rng.choice(n, 2, replace=False))
+        d = rng.integers(1, 200000, rng.integers(3, 12))
+        lines.append("c%d+ c%d+\t%d\t%s\n" % (a, b, len(d), " ".join(map(str, d))))
+    clmf.write_text("".join(lines))
+    clm = A.CLM(str(clmf), str(ids)); orc = O.OracleCLM(str(clmf), str(ids))
+    eng = A.Engine(0); eng.load(clm)
+    assert clm.tables()["nlinks"].max() == 2600
+    want = orc.population_evaluate(tours.astype(np.int64))
+    assert eng.eval_m_kernel(len(tours))[0] == 2                           # the resident-table kernel is the one under test
+    assert close(eng.eval_m(tours), want) and close(eng.eval_m(tours, kind="dense"), want)
+    best, st = eng.ga_run(tours[0], eng.ga_params(npop=64, ngen=30, max_gens=300, seed=2))
+    assert close(st.best_score, -orc.evaluate(best.astype(np.int64)))
+    eng.close()
+
+
 # ---------------------------------------------------------------- operators
 def test_mutation_operators_bit_exact(fix):
     eng, clm, orc = fix

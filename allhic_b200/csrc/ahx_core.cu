@@ -743,7 +743,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   ctx->d_hof.release(); ctx->d_sel_idx.release(); ctx->d_sel_tours.release(); ctx->d_sel_fit.release(); ctx->d_taken.release();
   ctx->d_state.release(); ctx->d_plan.release(); ctx->d_pos.release(); ctx->d_cum.release(); ctx->d_S4.release(); ctx->d_trace.release();
   ctx->d_pairinfo.release(); ctx->d_stepacc.release(); ctx->d_counts.release();
-  ctx->d_rowof[0].release(); ctx->d_rowof[1].release(); ctx->d_sel_rows.release(); ctx->d_row_fit.release(); ctx->d_gbar.release(); ctx->d_used.release(); ctx->d_gmin.release(); ctx->d_xpool.release(); ctx->d_gmask.release();
+  ctx->d_rowof[0].release(); ctx->d_rowof[1].release(); ctx->d_sel_rows.release(); ctx->d_row_fit.release(); ctx->d_gbar.release(); ctx->d_used.release(); ctx->d_gmin.release(); ctx->d_xpool.release(); ctx->d_gmask.release(); ctx->d_step_off.release(); ctx->d_rec_o.release(); ctx->d_rec_d.release();
   for (auto ev : ctx->chunk_ev) cudaEventDestroy(ev);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -873,6 +873,7 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
   // CSR of pairs touching each contig (for flipOne's O(deg) deltas)
   std::vector<int32_t> ptr(N + 1, 0), adj(2 * E);
   for (int64_t e = 0; e < E; ++e) { ptr[pa[e] + 1]++; ptr[pb[e] + 1]++; }
+  ctx->h_deg.assign(ptr.begin() + 1, ptr.end());
   for (int32_t i = 0; i < N; ++i) ptr[i + 1] += ptr[i];
   {
     std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);

@@ -77,6 +77,7 @@ struct ahx_ctx {
   std::vector<int64_t> h_sizes;
   std::vector<int32_t> h_pa, h_pb, h_nl;
   std::vector<int8_t> h_strand;
+  std::vector<int32_t> h_deg;              // pairs touching each contig (host copy of the CSR row lengths)
 
   // ---- scratch
   ahx::DevBuf<int32_t> d_tours;      // staging for ahx_eval_*
@@ -123,6 +124,8 @@ struct ahx_ctx {
   ahx::DevBuf<double> d_S4, d_trace;
   ahx::DevBuf<uint8_t> d_pairinfo, d_stepacc;
   ahx::DevBuf<long long> d_counts;
+  ahx::DevBuf<int32_t> d_step_off, d_rec_o;   // flipOne: per-step records (ahx_flip.cu)
+  ahx::DevBuf<double> d_rec_d;
 };
 
 namespace ahx {

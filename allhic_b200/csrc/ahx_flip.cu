@@ -124,6 +124,119 @@ __global__ void __launch_bounds__(32) flip_one_kernel(const int *__restrict__ to
   if (lane == 0) { counts[0] = n_acc; counts[1] = n_rej; *final_score = score; }
 }
 
+// ---- flipOne, restructured ----------------------------------------------------------
+// The greedy pass is sequential (each accept changes the baseline of the next contig), but
+// almost nothing in a step depends on earlier decisions: the contig's own sign is still its
+// initial one (every contig is visited once), and a partner's sign is either '+' or '-'.  So
+// flip_records_kernel computes, for every (step, adjacent pair) IN PARALLEL, the change of
+// the sum for both possible partner signs, laid out in step order; the sequential kernel
+// then only streams these records (prefetched one step ahead), picks d[sign of partner] and
+// reduces.  Same terms, same lane assignment and summation order as flip_one_kernel:
+// bit-identical scores, a twentieth of the latency.
+__global__ void flip_records_kernel(const int *__restrict__ tour, int L, const unsigned char *__restrict__ signs,
+                                    const int *__restrict__ pa, const int *__restrict__ pb, const int *__restrict__ adj_ptr,
+                                    const int *__restrict__ adj_e, const double *__restrict__ S4, const unsigned char *__restrict__ info,
+                                    const int *__restrict__ step_off, double *__restrict__ rec_d0, double *__restrict__ rec_d1,
+                                    int *__restrict__ rec_o) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= L) return;
+  const int c = tour[i];
+  const unsigned char oldc = sign_code(signs[c]), newc = rr_code(oldc);
+  const int beg = adj_ptr[c], deg = adj_ptr[c + 1] - beg, off = step_off[i];
+  for (int j = lane; j < deg; j += 32) {
+    const int e = adj_e[beg + j];
+    const int a = pa[e], b = pb[e];
+    const bool c_is_a = a == c;
+    double d[2];
+#pragma unroll
+    for (int so = 0; so < 2; ++so) {   // the partner's sign when this step runs
+      const unsigned char s = static_cast<unsigned char>(so);
+      d[so] = c_is_a ? pair_term(S4, info, e, newc, s) - pair_term(S4, info, e, oldc, s)
+                     : pair_term(S4, info, e, s, newc) - pair_term(S4, info, e, s, oldc);
+    }
+    rec_d0[off + j] = d[0]; rec_d1[off + j] = d[1]; rec_o[off + j] = c_is_a ? b : a;
+  }
+}
+
+// kBlock threads compute the starting score, then warp 0 walks the tour.  Shared memory:
+// step_off (L + 1 ints), the tour (L ints), the current sign codes (N bytes, all 0 / 1).
+__global__ void __launch_bounds__(kBlock) flip_one_stream_kernel(const int *__restrict__ tour_g, int L, int N, unsigned char *__restrict__ signs,
+                                                                 const int *__restrict__ pa, const int *__restrict__ pb, int E,
+                                                                 const double *__restrict__ S4, const unsigned char *__restrict__ info,
+                                                                 const int *__restrict__ step_off_g, const double *__restrict__ rec_d0,
+                                                                 const double *__restrict__ rec_d1, const int *__restrict__ rec_o,
+                                                                 double *__restrict__ trace, unsigned char *__restrict__ step_acc,
+                                                                 long long *__restrict__ counts, double *__restrict__ final_score) {
+  extern __shared__ __align__(8) unsigned char smem_flip[];
+  __shared__ double red_scratch[kWarps];
+  __shared__ double s_score;
+  int *step_off = reinterpret_cast<int *>(smem_flip);
+  int *tour = step_off + L + 1;
+  unsigned char *sg = reinterpret_cast<unsigned char *>(tour + L);
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i <= L; i += kBlock) step_off[i] = step_off_g[i];
+  for (int i = tid; i < L; i += kBlock) tour[i] = tour_g[i];
+  for (int i = tid; i < N; i += kBlock) sg[i] = sign_code(signs[i]);
+  __syncthreads();
+  double sum = 0.0;   // score := EvaluateQ() (orientation.go:91), fixed-shape block sum
+  for (int e = tid; e < E; e += kBlock) sum += pair_term(S4, info, e, sg[pa[e]], sg[pb[e]]);
+  sum = block_sum(sum, red_scratch, tid);
+  if (tid == 0) s_score = 0.0 - sum;
+  __syncthreads();
+  if (tid >= 32) return;
+  double score = s_score;
+  long long n_acc = 0, n_rej = 0;
+  // records of the next kD steps, the first 64 of each (two per lane; few contigs have more partners): the
+  // loads of step i + kD are in flight while steps i .. i + kD - 1 are decided (a step is ~400 cycles, a
+  // DRAM round trip ~1500)
+  constexpr int kW = 2, kD = 4;
+  double qd0[kD][kW], qd1[kD][kW]; int qo[kD][kW];
+  auto fetch = [&](int s, double (&a0)[kW], double (&a1)[kW], int (&ao)[kW]) {
+#pragma unroll
+    for (int w = 0; w < kW; ++w) {
+      a0[w] = a1[w] = 0.0; ao[w] = -1;
+      if (s < L && step_off[s] + w * 32 + lane < step_off[s + 1]) {
+        const int k = step_off[s] + w * 32 + lane;
+        a0[w] = rec_d0[k]; a1[w] = rec_d1[k]; ao[w] = rec_o[k];
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < kD; ++s) fetch(s, qd0[s], qd1[s], qo[s]);
+  // the loop is unrolled by kD so that slot s is a fixed set of registers: step i uses slot i mod kD and
+  // refills it for step i + kD right away (moving the slots along each step would wait for every load
+  // one step after it was issued)
+  for (int i0 = 0; i0 < L; i0 += kD) {
+#pragma unroll
+    for (int s = 0; s < kD; ++s) {
+      const int i = i0 + s;
+      if (i >= L) break;
+      const int beg = step_off[i], end = step_off[i + 1];
+      double d0[kW], d1[kW]; int o[kW];
+#pragma unroll
+      for (int w = 0; w < kW; ++w) { d0[w] = qd0[s][w]; d1[w] = qd1[s][w]; o[w] = qo[s][w]; }
+      fetch(i + kD, qd0[s], qd1[s], qo[s]);
+      double delta = 0.0;   // change of the positive sum when tour[i] flips (entries in adjacency order, lane-strided)
+#pragma unroll
+      for (int w = 0; w < kW; ++w) if (o[w] >= 0) delta += sg[o[w]] ? d1[w] : d0[w];
+      for (int k = beg + kW * 32 + lane; k < end; k += 32) delta += sg[rec_o[k]] ? rec_d1[k] : rec_d0[k];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, d);
+      const double new_score = score - delta;
+      const bool accept = new_score > score;        // orientation.go:97
+      if (lane == 0) {
+        if (trace) { trace[2 * i] = score; trace[2 * i + 1] = new_score; }
+        if (step_acc) step_acc[i] = accept ? 1 : 0;
+        if (accept) { const int c = tour[i]; sg[c] = rr_code(sg[c]); }   // rejected: the reference flips back (orientation.go:101)
+      }
+      if (accept) { score = new_score; ++n_acc; } else ++n_rej;
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < N; i += 32) signs[i] = sg[i] == 1 ? '-' : '+';
+  if (lane == 0) { counts[0] = n_acc; counts[1] = n_rej; *final_score = score; }
+}
+
 // EvaluateQ for many sign vectors on ONE tour: the 12 logarithms per pair depend on the
 // tour only, so they are computed once (pair_scores_kernel) and each individual is a
 // table lookup per stored pair.  One CTA per individual; shared memory: sign codes, N bytes.
@@ -223,11 +336,35 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
     ctx->launches++;
     AHX_CUDA(ctx, cudaGetLastError());
   }
-  AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->N));
   double *d_final = ctx->d_trace.p + static_cast<size_t>(Lm) * 2;
-  flip_one_kernel<<<1, 32, ctx->N, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_adj_ptr.p,
-                                                 ctx->d_adj_e.p, ctx->d_S4.p, ctx->d_pairinfo.p, ctx->d_trace.p, ctx->d_stepacc.p,
-                                                 ctx->d_counts.p, d_final);
+  bool plain = true;   // Signs hold '+' / '-' only (Activate, rr): the streamed form assumes it
+  for (int32_t i = 0; i < ctx->N; ++i) plain = plain && (signs[i] == '+' || signs[i] == '-');
+  const size_t smem_stream = sizeof(int) * (2 * static_cast<size_t>(L) + 1) + ctx->N;
+  if (plain && smem_stream + 1024 <= ctx->smem_optin) {
+    std::vector<int32_t> off(static_cast<size_t>(L) + 1, 0);
+    for (int32_t i = 0; i < L; ++i) off[i + 1] = off[i] + ctx->h_deg[tour[i]];
+    const size_t nrec = static_cast<size_t>(std::max(off[L], 1));
+    AHX_CUDA(ctx, ctx->d_step_off.reserve(static_cast<size_t>(L) + 1)); AHX_CUDA(ctx, ctx->d_rec_o.reserve(nrec));
+    AHX_CUDA(ctx, ctx->d_rec_d.reserve(2 * nrec));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_step_off.p, off.data(), sizeof(int32_t) * (L + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (L > 0) {
+      flip_records_kernel<<<(L + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_tours.p, L, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, ctx->d_adj_ptr.p, ctx->d_adj_e.p,
+                                                               ctx->d_S4.p, ctx->d_pairinfo.p, ctx->d_step_off.p, ctx->d_rec_d.p, ctx->d_rec_d.p + nrec,
+                                                               ctx->d_rec_o.p);
+      ctx->launches++;
+    }
+    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stream)));
+    flip_one_stream_kernel<<<1, kBlock, smem_stream, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_S4.p,
+                                                                ctx->d_pairinfo.p, ctx->d_step_off.p, ctx->d_rec_d.p, ctx->d_rec_d.p + nrec, ctx->d_rec_o.p,
+                                                                ctx->d_trace.p, ctx->d_stepacc.p, ctx->d_counts.p, d_final);
+    AHX_CUDA(ctx, cudaGetLastError());
+    AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `off` is stack-owned
+  } else {
+    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->N));
+    flip_one_kernel<<<1, 32, ctx->N, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_adj_ptr.p,
+                                                   ctx->d_adj_e.p, ctx->d_S4.p, ctx->d_pairinfo.p, ctx->d_trace.p, ctx->d_stepacc.p,
+                                                   ctx->d_counts.p, d_final);
+  }
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
   long long counts[2] = {0, 0};

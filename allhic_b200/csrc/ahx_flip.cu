@@ -322,6 +322,11 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   if (rc != AHX_OK) return rc;
   if (!signs) return fail(ctx, AHX_ERR_ARG, "ahx_flip_one: null signs");
   if ((rc = validate_tour(ctx, L, tour, "ahx_flip_one")) != AHX_OK) return rc;
+  // CLM.Signs only ever holds '+' / '-' (Activate writes '+', every change goes through rr, clm.go:160-165).
+  // With any other byte the reference's greedy pass compares against a stale score (a rejected step
+  // rewrites the byte to '+' without re-scoring): not worth imitating, so it is an argument error here.
+  for (int32_t i = 0; i < ctx->N; ++i)
+    if (signs[i] != '+' && signs[i] != '-') return fail(ctx, AHX_ERR_ARG, "ahx_flip_one: signs must be '+' or '-'");
   if (static_cast<size_t>(ctx->N) + 1024 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_flip_one: too many contigs");
   if ((rc = upload_tour_index(ctx, L, tour)) != AHX_OK) return rc;
   const int E = static_cast<int>(ctx->E), Lm = std::max<int32_t>(L, 1);
@@ -337,10 +342,8 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
     AHX_CUDA(ctx, cudaGetLastError());
   }
   double *d_final = ctx->d_trace.p + static_cast<size_t>(Lm) * 2;
-  bool plain = true;   // Signs hold '+' / '-' only (Activate, rr): the streamed form assumes it
-  for (int32_t i = 0; i < ctx->N; ++i) plain = plain && (signs[i] == '+' || signs[i] == '-');
   const size_t smem_stream = sizeof(int) * (2 * static_cast<size_t>(L) + 1) + ctx->N;
-  if (plain && smem_stream + 1024 <= ctx->smem_optin) {
+  if (smem_stream + 1024 <= ctx->smem_optin) {
     std::vector<int32_t> off(static_cast<size_t>(L) + 1, 0);
     for (int32_t i = 0; i < L; ++i) off[i + 1] = off[i] + ctx->h_deg[tour[i]];
     const size_t nrec = static_cast<size_t>(std::max(off[L], 1));

@@ -208,7 +208,8 @@ int ahx_mutate(ahx_ctx *ctx, int32_t L, const int32_t *tour_in, int32_t op, int3
 
 /* ------------------------------------------------------------------------- *
  * Orientation heuristics, orientation.go:31-120.  signs (n_tigs bytes) is
- * updated in place; *accepted = 1 for ACCEPT, 0 for REJECT.
+ * updated in place; *accepted = 1 for ACCEPT, 0 for REJECT.  ahx_flip_one
+ * requires every byte to be '+' or '-' (all CLM.Signs ever holds).
  * ------------------------------------------------------------------------- */
 int ahx_flip_whole(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs,
                    double *old_score, double *new_score, int32_t *accepted);

@@ -400,6 +400,23 @@ def test_flip_whole_and_one_match_oracle(fix, syn):
             assert close(eng.eval_q(t, s2)[0], fs_o)
 
 
+def test_flip_one_rejects_foreign_sign_bytes(fix):
+    """CLM.Signs only ever holds '+' / '-' (Activate writes '+', every change goes through rr,
+    clm.go:160-165); ahx_flip_one refuses anything else instead of imitating the reference's
+    stale-score behaviour on such input.  EvaluateQ itself accepts it (no stored orientation
+    matches, the pair is skipped, orientation.go:143)."""
+    import allhic_b200 as A
+    eng, clm, orc = fix
+    rng = np.random.default_rng(62)
+    t = rng.permutation(clm.N).astype(np.int32)
+    weird = rand_signs(rng, clm.N); weird[t[3]] = ord('?')
+    with pytest.raises(A.AhxError) as ei:
+        eng.flip_one(t, weird)
+    assert ei.value.code == -1
+    orc.set_tour(t); orc.set_signs(weird)
+    assert close(eng.eval_q(t, weird)[0], orc.evaluate_q())
+
+
 def test_flip_all_matches_dense_eigensolver(fix):
     eng, clm, orc = fix
     rng = np.random.default_rng(71)

@@ -21,6 +21,8 @@ rm -rf /tmp/fx && mkdir -p /tmp/fx && cp tests/golden/test.ids tests/golden/test
 ( time ./allhic_b200/bin/allhic-b200 optimize /tmp/fx/test.ids /tmp/fx/test.clm ) > $OUT/${TAG}_optimize_fixture.stdout 2> $OUT/${TAG}_optimize_fixture.stderr; echo "optimize rc=$?"
 tail -4 $OUT/${TAG}_optimize_fixture.stderr; cp /tmp/fx/test.tour $OUT/${TAG}_fixture.tour 2>/dev/null
 ( time ./allhic_b200/bin/allhic-b200 optimize /tmp/fx/test.ids /tmp/fx/test.clm --skipGA ) > $OUT/${TAG}_optimize_skipga.stdout 2> $OUT/${TAG}_optimize_skipga.stderr; echo "optimize --skipGA rc=$?"
+# --resume (optimize.go:44-51): picks up the .tour the run above left, backs it up to .tour.sav, re-activates its contigs
+( ./allhic_b200/bin/allhic-b200 optimize /tmp/fx/test.ids /tmp/fx/test.clm --resume --ngen 200 ) > $OUT/${TAG}_optimize_resume.stdout 2> $OUT/${TAG}_optimize_resume.stderr; echo "optimize --resume rc=$? $(grep -c Success $OUT/${TAG}_optimize_resume.stderr) Success, backup: $(ls /tmp/fx/*.sav 2>/dev/null | wc -l)"
 
 echo "== bench (ours, default flags)"
 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cut -c1-600 $OUT/${TAG}_bench.json

@@ -35,8 +35,13 @@ def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None):
                 g = order.pop(0)
             refile, clmfile = groups[g]
             t0 = time.perf_counter()
-            p = subprocess.run([binary, "optimize", refile, clmfile, "--device", str(dev), *flags],
-                               capture_output=True, text=True)
+            # the process sees its GPU only: CUDA start-up enumerates every visible device, which costs
+            # seconds per process on an 8-GPU box
+            env = dict(os.environ)
+            vis = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+            env["CUDA_VISIBLE_DEVICES"] = vis[dev] if dev < len(vis) else str(dev)
+            p = subprocess.run([binary, "optimize", refile, clmfile, "--device", "0", *flags],
+                               capture_output=True, text=True, env=env)
             dt = time.perf_counter() - t0
             scores = re.findall(r"max_score=([0-9.eE+-]+)", p.stdout)
             if log_dir:

@@ -17,10 +17,14 @@ n_cpu = int(sys.argv[sys.argv.index("--cpu") + 1]) if "--cpu" in sys.argv else 2
 cfgs = synth.config4_groups()[:n_groups]
 outdir = os.path.join(os.environ.get("TMPDIR", "/tmp"), "allhic_b200_config4")
 os.makedirs(outdir, exist_ok=True)
-groups = []
-for g, c in enumerate(cfgs):
+def _make(c):
     ids, clm, _ = synth.materialize(c["n"], seed=c["seed"], outdir=outdir)
-    groups.append((ids, clm))
+    return ids, clm
+
+
+from concurrent.futures import ProcessPoolExecutor  # noqa: E402
+with ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:   # the generator is single-threaded numpy
+    groups = list(ex.map(_make, cfgs))
 ndev = _ffi.lib().ahx_device_count()
 t0 = time.perf_counter()
 res = farm.optimize_groups(groups, list(range(max(1, ndev))))

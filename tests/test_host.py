@@ -144,7 +144,7 @@ def test_farm_runs_every_group_once_largest_first(tmp_path):
     from allhic_b200 import farm
     fake = tmp_path / "fake-allhic"
     fake.write_text("#!/bin/sh\n# optimize <refile> <clmfile> --device <d>\n"
-                    "echo \"Current iteration GA2-500: max_score=0.5$5\"\necho \"$2 $5\" >> %s/calls.log\necho 'NOTICE Success' >&2\n" % tmp_path)
+                    "echo \"Current iteration GA2-500: max_score=0.5$5\"\necho \"$2 $CUDA_VISIBLE_DEVICES\" >> %s/calls.log\necho 'NOTICE Success' >&2\n" % tmp_path)
     fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
     groups = []
     for g, n in enumerate([5, 50, 20, 35]):

@@ -72,8 +72,52 @@ __host__ __device__ inline MutPlan plan_mutation(const Philox &ph, uint32_t glo,
 }
 
 // SelTournament{k}.Apply(2, ...): two distinct winners; `which` picks one.
+// The reference's k = 3 (evaluate.go:273) has its own out-of-line instance: loops unrolled, the
+// sample in registers, the fitness loads issued together.  Out of line so that this cold, serial,
+// register-hungry code does not weigh on the register allocation of the kernels' hot loops.
+__device__ __noinline__ int tournament_pair_3(const double *__restrict__ fit, int P, const Philox &ph, uint32_t glo, uint32_t ghi,
+                                              uint32_t pair, int which) {
+  constexpr int K = 3;
+  uint32_t r[8];
+  {
+    uint32_t o4[4];
+    ph(glo, ghi, pair, kStreamSelect, o4);
+    r[0] = o4[0]; r[1] = o4[1]; r[2] = o4[2]; r[3] = o4[3];
+    ph(glo, ghi, pair, kStreamSelect + 1, o4);
+    r[4] = o4[0]; r[5] = o4[1]; r[6] = o4[2]; r[7] = o4[3];
+  }
+  int banned = -1, winner = -1;
+#pragma unroll
+  for (int round = 0; round < 2; ++round) {
+    if (round > which) break;
+    const int pool = P - (banned >= 0 ? 1 : 0);
+    int chosen[K], ids[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      int v = rand_below(r[round * K + i], pool - i);   // v-th not yet sampled index
+      int pos = 0;
+#pragma unroll
+      for (int m = 0; m < K; ++m) if (m < i && pos == m && chosen[m] <= v) { ++v; ++pos; }
+#pragma unroll
+      for (int m = K - 1; m > 0; --m) if (m <= i && m > pos) chosen[m] = chosen[m - 1];
+#pragma unroll
+      for (int m = 0; m < K; ++m) if (m == pos) chosen[m] = v;
+      ids[i] = (banned >= 0 && v >= banned) ? v + 1 : v;
+    }
+    double f[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) f[i] = __ldcg(fit + ids[i]);   // independent loads; written by other CTAs in an earlier generation of the same launch
+    int best = ids[0]; double bestfit = f[0];
+#pragma unroll
+    for (int i = 1; i < K; ++i) if (f[i] < bestfit) { best = ids[i]; bestfit = f[i]; }
+    winner = best; banned = best;
+  }
+  return winner;
+}
+
 __device__ inline int tournament_pair(const double *__restrict__ fit, int P, int k, const Philox &ph, uint32_t glo,
                                       uint32_t ghi, uint32_t pair, int which) {
+  if (k == 3) return tournament_pair_3(fit, P, ph, glo, ghi, pair, which);
   uint32_t r[2 * kMaxContestants];
 #pragma unroll
   for (int c = 0; c < (2 * kMaxContestants) / 4; ++c) {

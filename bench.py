@@ -35,8 +35,8 @@ try:
 except Exception:
     pass
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the evaluate kernel, from the committed
-# ncu --set full capture of (workload, P) -- profiles/r1p_ncu_full_summary.txt
-NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64207616 + 847360}
+# ncu --set full capture of (workload, P) -- profiles/r1r_ncu_full_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64207872 + 360448}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 

@@ -40,7 +40,7 @@ if [ -n "$FULL" ]; then
   echo "== ncu --set full of the hot kernels (profiles/prof_target.py: eval_m, GA generation, eval_q, flips)"
   T="python profiles/prof_target.py config3"
   $T > $OUT/${TAG}_prof_plain.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'eval_m_res_kernel|eval_m_x32_kernel|ga_plan_kernel|ga_apply_kernel|eval_q_kernel|pair_scores_kernel|flip_one_kernel' -s 2 -c 16 -f -o $OUT/${TAG}_prof $T > $OUT/${TAG}_ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'eval_m_res_kernel|ga_persist_kernel|eval_q_kernel|eval_q_lookup_kernel|pair_scores_kernel|flip_records_kernel|flip_one_stream_kernel|flip_one_kernel' -s 2 -c 16 -f -o $OUT/${TAG}_prof $T > $OUT/${TAG}_ncu_full.log 2>&1
   echo "ncu full rc=$?"; tail -2 $OUT/${TAG}_prof_plain.log
   python profiles/prof_target.py config3 converged > $OUT/${TAG}_prof_converged.log 2>&1; tail -2 $OUT/${TAG}_prof_converged.log
 fi

@@ -50,7 +50,7 @@ struct GaDev {
 struct MutPlan { int mutated, op, p, q, dir; };
 
 // Draws of eaopt's `rng.Float64() < MutRate` and Tour.Mutate (evaluate.go:221-232)
-__host__ __device__ inline MutPlan plan_mutation(const Philox &ph, uint32_t glo, uint32_t ghi, uint32_t o, double mut_prob, int L) {
+__host__ __device__ __noinline__ MutPlan plan_mutation(const Philox &ph, uint32_t glo, uint32_t ghi, uint32_t o, double mut_prob, int L) {
   uint32_t r[4], s[4];
   ph(glo, ghi, o, kStreamMutate, r);
   MutPlan m{0, -1, 0, 0, 0};

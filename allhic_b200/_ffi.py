@@ -74,6 +74,7 @@ SIGNATURES = {
     "ahx_ga_get_elites": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
     "ahx_ga_put_migrants": (C.c_int, [_vp, C.c_int32, _vp]),
     "ahx_ga_selfcheck": (C.c_int, [_vp, _p64]),
+    "ahx_ga_kernel": (C.c_int, [_vp]),
     "ahx_ga_end": (C.c_int, [_vp]),
     "ahx_mutate": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "ahx_flip_whole": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _pd, _p32]),

@@ -589,7 +589,7 @@ static std::vector<uint32_t> tour_coordinates(const ahx_ctx *ctx, int32_t L, con
 static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double mut_prob) {
   GaResCfg c;
   if (const char *env = getenv("AHX_GA_RES")) if (!atoi(env)) return c;
-  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res[0] <= 0 || L != ctx->N || 2 * static_cast<int64_t>(P) > 32 * kGaMaxWords) return c;
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res[0] <= 0 || L != ctx->N) return c;
   const double expect = std::max(1.0, P * mut_prob);
   const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
   const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
@@ -979,6 +979,12 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
   AHX_CUDA(ctx, cudaGetLastError());
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AHX_OK;
+}
+
+int ahx_ga_kernel(ahx_ctx *ctx) {
+  if (!ctx || !ctx->ga_active) return -1;
+  if (ctx->ga_res) return ctx->ga_stream ? 3 : 2;
+  return ctx->ga_x32 ? 1 : 0;
 }
 
 int ahx_ga_selfcheck(ahx_ctx *ctx, int64_t *n_bad) {

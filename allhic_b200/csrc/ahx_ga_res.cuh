@@ -112,7 +112,6 @@ __device__ __forceinline__ void remap_of(const MutPlan &mp, int L, const int *pt
   }
 }
 
-constexpr int kGaMaxWords = kRThreads;   // one mask word per thread in the block scans: 2P <= 32 * kRThreads
 
 inline size_t ga_res_extra_bytes(int P, int T, int nbmax) {
   const size_t wm = (static_cast<size_t>(P) + 31) / 32, wr = (2 * static_cast<size_t>(P) + 31) / 32;
@@ -205,6 +204,21 @@ __device__ __forceinline__ uint32_t block_scan_u32(uint32_t v, uint32_t *scratch
   return r;
 }
 
+// In-place exclusive prefix sum of n words in shared memory (any n: chunks of kRThreads with a
+// running carry); returns the total.  Ends with a block barrier.
+__device__ __forceinline__ uint32_t block_scan_array(uint32_t *vals, int n, uint32_t *scratch) {
+  uint32_t carry = 0;
+  for (int base = 0; base < n; base += kRThreads) {
+    const int i = base + static_cast<int>(threadIdx.x);
+    uint32_t tot = 0;
+    const uint32_t e = block_scan_u32(i < n ? vals[i] : 0u, scratch, &tot);
+    if (i < n) vals[i] = carry + e;
+    carry += tot;
+  }
+  __syncthreads();
+  return carry;
+}
+
 // index of the m-th (0-based) set bit of a mask given the exclusive word prefix
 __device__ __forceinline__ int mask_select(const uint32_t *mask, const uint32_t *pref, int nwords, uint32_t m, bool invert, int nbits) {
   int lo = 0, hi = nwords - 1;
@@ -251,14 +265,13 @@ __device__ __forceinline__ void ga_publish_mask(const GaRes &q, const Philox &ph
 }
 // returns the number of mutated offspring; mflag / mpref: the mask and its exclusive word prefix
 __device__ __forceinline__ uint32_t ga_load_mask(const GaRes &q, const uint32_t *gmask, uint32_t *mflag, uint32_t *mpref, uint32_t *scan_tmp) {
-  const int tid = threadIdx.x, WM = (q.P + 31) / 32;
-  const uint32_t w = tid < WM ? __ldcg(gmask + tid) : 0u;
-  if (tid < WM) mflag[tid] = w;
-  uint32_t M = 0;
-  const uint32_t e1 = block_scan_u32(__popc(w), scan_tmp, &M);
-  if (tid < WM) mpref[tid] = e1;
+  const int WM = (q.P + 31) / 32;
+  for (int w = threadIdx.x; w < WM; w += kRThreads) {
+    const uint32_t v = __ldcg(gmask + w);
+    mflag[w] = v; mpref[w] = __popc(v);
+  }
   __syncthreads();
-  return M;
+  return block_scan_array(mpref, WM, scan_tmp);
 }
 
 template <int T, bool STREAM>
@@ -301,29 +314,27 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     unsigned char *used_old = q.used + static_cast<size_t>((gen + 2) % 3) * ub;        // generation gen-1's map: nobody reads it any more
     unsigned long long *gmin_new = q.gmin + (gen + 1) % 3;
     // ---- rows the current generation references -> free-row select structure
-    uint32_t nfree = 0;
-    {
+    for (int wi = tid; wi < WR; wi += kRThreads) {
       uint32_t w = 0;
-      if (tid < WR) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(used_cur + static_cast<size_t>(tid) * 32);
-        const int nvalid = min(32, 2 * q.P - tid * 32);
+      const uint4 *src = reinterpret_cast<const uint4 *>(used_cur + static_cast<size_t>(wi) * 32);
+      const int nvalid = min(32, 2 * q.P - wi * 32);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (nvalid <= h * 16) break;
-          const uint4 v = __ldcg(src + h);                       // the map is padded to a multiple of 32 bytes
-          const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+      for (int h = 0; h < 2; ++h) {
+        if (nvalid <= h * 16) break;
+        const uint4 v = __ldcg(src + h);                       // the map is padded to a multiple of 32 bytes
+        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) w |= ((x[i] >> (8 * b)) & 1u) << (h * 16 + i * 4 + b);
-        }
-        rused[tid] = w;
-        w = ~w;
-        if (nvalid < 32) w &= (1u << nvalid) - 1u;
+          for (int b = 0; b < 4; ++b) w |= ((x[i] >> (8 * b)) & 1u) << (h * 16 + i * 4 + b);
       }
-      const uint32_t e2 = block_scan_u32(tid < WR ? __popc(w) : 0u, scan_tmp, &nfree);
-      if (tid < WR) rpref[tid] = e2;
+      rused[wi] = w;
+      w = ~w;
+      if (nvalid < 32) w &= (1u << nvalid) - 1u;
+      rpref[wi] = __popc(w);
     }
+    __syncthreads();
+    block_scan_array(rpref, WR, scan_tmp);   // at least P of the 2P rows are free
     __syncthreads();
     AHX_TICK(0);   // row map -> free-row select
     // ---- slot table of the mutated offspring this CTA scores

@@ -180,6 +180,10 @@ class Engine:
         self._ck(self._l.ahx_ga_selfcheck(self.h, C.byref(n)))
         return n.value
 
+    def ga_kernel(self):
+        """3/2 persistent kernel (pair table streamed / resident), 1 two kernels per generation, 0 fp64, -1 idle."""
+        return self._l.ahx_ga_kernel(self.h)
+
     def ga_end(self):
         self._ck(self._l.ahx_ga_end(self.h))
 

@@ -198,6 +198,10 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours /* n*L */)
  * (permutation of the active contigs, fitness within 1e-12 of a fresh Tour.Evaluate, stored
  * coordinates equal to the tour's) and counts the individuals that fail. */
 int ahx_ga_selfcheck(ahx_ctx *ctx, int64_t *n_bad);
+/* Which generation loop the active run uses: 3 persistent kernel with the pair table streamed,
+ * 2 persistent kernel with the table in shared memory, 1 two kernels per generation (32-bit
+ * coordinates), 0 the fp64 kernels; -1 when no run is active. */
+int ahx_ga_kernel(ahx_ctx *ctx);
 int ahx_ga_end(ahx_ctx *ctx);
 
 /* One mutation operator applied to one tour on the device (test hook for

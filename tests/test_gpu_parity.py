@@ -380,6 +380,21 @@ def test_ga_mutation_heavy_and_tiny_populations(fix):
         eng.ga_end()
 
 
+def test_ga_large_population_stays_on_the_persistent_kernel(fix):
+    """Populations beyond one mask word per thread (2P > 32 * 768) run the chunked block scans."""
+    eng, clm, orc = fix
+    rng = np.random.default_rng(8)
+    init = rng.permutation(clm.N).astype(np.int32)
+    for npop in (12289, 40000):
+        eng.ga_begin(init, eng.ga_params(npop=npop, ngen=1 << 30, max_gens=1 << 40, seed=9))
+        assert eng.ga_kernel() in (2, 3)
+        st = eng.ga_advance(40)
+        assert st.generations == 40 and eng.ga_selfcheck() == 0
+        best, score = eng.ga_best()
+        assert close(score, -orc.evaluate(best.astype(np.int64)))
+        eng.ga_end()
+
+
 # ---------------------------------------------------------------- orientation
 def test_flip_whole_and_one_match_oracle(fix, syn):
     for eng, clm, orc in (fix, syn):

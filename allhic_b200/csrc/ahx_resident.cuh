@@ -12,7 +12,6 @@
 //                           mode, streamed for every batch through a ring of kRStages tiles
 //   nl8     uint8[E_res]    nlinks of the entry (a pair with more than 255 links is split
 //                           over several entries: sum_i n_i / d == n / d up to rounding)
-//   n2lut   double[256]     2n for n = 0..255 (the numerators)
 //   X[2]    uint32[N*T]     2*mid of contig c in tour t at X[c*T + t], double buffered
 //   sizes   uint32[N]       contig sizes, staged here when they fit (else read from global)
 // Roles:
@@ -71,7 +70,7 @@ __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~sta
 inline size_t res_smem_bytes(int T, int N, long long E_res, bool stream = false, bool sizes = false) {
   return (sizes ? res_align16(4ull * N) : 0) + (stream ? static_cast<size_t>(kRStages) * kRTileBytes : res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res))) +
          2 * res_align16(4ull * N * T) + (stream ? 8ull * 2 * kRStages : 0) +
-         8ull * 256 + 8ull * 2 * kRC * T + res_align16(4ull * (kRC + kRP) * T) + 8 * 8;
+         8ull * 2 * kRC * T + res_align16(4ull * (kRC + kRP) * T) + 8 * 8;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -236,9 +235,9 @@ __device__ __forceinline__ double rcp_pos(double x) {
 
 // acc[t] += nlinks / dist for one table entry:
 //   p  = byte offsets of the two contigs' coordinate groups in X: (a*4T) | (b*4T) << 16
-//   n2 = 2 * nlinks of the entry as a double (from the 256-entry table in shared memory)
+//   n  = nlinks of the entry as a double (res_n); the sum is doubled once at the end
 //   d  = |X_a - X_b| = 2 dist;  inside the window  <=>  0 < d <= 2 LIMIT  (evaluate.go:135-137)
-//   term = (2 nlinks) / d                                                  (evaluate.go:140)
+//   term = (2 nlinks) / d = 2 (n / d)                                      (evaluate.go:140)
 // The window mask rides on the uint32 -> double conversion: the exact conversion is
 // (2^52 + d) - 2^52, i.e. a double with high word 0x43300000 and low word d, minus 2^52;
 // outside the window the high word is 0x4B300000 instead (one SEL replaces the constant's
@@ -253,12 +252,15 @@ __device__ __forceinline__ double rcp_pos(double x) {
 //   d - 1 < 2 LIMIT (unsigned).
 // Issue-slot model measured with profiles/microbench/term_probe.cu: an fp64 instruction
 // costs 2 issue cycles, anything else 1.
-// numerator 2n as a double: from the 256-entry table (one LDS.64; T = 4, where instruction issue is the
-// limit) or computed (one DADD; T <= 2, where the shared-memory pipe is: fewer gathers per table entry)
-template <int T>
-__device__ __forceinline__ double res_n2(const double *n2lut, uint32_t n8) {
-  if constexpr (T >= 4) return n2lut[n8];
-  else return u32_to_double(2u * n8);
+// Numerator: byte K of a word of four 8-bit link counts as a double -- one I2F.F64.U8 with a
+// byte selector (XU pipe, no shared-memory access; the 256-entry 2n table it replaces was 20 %
+// of the kernel's shared-memory wavefronts, r1s).  The factor 2 of (2 nlinks) / d is applied
+// once per tour to the finished sum (exact).
+template <int K>
+__device__ __forceinline__ double res_n(uint32_t n8x4) {
+  double v;
+  asm("{.reg .b16 h; cvt.u16.u32 h, %1; cvt.rn.f64.u8 %0, h;}" : "=d"(v) : "r"(n8x4 >> (8 * K)));
+  return v;
 }
 
 // SCALED: p holds byte offsets (resident tables); otherwise contig indices a | b << 16 (the
@@ -284,6 +286,7 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
     const double x = __hiloint2double(in ? 0x43300000 : 0x4B300000, static_cast<int>(d)) - 4503599627370496.0;
     double r0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));                 // MUFU.RCP64H: high word, relative error 2^-20
+    r0 = __hiloint2double(__double2hiint(r0), static_cast<int>(d));         // any low word will do (2^-27): saves zeroing it
     double e = fma(-x, r0, 1.0);
     e = fma(e, e, e);
     acc[t] = fma(n2, fma(r0, e, r0), acc[t]);                               // r0 (1 + e + e^2): <= 1 ulp of 1/x (rcp_probe.cu V1)
@@ -294,7 +297,7 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
 // ---- persistent GA kernel (ahx_ga_res.cuh) ------------------------------------------
 struct ResSmem {
   uint32_t *table; uint8_t *nl8; uint32_t *X0; size_t xstride;
-  double *n2lut, *partial; uint64_t *full, *done, *tab, *tfull, *tempty; uint32_t *scan_scratch;
+  double *partial; uint64_t *full, *done, *tab, *tfull, *tempty; uint32_t *scan_scratch;
   unsigned char *ring;       // STREAM: kRStages tiles
   const uint32_t *sizes;     // contig sizes: shared-memory copy, or the global array
   unsigned char *extra;      // first byte after the evaluate layout (GA scratch)
@@ -313,7 +316,6 @@ __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g
   m.X0 = reinterpret_cast<uint32_t *>(sp);
   m.xstride = res_align16(4ull * g.N * T) / 4;   // words between the two X buffers
   sp += 2 * res_align16(4ull * g.N * T);
-  m.n2lut = reinterpret_cast<double *>(sp); sp += 8ull * 256;                // n2lut[n] = 2n (numerators, evaluate.go:140)
   m.partial = reinterpret_cast<double *>(sp); sp += 8ull * 2 * kRC * T;      // [buf][warp][t]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 8 * 8;            // full[2], done[2], tab
   m.full = bars; m.done = bars + 2; m.tab = bars + 4;
@@ -331,7 +333,6 @@ __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g
 template <bool STREAM = false>
 __device__ __forceinline__ void res_init(const ResSmem &m, const ResArgs &g, bool load_table) {
   const int tid = threadIdx.x;
-  if (tid < 256) m.n2lut[tid] = 2.0 * tid;
   if (g.sizes_in_smem)
     for (int i = tid; i < g.N; i += kRThreads) const_cast<uint32_t *>(m.sizes)[i] = __ldg(g.sizes32 + i);
   if (tid == 0) {
@@ -399,16 +400,23 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < kRC; ++w) s += m.partial[(buf * kRC + w) * T + ptid];
-        src.store(batch, ptid, 0.0 - (s < kResFlush ? 0.0 : s));   // score starts at +0.0 and only subtracts (evaluate.go:128,140)
+        src.store(batch, ptid, 0.0 - (s < kResFlush ? 0.0 : 2.0 * s));   // score starts at +0.0 and only subtracts (evaluate.go:128,140)
       }
     };
     for (int b = first; b < nb; b += stride, ++k) {
-      if (k - k0 >= 2) finalize(k - 2, b - 2 * stride);
+      if (k - k0 >= 2) {
+        // X[k & 1] is free once the consumers are done with batch k - 2: build warp 0 polls the mbarrier
+        // (and folds that batch's partial sums), the others block on a named barrier -- polling from all
+        // build warps took 10 % of the SM's issue slots (r1s)
+        if (ptid < 32) finalize(k - 2, b - 2 * stride);
+        named_bar_sync(3, NB * 32);
+      }
       if (ptid < T) src.prefetch(b + stride, ptid);   // next batch's rows: HBM -> L2 now
       if (k > k0) src.template build<NB, 1>(b, g.L, g.N, m.sizes, m.X0 + (k & 1) * m.xstride, m.scan_scratch, g.errflag, ptid);
       mbar_arrive(&m.full[k & 1]);
     }
-    for (int kk = max(k0, k - 2); kk < k; ++kk) finalize(kk, first + (kk - k0) * stride);
+    if (ptid < 32)
+      for (int kk = max(k0, k - 2); kk < k; ++kk) finalize(kk, first + (kk - k0) * stride);
   } else {
     // ------------------------------------------------------------ consumers
     const int lane = tid & 31, wid = tid >> 5;
@@ -438,10 +446,10 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
           }
 #pragma unroll
           for (int u = 0; u < UI; ++u) {
-            res_pair_terms<T, SUB, true>(X, p[u].x, res_n2<T>(m.n2lut, n[u] & 0xffu), acc);
-            res_pair_terms<T, SUB, true>(X, p[u].y, res_n2<T>(m.n2lut, (n[u] >> 8) & 0xffu), acc);
-            res_pair_terms<T, SUB, true>(X, p[u].z, res_n2<T>(m.n2lut, (n[u] >> 16) & 0xffu), acc);
-            res_pair_terms<T, SUB, true>(X, p[u].w, res_n2<T>(m.n2lut, n[u] >> 24), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].x, res_n<0>(n[u]), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].y, res_n<1>(n[u]), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].z, res_n<2>(n[u]), acc);
+            res_pair_terms<T, SUB, true>(X, p[u].w, res_n<3>(n[u]), acc);
           }
         }
       } else {
@@ -463,10 +471,10 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
           }
 #pragma unroll
           for (int u = 0; u < US; ++u) {
-            res_pair_terms<T, SUB, false>(X, p[u].x, res_n2<T>(m.n2lut, n[u] & 0xffu), acc);
-            res_pair_terms<T, SUB, false>(X, p[u].y, res_n2<T>(m.n2lut, (n[u] >> 8) & 0xffu), acc);
-            res_pair_terms<T, SUB, false>(X, p[u].z, res_n2<T>(m.n2lut, (n[u] >> 16) & 0xffu), acc);
-            res_pair_terms<T, SUB, false>(X, p[u].w, res_n2<T>(m.n2lut, n[u] >> 24), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].x, res_n<0>(n[u]), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].y, res_n<1>(n[u]), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].z, res_n<2>(n[u]), acc);
+            res_pair_terms<T, SUB, false>(X, p[u].w, res_n<3>(n[u]), acc);
           }
           __syncwarp();
           if (lane == 0) {

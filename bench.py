@@ -36,7 +36,7 @@ except Exception:
     pass
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the evaluate kernel, from the committed
 # ncu --set full capture of (workload, P) -- profiles/r1r_ncu_full_summary.txt
-NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64207872 + 360448}
+NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64207360 + 583424}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 
@@ -311,9 +311,9 @@ def main():
             "kernel": {3: "eval_m_res_kernel (table streamed)", 2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[kind], "tours_per_batch": tpb,
             "algorithmic_per_tour": {"stored_pairs_E": E, "fp64_flop": flop_per_pair * E, "smem_gather_bytes": 8 * E,
                                      "in_window_pairs_E_act": e_act, "hbm_bytes": 4 * L + 8},
-            "issue_model": {"issue_cycles_per_pair_term": 17.2, "note": "SASS of the consumer loop: 5 fp64 (2 issue cycles each, term_probe.cu) + 7.2 other instructions per (pair, tour); "
+            "issue_model": {"issue_cycles_per_pair_term": 16.06, "note": "SASS of the consumer loop: 5 fp64 (2 issue cycles each, term_probe.cu) + 6.06 other instructions per (pair, tour); "
                             "frac = terms/s x cycles / (SMs x 4 schedulers x clock)",
-                            "frac": P * E * 17.2 / 32.0 / kern_s / (eng.sm_count() * 4 * sm_mhz * 1e6)},
+                            "frac": P * E * 16.06 / 32.0 / kern_s / (eng.sm_count() * 4 * sm_mhz * 1e6)},
             "measured_div_add_peak_per_s": ddiv_g * 1e9,
             "legs": {k: {"achieved": v[0], "peak": v[1], "unit": v[2], "frac": v[0] / v[1]} for k, v in legs.items()},
             "dense_equivalent": {"window_pairs_per_tour": w_dense, "bytes_per_tour": 4 * w_dense + 12 * L,

@@ -806,10 +806,10 @@ int ahx_load(ahx_ctx *ctx, int32_t N, const int64_t *sizes, int64_t E, const int
     long long total = 0;
     for (int32_t i = 0; i < N; ++i) total += sizes[i];
     ctx->x32_ok = 2 * total + 2LL * AHX_LIMIT + 2 < 0xFFFFFFFFLL;
-    std::vector<uint32_t> s32(N);
+    std::vector<uint32_t> s32(static_cast<size_t>(N) + 1, 0u);   // entry N = 0: the "skip" contig of res_build_x
     for (int32_t i = 0; i < N; ++i) s32[i] = static_cast<uint32_t>(std::min<int64_t>(sizes[i], 0xFFFFFFFFLL));
-    AHX_CUDA(ctx, ctx->d_sizes32.reserve(N));
-    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes32.p, s32.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+    AHX_CUDA(ctx, ctx->d_sizes32.reserve(static_cast<size_t>(N) + 1));
+    AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes32.p, s32.data(), sizeof(uint32_t) * (static_cast<size_t>(N) + 1), cudaMemcpyHostToDevice, ctx->stream));
     AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<int64_t> ord;
     order_pairs(E, pa, pb, &ord, 8);

@@ -36,6 +36,8 @@
 #ifndef AHX_RESIDENT_CUH_
 #define AHX_RESIDENT_CUH_
 
+#include <type_traits>
+
 #include "ahx_device.cuh"
 
 namespace ahx {
@@ -59,7 +61,7 @@ template <bool STREAM> struct ResRoles { static constexpr int NB = STREAM ? kRP 
 struct ResArgs {
   const uint32_t *pairs;      // [E_res]
   const uint8_t *nl8;         // [E_res]
-  const uint32_t *sizes32;    // [N]
+  const uint32_t *sizes32;    // [N + 1], entry N = 0
   int E_res, N, L;
   int *errflag;
   int sizes_in_smem;          // the contig sizes are staged in shared memory (4N bytes) instead of gathered from global memory
@@ -68,7 +70,7 @@ struct ResArgs {
 __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
 // dynamic shared memory of the resident kernel
 inline size_t res_smem_bytes(int T, int N, long long E_res, bool stream = false, bool sizes = false) {
-  return (sizes ? res_align16(4ull * N) : 0) + (stream ? static_cast<size_t>(kRStages) * kRTileBytes : res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res))) +
+  return (sizes ? res_align16(4ull * (N + 1)) : 0) + (stream ? static_cast<size_t>(kRStages) * kRTileBytes : res_align16(4ull * E_res) + res_align16(static_cast<size_t>(E_res))) +
          2 * res_align16(4ull * N * T) + (stream ? 8ull * 2 * kRStages : 0) +
          8ull * 2 * kRC * T + res_align16(4ull * (kRC + kRP) * T) + 8 * 8;
 }
@@ -156,9 +158,22 @@ struct ResDirect {
 // 2*sum(sizes) < 2^32 in x32 mode, so all prefix sums run in 32 bits.
 // NW warps build one batch together (the kRP producer warps in steady state, all kRC + kRP
 // warps for the first batch of a call, when nothing else can run yet); BAR: named barrier.
-template <int T, int NW, int BAR, typename Src>
-__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *sizes32, uint32_t *X,
-                                            uint32_t *scan_scratch /* NW*T */, int *errflag, int ptid) {
+// size of contig c, c in [0, N]: entry N of the sizes array is 0 (the "skip" contig of positions
+// beyond the end and of invalid entries).  SM: the array is the shared-memory copy (32-bit address).
+template <bool SM>
+__device__ __forceinline__ uint32_t res_size_at(const uint32_t *sizes32, uint32_t sbase, uint32_t c) {
+  if constexpr (SM) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + 4u * c));
+    return v;
+  } else {
+    return __ldg(sizes32 + c);
+  }
+}
+
+template <int T, int NW, int BAR, bool SM, typename Src>
+__device__ __forceinline__ void res_build_x_impl(const Src &src, int batch, int L, int N, const uint32_t *sizes32, uint32_t *X,
+                                                 uint32_t *scan_scratch /* NW*T */, int *errflag, int ptid) {
   constexpr int PPI = 4 * (32 / T);              // positions of one tour per warp instruction group
   constexpr int kU = 4;                          // groups in flight per lane (16 positions)
   const int lane = ptid & 31, wid = ptid >> 5;
@@ -167,20 +182,43 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
   const int Q = ((L + NW - 1) / NW + PPI - 1) / PPI * PPI;
   const int beg = min(L, wid * Q), end = cur.live() ? min(L, beg + Q) : beg;   // dead slot: every position is "beyond the end"
   const int wend = min(L, beg + Q);                                            // warp-uniform loop bound
+  // iterations whose 16 positions per lane are all inside the range, for every lane of the warp, take
+  // the short path (no per-position range tests); the last, ragged one (and dead slots) the general one
+  const int fend = __all_sync(0xffffffffu, cur.live()) ? wend : beg;
+  const uint32_t un = static_cast<uint32_t>(N);
+  const uint32_t sbase = SM ? static_cast<uint32_t>(__cvta_generic_to_shared(sizes32)) : 0u;
   bool bad = false;
   if (L < N) {   // sub-tour: contigs outside the tour must fail every window test
     for (int i = ptid; i < N * T; i += NW * 32) X[i] = kInactiveX;
   }
-  // pass 1: sum of sizes over this warp's range, per tour
-  uint32_t local = 0;
-  for (int p0 = beg + sub; p0 - sub < wend; p0 += PPI * kU) {
-    unsigned c[kU][4];
+  // contigs of the lane's 16 positions from p0 on, sanitised to [0, N]: N = skip (beyond the end, or an
+  // invalid entry, which also raises `bad`)
+  auto fetch = [&](int p0, unsigned (&c)[kU][4], auto ragged) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) cur.get4(p0 + u * PPI, end, c[u]);
 #pragma unroll
     for (int u = 0; u < kU; ++u)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) local += c[u][e] < static_cast<unsigned>(N) ? sizes32[c[u][e]] : 0u;
+      for (int e = 0; e < 4; ++e) {
+        if constexpr (decltype(ragged)::value) bad |= (p0 + u * PPI + e < end) && c[u][e] >= un;
+        else bad |= c[u][e] >= un;
+        c[u][e] = min(c[u][e], un);
+      }
+  };
+  // pass 1: sum of sizes over this warp's range, per tour
+  uint32_t local = 0;
+  auto pass1 = [&](int p0, auto ragged) {
+    unsigned c[kU][4];
+    fetch(p0, c, ragged);
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) local += res_size_at<SM>(sizes32, sbase, c[u][e]);
+  };
+  {
+    int p0 = beg + sub;
+    for (; p0 - sub + PPI * kU <= fend; p0 += PPI * kU) pass1(p0, std::false_type{});
+    for (; p0 - sub < wend; p0 += PPI * kU) pass1(p0, std::true_type{});
   }
 #pragma unroll
   for (int d = T; d < 32; d <<= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
@@ -190,18 +228,13 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
 #pragma unroll
   for (int w = 0; w < NW; ++w) carry += (w < wid) ? scan_scratch[w * T + t] : 0u;
   // pass 2: prefix sums + scatter
-  for (int p0 = beg + sub; p0 - sub < wend; p0 += PPI * kU) {
+  auto pass2 = [&](int p0, auto ragged) {
     unsigned c[kU][4]; uint32_t sz[kU][4];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) cur.get4(p0 + u * PPI, end, c[u]);
+    fetch(p0, c, ragged);
 #pragma unroll
     for (int u = 0; u < kU; ++u)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool on = p0 + u * PPI + e < end;
-        if (on && c[u][e] >= static_cast<unsigned>(N)) { bad = true; c[u][e] = 0xFFFFFFFFu; }
-        sz[u][e] = c[u][e] != 0xFFFFFFFFu ? sizes32[c[u][e]] : 0u;
-      }
+      for (int e = 0; e < 4; ++e) sz[u][e] = res_size_at<SM>(sizes32, sbase, c[u][e]);
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const uint32_t tot = sz[u][0] + sz[u][1] + sz[u][2] + sz[u][3];
@@ -211,14 +244,26 @@ __device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, in
       uint32_t cum = carry + v - tot;                                           // sizes before this lane's 4 positions
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (c[u][e] != 0xFFFFFFFFu) X[static_cast<size_t>(c[u][e]) * T + t] = 2u * cum + sz[u][e];   // 2*cum + size
+        if (c[u][e] != un) X[c[u][e] * T + t] = 2u * cum + sz[u][e];            // 2*cum + size = 2*mid (evaluate.go:120-126)
         cum += sz[u][e];
       }
       carry += __shfl_sync(0xffffffffu, v, 32 - T + t);
     }
+  };
+  {
+    int p0 = beg + sub;
+    for (; p0 - sub + PPI * kU <= fend; p0 += PPI * kU) pass2(p0, std::false_type{});
+    for (; p0 - sub < wend; p0 += PPI * kU) pass2(p0, std::true_type{});
   }
   if (bad) *errflag = 1;
   named_bar_sync(BAR, NW * 32);   // scan_scratch may be rewritten by the next batch; X[buf] is complete
+}
+
+template <int T, int NW, int BAR, typename Src>
+__device__ __forceinline__ void res_build_x(const Src &src, int batch, int L, int N, const uint32_t *sizes32, uint32_t *X,
+                                            uint32_t *scan_scratch /* NW*T */, int *errflag, int ptid) {
+  if (__isShared(sizes32)) res_build_x_impl<T, NW, BAR, true>(src, batch, L, N, sizes32, X, scan_scratch, errflag, ptid);
+  else res_build_x_impl<T, NW, BAR, false>(src, batch, L, N, sizes32, X, scan_scratch, errflag, ptid);
 }
 
 // ---- consumer: every stored pair x T tours, branch-free ----------------------------
@@ -322,7 +367,7 @@ __device__ __forceinline__ ResSmem res_carve(unsigned char *sp, const ResArgs &g
   if constexpr (STREAM) { m.tfull = reinterpret_cast<uint64_t *>(sp); m.tempty = m.tfull + kRStages; sp += 8ull * 2 * kRStages; }
   m.scan_scratch = reinterpret_cast<uint32_t *>(sp); sp += res_align16(4ull * (kRC + kRP) * T);
   m.sizes = g.sizes32;
-  if (g.sizes_in_smem) { m.sizes = reinterpret_cast<const uint32_t *>(sp); sp += res_align16(4ull * g.N); }
+  if (g.sizes_in_smem) { m.sizes = reinterpret_cast<const uint32_t *>(sp); sp += res_align16(4ull * (g.N + 1)); }
   m.extra = sp;
   return m;
 }
@@ -334,7 +379,7 @@ template <bool STREAM = false>
 __device__ __forceinline__ void res_init(const ResSmem &m, const ResArgs &g, bool load_table) {
   const int tid = threadIdx.x;
   if (g.sizes_in_smem)
-    for (int i = tid; i < g.N; i += kRThreads) const_cast<uint32_t *>(m.sizes)[i] = __ldg(g.sizes32 + i);
+    for (int i = tid; i <= g.N; i += kRThreads) const_cast<uint32_t *>(m.sizes)[i] = __ldg(g.sizes32 + i);   // entry N = 0: the skip contig
   if (tid == 0) {
     mbar_init(&m.full[0], ResRoles<STREAM>::NB * 32); mbar_init(&m.full[1], ResRoles<STREAM>::NB * 32);
     mbar_init(&m.done[0], kRC); mbar_init(&m.done[1], kRC);
@@ -437,13 +482,21 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
         const uint4 *table4 = reinterpret_cast<const uint4 *>(m.table);
         const uint32_t *nl8x4 = reinterpret_cast<const uint32_t *>(m.nl8);
         const int nvec = g.E_res / kRUnroll;
-        for (int i = tid; i < nvec; i += UI * kRCT) {
-          uint4 p[UI]; uint32_t n[UI];
+        // software-pipelined: the entries of iteration I + 1 are fetched while iteration I computes
+        uint4 pn[UI]; uint32_t nn[UI];
+        auto fetch = [&](int i) {
 #pragma unroll
           for (int u = 0; u < UI; ++u) {
             const int iu = min(i + u * kRCT, nvec - 1);
-            p[u] = table4[iu]; n[u] = i + u * kRCT < nvec ? nl8x4[iu] : 0u;   // beyond the end: zero link counts
+            pn[u] = table4[iu]; nn[u] = i + u * kRCT < nvec ? nl8x4[iu] : 0u;   // beyond the end: zero link counts
           }
+        };
+        fetch(tid);
+        for (int i = tid; i < nvec; i += UI * kRCT) {
+          uint4 p[UI]; uint32_t n[UI];
+#pragma unroll
+          for (int u = 0; u < UI; ++u) { p[u] = pn[u]; n[u] = nn[u]; }
+          if (i + UI * kRCT < nvec) fetch(i + UI * kRCT);
 #pragma unroll
           for (int u = 0; u < UI; ++u) {
             res_pair_terms<T, SUB, true>(X, p[u].x, res_n<0>(n[u]), acc);

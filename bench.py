@@ -377,15 +377,18 @@ def main():
         nq = 1024
         signs = np.where(rng.random((nq, n)) < 0.5, ord('+'), ord('-')).astype(np.uint8)
         eng.eval_q(tours[0], signs[:8])
-        t0 = time.perf_counter(); reps = 5
-        for _ in range(reps):
+        q_t, f_t = [], []
+        for _ in range(15):                       # medians: these calls are short and host-timed
+            t0 = time.perf_counter()
             eng.eval_q(tours[0], signs)
-        q_s = (time.perf_counter() - t0) / reps
-        t0 = time.perf_counter()
-        s2, *_ = eng.flip_one(tours[0], signs[0])
-        f_s = time.perf_counter() - t0
+            q_t.append(time.perf_counter() - t0)
+        for _ in range(7):
+            t0 = time.perf_counter()
+            s2, *_ = eng.flip_one(tours[0], signs[0])
+            f_t.append(time.perf_counter() - t0)
+        q_s, f_s = float(np.median(q_t)), float(np.median(f_t))
         out["orientation"] = {"eval_q_per_s_e2e": nq / q_s, "batch": nq, "flip_one_pass_ms_e2e": f_s * 1e3, "tour_length": int(L),
-                              "note": "host buffers through ahx_eval_q / ahx_flip_one; the reference does 1 + L full EvaluateQ per flipOne pass"}
+                              "note": "host buffers through ahx_eval_q / ahx_flip_one, medians of 15 / 7 calls; the reference does 1 + L full EvaluateQ per flipOne pass"}
         if world == 1 and args.cpu_seconds > 0:
             # the CPU restatement beside it: EvaluateQ as the reference does it (dense 96*N^2-byte Q() rebuilt per call,
             # orientation.go:137-193) and with the map lookup that avoids Q(); a flipOne pass = (1 + L) such calls

@@ -459,7 +459,8 @@ static cudaError_t launch_res_t(ahx_ctx *ctx, bool sizes, const IdxT *tours, con
   const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res[res_ti(T)], STREAM, sizes);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  ResArgs g{(STREAM ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, L, ctx->d_errflag.p, sizes ? 1 : 0};
+  const bool scaled = static_cast<uint64_t>(ctx->N) * 4u * T <= 65535u;   // the table of byte offsets exists (ahx_load)
+  ResArgs g{(STREAM && !scaled ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, L, ctx->d_errflag.p, sizes ? 1 : 0, scaled ? 1 : 0};
   ResDirect<T, IdxT> src{};
   src.tours = tours; src.rows = rows; src.P = P; src.L = L; src.out = out;
   const int nb = (P + T - 1) / T;

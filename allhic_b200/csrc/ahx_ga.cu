@@ -653,7 +653,8 @@ static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->ga_smem));
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
-  ResArgs g{(STREAM ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, ctx->ga_L, ctx->d_errflag.p, 0};
+  const bool scaled = static_cast<uint64_t>(ctx->N) * 4u * T <= 65535u;   // the table of byte offsets exists (ahx_load)
+  ResArgs g{(STREAM && !scaled ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, ctx->ga_L, ctx->d_errflag.p, 0, scaled ? 1 : 0};
   GaRes q = make_res(ctx);
   void *args[] = {&g, &q, &n_gens};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(ctx->ga_G), dim3(kRThreads), args, ctx->ga_smem, s);

@@ -65,6 +65,7 @@ struct ResArgs {
   int E_res, N, L;
   int *errflag;
   int sizes_in_smem;          // the contig sizes are staged in shared memory (4N bytes) instead of gathered from global memory
+  int scaled;                 // STREAM: `pairs` holds byte offsets (a*4T) | (b*4T) << 16 like the resident table, not contig indices
 };
 
 __host__ __device__ inline size_t res_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
@@ -507,35 +508,43 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
         }
       } else {
         constexpr int US = UI > 2 ? 2 : UI;   // at most half of the ring's stages in use, the other half loading
-        for (int tile = 0; tile < ntiles; tile += US) {
-          uint4 p[US]; uint32_t n[US];
+        // ring position of this batch's first tile; stage and phase then advance incrementally
+        const long long c0 = static_cast<long long>(k) * ntiles;                  // tiles pushed through the ring since res_init
+        int st = static_cast<int>(c0 % kRStages);
+        uint32_t ph = static_cast<uint32_t>((c0 / kRStages) & 1);
+        auto run = [&](auto scaled, auto count) {
+          constexpr bool SC = decltype(scaled)::value;
+          constexpr int NT = decltype(count)::value;                              // tiles of this step (US, or 1 for the odd last one)
+          uint4 p[NT]; uint32_t n[NT]; int used[NT];
 #pragma unroll
-          for (int u = 0; u < US; ++u) {
-            if (tile + u < ntiles) {
-              const long long c = static_cast<long long>(k) * ntiles + tile + u;
-              const int st = static_cast<int>(c % kRStages);
-              mbar_wait(&m.tfull[st], static_cast<uint32_t>((c / kRStages) & 1));
-              const unsigned char *src_tile = m.ring + static_cast<size_t>(st) * kRTileBytes;
-              p[u] = reinterpret_cast<const uint4 *>(src_tile)[tid];
-              n[u] = reinterpret_cast<const uint32_t *>(src_tile + 4 * kRPad)[tid];
-            } else {
-              p[u] = make_uint4(0x10000u, 0x10000u, 0x10000u, 0x10000u); n[u] = 0u;   // contigs (0, 1), zero links
-            }
+          for (int u = 0; u < NT; ++u) {
+            mbar_wait(&m.tfull[st], ph);
+            const unsigned char *src_tile = m.ring + static_cast<size_t>(st) * kRTileBytes;
+            p[u] = reinterpret_cast<const uint4 *>(src_tile)[tid];
+            n[u] = reinterpret_cast<const uint32_t *>(src_tile + 4 * kRPad)[tid];
+            used[u] = st;
+            if (++st == kRStages) { st = 0; ph ^= 1u; }
           }
 #pragma unroll
-          for (int u = 0; u < US; ++u) {
-            res_pair_terms<T, SUB, false>(X, p[u].x, res_n<0>(n[u]), acc);
-            res_pair_terms<T, SUB, false>(X, p[u].y, res_n<1>(n[u]), acc);
-            res_pair_terms<T, SUB, false>(X, p[u].z, res_n<2>(n[u]), acc);
-            res_pair_terms<T, SUB, false>(X, p[u].w, res_n<3>(n[u]), acc);
+          for (int u = 0; u < NT; ++u) {
+            res_pair_terms<T, SUB, SC>(X, p[u].x, res_n<0>(n[u]), acc);
+            res_pair_terms<T, SUB, SC>(X, p[u].y, res_n<1>(n[u]), acc);
+            res_pair_terms<T, SUB, SC>(X, p[u].z, res_n<2>(n[u]), acc);
+            res_pair_terms<T, SUB, SC>(X, p[u].w, res_n<3>(n[u]), acc);
           }
           __syncwarp();
           if (lane == 0) {
 #pragma unroll
-            for (int u = 0; u < US; ++u)
-              if (tile + u < ntiles) mbar_arrive(&m.tempty[static_cast<int>((static_cast<long long>(k) * ntiles + tile + u) % kRStages)]);   // done with the stage
+            for (int u = 0; u < NT; ++u) mbar_arrive(&m.tempty[used[u]]);         // done with the stage
           }
-        }
+        };
+        auto sweep = [&](auto scaled) {
+          int tile = 0;
+          for (; tile + US <= ntiles; tile += US) run(scaled, std::integral_constant<int, US>{});
+          for (; tile < ntiles; ++tile) run(scaled, std::integral_constant<int, 1>{});
+        };
+        // entries are byte offsets into X when N * 4T fits 16 bits (one instruction less per gather), else contig indices
+        if (g.scaled) sweep(std::true_type{}); else sweep(std::false_type{});
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {

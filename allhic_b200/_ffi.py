@@ -65,6 +65,7 @@ SIGNATURES = {
     "ahx_pop_eval_m": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "ahx_pop_scores": (C.c_int, [_vp, _vp]),
     "ahx_eval_m_kernel": (C.c_int, [_vp, C.c_int32, C.c_int32, _p32]),
+    "ahx_pair_table_entries": (C.c_int64, [_vp, C.c_int32]),
     "ahx_flush_l2": (C.c_int, [_vp]),
     "ahx_ga_default_params": (None, [C.POINTER(GAParams)]),
     "ahx_ga_run": (C.c_int, [_vp, C.POINTER(GAParams), C.c_int32, _vp, _vp, C.POINTER(GAStats), GA_CALLBACK, _vp]),

@@ -596,8 +596,8 @@ static int validate_tours(ahx_ctx *ctx, int32_t P, int32_t L, const IdxT *tours,
 // 128-bit load is served one quarter-warp (8 lanes) at a time across 8 bank
 // groups, group = contig mod 8.  Pairs are therefore emitted in blocks of 8 in
 // which all `a mod 8` and all `b mod 8` are distinct (greedy over the 64
-// (a mod 8, b mod 8) buckets, largest bucket first); blocks that cannot be
-// filled are padded with (0,0,0) entries, which contribute nothing (d = 0).
+// (a mod 8, b mod 8) buckets, largest bucket first); lanes of a block that cannot be
+// filled that way take conflicting pairs rather than padding.
 // The order of the terms only changes the (fixed) summation order.
 // W: lanes that are served together by one shared-memory wavefront of the coordinate gather =
 // 32 / T (a contig's T coordinates are 4T bytes: 8 lanes x 16 B, 16 x 8 B or 32 x 4 B per 128 B);
@@ -624,6 +624,27 @@ void order_pairs(int64_t E, const int32_t *pa, const int32_t *pb, std::vector<in
         order->push_back(bucket[static_cast<size_t>(r) * W + best].back());
         bucket[static_cast<size_t>(r) * W + best].pop_back();
         used_b[best] = 1; --left; ++filled;
+      }
+    }
+    // lanes without a conflict-free candidate take the pair that collides with the fewest lanes of
+    // the block (ties: fullest bucket): a bank conflict costs one extra wavefront of one gather, a
+    // padding entry a whole term per tour (the padded tables were 9 % longer than the pair lists at
+    // config3 and config5, 33 % at config2)
+    if (filled < W && left > 0) {
+      std::vector<int> na(W, 0), nb(W, 0);
+      for (size_t i = order->size() - filled; i < order->size(); ++i) { ++na[pa[(*order)[i]] % W]; ++nb[pb[(*order)[i]] % W]; }
+      for (; filled < W && left > 0; ++filled, --left) {
+        int best = -1, best_cost = 0; size_t best_n = 0;
+        for (int r = 0; r < W; ++r)
+          for (int cc = 0; cc < W; ++cc) {
+            const size_t n = bucket[static_cast<size_t>(r) * W + cc].size();
+            if (!n) continue;
+            const int cost = na[r] + nb[cc];
+            if (best < 0 || cost < best_cost || (cost == best_cost && n > best_n)) { best = r * W + cc; best_cost = cost; best_n = n; }
+          }
+        order->push_back(bucket[best].back());
+        bucket[best].pop_back();
+        ++na[best / W]; ++nb[best % W];
       }
     }
     for (; filled < W; ++filled) order->push_back(-1);
@@ -980,6 +1001,12 @@ int ahx_eval_m_kernel(const ahx_ctx *ctx, int32_t P, int32_t L, int32_t *tours_p
   else if (eval_m_smem_bytes(1, ctx->N, L) + 1024 <= ctx->smem_optin) T = pick_T(ctx, P, L);
   if (tours_per_batch) *tours_per_batch = T;
   return kind;
+}
+
+int64_t ahx_pair_table_entries(const ahx_ctx *ctx, int32_t tours_per_batch) {
+  if (!ctx || !ctx->loaded) return AHX_ERR_STATE;
+  if (tours_per_batch != 1 && tours_per_batch != 2 && tours_per_batch != 4) return AHX_ERR_ARG;
+  return ctx->E_res[res_ti(tours_per_batch)];
 }
 
 int ahx_flush_l2(ahx_ctx *ctx) {

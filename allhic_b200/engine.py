@@ -125,6 +125,10 @@ class Engine:
             self._ck(kind)
         return kind, t.value
 
+    def pair_table_entries(self, tours_per_batch):
+        """Entries (stored pairs + padding) of the resident kernel's pair table for T tours per batch."""
+        return int(self._l.ahx_pair_table_entries(self.h, tours_per_batch))
+
     def flush_l2(self):
         self._ck(self._l.ahx_flush_l2(self.h))
 

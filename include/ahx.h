@@ -145,6 +145,10 @@ int ahx_pop_scores(ahx_ctx *ctx, double *out /* P */);
  * one CTA per T tours), 0 eval_m_sparse_kernel (fp64 coordinates).
  * *tours_per_batch (optional) receives the tours one CTA scores together. */
 int ahx_eval_m_kernel(const ahx_ctx *ctx, int32_t P, int32_t L, int32_t *tours_per_batch);
+/* Entries of eval_m_res_kernel's pair table for tours_per_batch = 1, 2 or 4: the stored pairs
+ * (pairs with more than 255 links split) plus the padding of the bank-conflict-free order;
+ * 0 if that table was not built.  Every entry costs one term per tour (roofline bookkeeping). */
+int64_t ahx_pair_table_entries(const ahx_ctx *ctx, int32_t tours_per_batch);
 /* Writes `bytes` of device memory (> L2) to evict the L2 between timed runs. */
 int ahx_flush_l2(ahx_ctx *ctx);
 

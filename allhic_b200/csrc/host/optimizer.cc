@@ -40,18 +40,19 @@ void CLM::check(int rc, const char *what) {
   if (rc != AHX_OK) logFatal("%s: %s", what, ahx_last_error(ctx_));
 }
 
-CLM::CLM(const std::string &clmfile, const std::string &refile, int device) : REfile(refile), Clmfile(clmfile) {
+CLM::CLM(const std::string &clmfile, const std::string &refile, int device, ahx_ctx *shared) : REfile(refile), Clmfile(clmfile) {
   logNotice("Parse REfile `%s`", refile.c_str());
   logNotice("Parse clmfile `%s`", clmfile.c_str());
   if (ahx_clm_parse(clmfile.c_str(), refile.c_str(), 0, &clm_) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));   // mustOpen -> log.Fatal
   const int n = ahx_clm_ntigs(clm_);
   for (int i = 0; i < n; ++i) Tigs.push_back({i, ahx_clm_tig_name(clm_, i), ahx_clm_tig_size(clm_, i), true});
-  if (ahx_create(device, &ctx_) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));
+  if (shared) { ctx_ = shared; own_ctx_ = false; }
+  else if (ahx_create(device, &ctx_) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));
   check(ahx_load_clm(ctx_, clm_), "ahx_load_clm");
 }
 
 CLM::~CLM() {
-  if (ctx_) ahx_destroy(ctx_);
+  if (ctx_ && own_ctx_) ahx_destroy(ctx_);
   if (clm_) ahx_clm_free(clm_);
 }
 
@@ -206,7 +207,7 @@ void CLM::OptimizeOrientations(FILE *fwtour, int phase, const char **tag1, const
 
 void Optimizer::Run() {
   std::mt19937_64 rng(static_cast<uint64_t>(Seed));
-  CLM clm(Clmfile, REfile, Device);
+  CLM clm(Clmfile, REfile, Device, Ctx);
   const std::string tourfile = RemoveExt(REfile) + ".tour";
   struct stat sb;
   if (Resume && stat(tourfile.c_str(), &sb) == 0) {   // optimize.go:44-51

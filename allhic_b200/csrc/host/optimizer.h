@@ -38,8 +38,9 @@ class CLM {
   allhic::Tour Tour;
   std::vector<uint8_t> Signs;
 
-  // NewCLM (clm.go:121): parse both files and upload the group to `device`.
-  CLM(const std::string &clmfile, const std::string &refile, int device);
+  // NewCLM (clm.go:121): parse both files and upload the group to `device`.  `shared`: a context the
+  // caller owns and reuses from group to group (`optimize-many`); else one is created and destroyed here.
+  CLM(const std::string &clmfile, const std::string &refile, int device, ahx_ctx *shared = nullptr);
   ~CLM();
   CLM(const CLM &) = delete;
   CLM &operator=(const CLM &) = delete;
@@ -60,6 +61,7 @@ class CLM {
  private:
   ahx_clm *clm_ = nullptr;
   ahx_ctx *ctx_ = nullptr;
+  bool own_ctx_ = true;
   void check(int rc, const char *what);
 };
 
@@ -71,6 +73,7 @@ struct Optimizer {       // optimize.go:21-35
   int NGen = 5000;       // base.go:69
   double MutProb = 0.2;  // base.go:71
   int Device = 0;
+  ahx_ctx *Ctx = nullptr;   // borrowed device context (optimize-many); nullptr: Run() makes its own
   std::string OutTourFile;
   void Run();            // optimize.go:38
 };

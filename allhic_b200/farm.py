@@ -4,6 +4,13 @@ processes", allhic.go:170-173; `pipeline` runs them sequentially,
 allhic.go:285-293).  Each group is a full `allhic-b200 optimize` run (the C++
 host over the C ABI) pinned to one GPU; groups are handed out
 longest-processing-time-first (weight ~ N^2) to whichever GPU is free.
+
+`persistent=True` (default) keeps ONE `allhic-b200 optimize-many -` process per
+GPU and feeds it groups over stdin as it reports them done: the CUDA context --
+about a second to create, several when eight processes start together, i.e. as
+much as the optimisation of a small group itself -- is made once per GPU
+instead of once per group.  `persistent=False` starts one `optimize` process
+per group.
 """
 import os
 import re
@@ -20,12 +27,71 @@ def _count_contigs(refile):
         return sum(1 for line in f if line.strip() and not line.startswith("#"))
 
 
-def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None):
+def _device_env(dev):
+    # the process sees its GPU only: CUDA start-up enumerates every visible device, which costs
+    # seconds per process on an 8-GPU box
+    env = dict(os.environ)
+    vis = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+    env["CUDA_VISIBLE_DEVICES"] = vis[dev] if dev < len(vis) else str(dev)
+    return env
+
+
+def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir):
+    """One `optimize-many -` process on device `dev`: write a group to its stdin, read its stdout up
+    to the AHX_GROUP_DONE line, repeat.  A worker that dies fails the group it was on and is restarted."""
+    proc = None
+    errf = open(os.path.join(log_dir, "device%d.stderr" % dev), "w") if log_dir else subprocess.DEVNULL
+    try:
+        while True:
+            with lock:
+                if not order:
+                    break
+                g = order.pop(0)
+            refile, clmfile = groups[g]
+            if proc is None or proc.poll() is not None:
+                proc = subprocess.Popen([binary, "optimize-many", "-", "--device", "0", *flags], stdin=subprocess.PIPE,
+                                        stdout=subprocess.PIPE, stderr=errf, text=True, bufsize=1, env=_device_env(dev))
+            t0 = time.perf_counter()
+            out, ok = [], False
+            try:
+                proc.stdin.write("%s %s\n" % (refile, clmfile))
+                proc.stdin.flush()
+                for line in proc.stdout:
+                    if line.startswith("AHX_GROUP_DONE "):
+                        ok = True
+                        break
+                    out.append(line)
+            except (BrokenPipeError, OSError):
+                pass
+            dt = time.perf_counter() - t0
+            scores = re.findall(r"max_score=([0-9.eE+-]+)", "".join(out))
+            results[g] = dict(group=g, device=dev, seconds=dt, n_contigs=_count_contigs(refile),
+                              final_score=float(scores[-1]) if scores else None, ok=ok)
+    finally:
+        if proc is not None and proc.poll() is None:
+            try:
+                proc.stdin.close()
+                proc.wait(timeout=60)
+            except Exception:
+                proc.kill()
+        if log_dir:
+            errf.close()
+
+
+def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None, persistent=True):
     """groups: list of (refile, clmfile); devices: CUDA device indices to farm over.
     Returns a list of dicts (group, device, seconds, final_score, n_contigs, ok) in input order."""
     order = sorted(range(len(groups)), key=lambda g: -_count_contigs(groups[g][0]) ** 2)
     lock = threading.Lock()
     results = [None] * len(groups)
+    if persistent:
+        threads = [threading.Thread(target=_persistent_worker, args=(d, groups, order, lock, results, flags, binary, log_dir))
+                   for d in devices]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        return results
 
     def worker(dev):
         while True:
@@ -35,11 +101,7 @@ def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None):
                 g = order.pop(0)
             refile, clmfile = groups[g]
             t0 = time.perf_counter()
-            # the process sees its GPU only: CUDA start-up enumerates every visible device, which costs
-            # seconds per process on an 8-GPU box
-            env = dict(os.environ)
-            vis = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
-            env["CUDA_VISIBLE_DEVICES"] = vis[dev] if dev < len(vis) else str(dev)
+            env = _device_env(dev)
             p = subprocess.run([binary, "optimize", refile, clmfile, "--device", "0", *flags],
                                capture_output=True, text=True, env=env)
             dt = time.perf_counter() - t0

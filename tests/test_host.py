@@ -136,15 +136,28 @@ def test_synth_is_deterministic():
     assert len(a["pa"]) > 120 and (a["pa"] < a["pb"]).all()
 
 
-def test_farm_runs_every_group_once_largest_first(tmp_path):
+@pytest.mark.parametrize("persistent", [False, True])
+def test_farm_runs_every_group_once_largest_first(tmp_path, persistent):
     """One linkage group per GPU (allhic.go:170-173): the farm hands groups out
-    longest-processing-time-first to whichever device is free; a stand-in for the
-    host binary records what it was asked to do."""
+    longest-processing-time-first to whichever device is free -- to one `optimize`
+    process per group, or (persistent) over stdin to one `optimize-many -` process per
+    device; a stand-in for the host binary records what it was asked to do."""
     import stat
     from allhic_b200 import farm
     fake = tmp_path / "fake-allhic"
-    fake.write_text("#!/bin/sh\n# optimize <refile> <clmfile> --device <d>\n"
-                    "echo \"Current iteration GA2-500: max_score=0.5$5\"\necho \"$2 $CUDA_VISIBLE_DEVICES\" >> %s/calls.log\necho 'NOTICE Success' >&2\n" % tmp_path)
+    fake.write_text("""#!/bin/sh
+run() {  # refile
+  echo "Current iteration GA2-500: max_score=0.5$3"
+  echo "$1 $CUDA_VISIBLE_DEVICES $$" >> %s/calls.log
+  echo 'NOTICE Success' >&2
+}
+if [ "$1" = optimize-many ]; then
+  i=0
+  while read re clm; do run "$re"; echo "AHX_GROUP_DONE $i $re"; i=$((i+1)); done
+else
+  run "$2"
+fi
+""" % tmp_path)
     fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
     groups = []
     for g, n in enumerate([5, 50, 20, 35]):
@@ -152,11 +165,13 @@ def test_farm_runs_every_group_once_largest_first(tmp_path):
         ids.write_text("#Contig\tRECounts\tLength\n" + "".join("t%d\t1\t100\n" % i for i in range(n)))
         (tmp_path / ("g%d.clm" % g)).write_text("")
         groups.append((str(ids), str(tmp_path / ("g%d.clm" % g))))
-    res = farm.optimize_groups(groups, devices=[0, 1], binary=str(fake))
+    res = farm.optimize_groups(groups, devices=[0, 1], binary=str(fake), persistent=persistent, log_dir=str(tmp_path))
     assert [r["group"] for r in res] == [0, 1, 2, 3] and all(r["ok"] for r in res)
     assert [r["n_contigs"] for r in res] == [5, 50, 20, 35]
     assert all(r["final_score"] is not None and r["device"] in (0, 1) for r in res)
-    calls = (tmp_path / "calls.log").read_text().split("\n")
-    assert sorted(c.split()[0] for c in calls if c) == sorted(g[0] for g in groups)   # each group exactly once
-    first_two = {c.split()[0] for c in calls[:2]}
-    assert str(tmp_path / "g1.ids") in first_two                                        # the largest group starts first
+    calls = [c.split() for c in (tmp_path / "calls.log").read_text().split("\n") if c]
+    assert sorted(c[0] for c in calls) == sorted(g[0] for g in groups)                  # each group exactly once
+    assert str(tmp_path / "g1.ids") in {c[0] for c in calls[:2]}                        # the largest group starts first
+    assert all(c[1] in ("0", "1") for c in calls)                                        # each process sees one GPU
+    if persistent:
+        assert len({c[2] for c in calls}) <= 2                                           # one process per device, reused

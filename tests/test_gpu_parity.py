@@ -395,6 +395,33 @@ def test_ga_large_population_stays_on_the_persistent_kernel(fix):
         eng.ga_end()
 
 
+def test_optimize_many_equals_separate_runs(built_lib, tmp_path):
+    """`allhic-b200 optimize-many` (one process and one device context for a list of groups, the host
+    binary's form of pipeline's loop, allhic.go:285-293) leaves the same .tour files as separate
+    `optimize` runs; the second group goes through a context that has already held another one."""
+    import shutil, subprocess
+    from allhic_b200 import farm, synth
+    g = synth.generate(120, 4242)
+    runs = {}
+    for mode in ("many", "single"):
+        d = tmp_path / mode
+        (d / "a").mkdir(parents=True); (d / "b").mkdir()
+        ids_a, clm_a = synth.write(g, str(d / "a" / "s120"))
+        shutil.copy(FIX_IDS, d / "b" / "test.ids"); shutil.copy(FIX_CLM, d / "b" / "test.clm")
+        pairs = [(ids_a, clm_a), (str(d / "b" / "test.ids"), str(d / "b" / "test.clm"))]
+        if mode == "many":
+            (d / "list").write_text("".join("%s %s\n" % p for p in pairs))
+            r = subprocess.run([farm.BINARY, "optimize-many", str(d / "list"), "--ngen", "300"], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and r.stderr.count("Success") == 2
+            assert [l.split()[1] for l in r.stdout.splitlines() if l.startswith("AHX_GROUP_DONE")] == ["0", "1"]
+        else:
+            for p in pairs:
+                r = subprocess.run([farm.BINARY, "optimize", p[0], p[1], "--ngen", "300"], capture_output=True, text=True, timeout=300)
+                assert r.returncode == 0 and "Success" in r.stderr
+        runs[mode] = [open(p[0].rsplit(".", 1)[0] + ".tour").read() for p in pairs]
+    assert runs["many"] == runs["single"]
+
+
 # ---------------------------------------------------------------- orientation
 def test_flip_whole_and_one_match_oracle(fix, syn):
     for eng, clm, orc in (fix, syn):
@@ -475,6 +502,20 @@ def test_config3_size_properties(built_lib):
     for k in range(3):
         orc.set_signs(sg[k]); assert close(q[k], orc.evaluate_q())
     assert (s == eng.eval_m(tours)).all()                           # bit-reproducible run to run
+    # the pair table is the pair list rounded up to one loop iteration of the consumers (2048 entries):
+    # lanes without a conflict-free candidate take colliding pairs, not padding (order_pairs)
+    nl = clm.tables()["nlinks"]
+    need = int(np.sum((nl + 254) // 255))
+    assert [eng.pair_table_entries(t) for t in (1, 2, 4)] == [(need + 2047) // 2048 * 2048] * 3
+    # invalid entries in the producers' short path (whole 16-position groups inside the range): any of
+    # -1, N, a huge index, in the middle of a tour of the middle of the population, is an argument error
+    import allhic_b200 as A
+    for badv in (-1, n, 1 << 30):
+        t2 = tours[:64].copy(); t2[37, 1001] = badv
+        with pytest.raises(A.AhxError) as ei:
+            eng.eval_m(t2)
+        assert ei.value.code == -1
+    assert close(eng.eval_m(tours[:64]), s[:64], 1e-13)              # flag cleared (64 tours: another T, another summation order)
     # the device-resident GA at the full size: every one of the 8000 individuals stays consistent with
     # its stored tour (permutation, fitness, coordinates) and the best-ever score never decreases
     eng.ga_begin(tours[0], eng.ga_params(npop=P, ngen=1 << 30, max_gens=1 << 40, seed=11))

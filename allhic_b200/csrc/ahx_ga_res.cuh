@@ -388,11 +388,11 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     ++nsync;
     grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
     AHX_TICK(3);   // grid barrier
+    const unsigned long long kmin = __ldcg(gmin_new);   // in flight together with the mask words (one L2 round trip, not two)
     M = ga_load_mask(q, q.gmask + static_cast<size_t>(ngen_now & 1) * WM, mflag, mpref, scan_tmp);
     // ---- bookkeeping (evaluate.go:287-306).  Clones are copies of individuals that already exist, so
     // only a mutated offspring can beat the hall of fame: compare the minimum over this generation's
     // evaluations; on a (rare) improvement the owners of that fitness agree on the lowest offspring index.
-    const unsigned long long kmin = __ldcg(gmin_new);
     if (kmin < fit_key(hof_fit)) {          // updateHallOfFame keeps the best ever; currentBest > *best
       hof_fit = key_fit(kmin); updated = ngen_now;
       for (int s = tid; s < nb_local * T; s += kRThreads) {

@@ -312,7 +312,7 @@ __device__ __forceinline__ double res_n(uint32_t n8x4) {
 // SCALED: p holds byte offsets (resident tables); otherwise contig indices a | b << 16 (the
 // streamed table of large groups, where N * 4T can exceed 16 bits).
 template <int T, bool SUB, bool SCALED>
-__device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, double n2, double (&acc)[T]) {
+__device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, double n, double (&acc)[T]) {
   using V = typename XVec<T>::type;
   uint32_t xa[T], xb[T];
   const unsigned char *Xb = reinterpret_cast<const unsigned char *>(X);
@@ -335,7 +335,7 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
     r0 = __hiloint2double(__double2hiint(r0), static_cast<int>(d));         // any low word will do (2^-27): saves zeroing it
     double e = fma(-x, r0, 1.0);
     e = fma(e, e, e);
-    acc[t] = fma(n2, fma(r0, e, r0), acc[t]);                               // r0 (1 + e + e^2): <= 1 ulp of 1/x (rcp_probe.cu V1)
+    acc[t] = fma(n, fma(r0, e, r0), acc[t]);                               // r0 (1 + e + e^2): <= 1 ulp of 1/x (rcp_probe.cu V1)
   }
 }
 

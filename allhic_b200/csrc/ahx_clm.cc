@@ -18,6 +18,7 @@
 #include <string>
 #include <string_view>
 #include <thread>
+#include <chrono>
 #include <unordered_map>
 #include <vector>
 
@@ -83,6 +84,37 @@ static inline uint64_t okey(int32_t a, int32_t b, uint8_t ao, uint8_t bo) {
 
 using namespace ahx;
 
+// uint64 -> int64 map for the two Go maps' key -> insertion index: open addressing, linear probing,
+// no erase.  (std::unordered_map's node allocations made the serial apply phase 2 us per CLM line.)
+struct FlatMap {
+  std::vector<uint64_t> k;   // key + 1; 0 = empty
+  std::vector<int64_t> v;
+  size_t n = 0, mask = 0;
+  static uint64_t mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; }
+  void rehash(size_t cap) {
+    std::vector<uint64_t> ok; std::vector<int64_t> ov;
+    ok.swap(k); ov.swap(v);
+    k.assign(cap, 0); v.assign(cap, 0); mask = cap - 1; n = 0;
+    for (size_t i = 0; i < ok.size(); ++i) if (ok[i]) { bool ins; *insert(ok[i] - 1, ov[i], &ins) = ov[i]; }
+  }
+  void reserve(size_t want) { size_t cap = 16; while (cap < want + want / 2) cap <<= 1; if (cap > k.size()) rehash(cap); }
+  const int64_t *find(uint64_t key) const {
+    if (k.empty()) return nullptr;
+    for (size_t i = mix(key) & mask;; i = (i + 1) & mask) {
+      if (k[i] == key + 1) return &v[i];
+      if (!k[i]) return nullptr;
+    }
+  }
+  // slot of `key`; a new key is entered with `val` (*inserted = true)
+  int64_t *insert(uint64_t key, int64_t val, bool *inserted) {
+    if ((n + 1) * 3 > k.size() * 2) rehash(k.empty() ? 16 : k.size() * 2);   // load factor <= 2/3
+    for (size_t i = mix(key) & mask;; i = (i + 1) & mask) {
+      if (k[i] == key + 1) { *inserted = false; return &v[i]; }
+      if (!k[i]) { k[i] = key + 1; v[i] = val; ++n; *inserted = true; return &v[i]; }
+    }
+  }
+};
+
 struct ahx_clm {
   int32_t n = 0;
   std::vector<std::string> names;
@@ -91,33 +123,44 @@ struct ahx_clm {
   struct Contact { int32_t ai, bi; int32_t strand; int64_t nlinks; double mean_dist; };
   struct Oriented { int32_t ai, bi; uint8_t ao, bo; std::array<int32_t, AHX_BB> g; };
   std::vector<Contact> contacts;                       // insertion order
-  std::unordered_map<uint64_t, int64_t> cmap;
-  std::vector<Oriented> oriented;                      // insertion order
-  std::unordered_map<uint64_t, int64_t> omap;
+  FlatMap cmap;
+  // orientedContacts, sharded by key hash so that ahx_clm_parse can fill the shards from several
+  // threads; within a shard entries keep the file's order ("later line wins" is a per-key rule)
+  struct OShard { FlatMap map; std::vector<Oriented> v; };
+  std::vector<OShard> osh = std::vector<OShard>(1);
+  size_t shard_of(uint64_t key) const { return osh.size() == 1 ? 0 : static_cast<size_t>((FlatMap::mix(key) >> 40) % osh.size()); }
   bool finalized = false;
   std::vector<int32_t> pa, pb, nl, slots, hist;
   std::vector<int8_t> strand;
 
-  void apply_line(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g,
-                  double mean_dist, int64_t nlinks) {
+  void apply_contact(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, double mean_dist, int64_t nlinks) {
     finalized = false;
     const int32_t st = (ao != bo) ? -1 : 1;                                 // clm.go:224-227
-    auto it = cmap.find(pair_key(ai, bi));
-    if (it != cmap.end()) {
-      Contact &c = contacts[it->second];
-      if (mean_dist < c.mean_dist) { c.strand = st; c.nlinks = nlinks; c.mean_dist = mean_dist; }
-    } else {
-      cmap.emplace(pair_key(ai, bi), static_cast<int64_t>(contacts.size()));
+    bool fresh;
+    const int64_t at = *cmap.insert(pair_key(ai, bi), static_cast<int64_t>(contacts.size()), &fresh);
+    if (fresh) {
       contacts.push_back({ai, bi, st, nlinks, mean_dist});
+    } else {
+      Contact &c = contacts[at];
+      if (mean_dist < c.mean_dist) { c.strand = st; c.nlinks = nlinks; c.mean_dist = mean_dist; }   // clm.go:229-236
     }
-    put_oriented(ai, bi, ao, bo, g);
-    put_oriented(bi, ai, rr(bo), rr(ao), g);                                // clm.go:238
   }
-  void put_oriented(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g) {
-    auto it = omap.find(okey(ai, bi, ao, bo));
-    if (it != omap.end()) { oriented[it->second].g = g; return; }
-    omap.emplace(okey(ai, bi, ao, bo), static_cast<int64_t>(oriented.size()));
-    oriented.push_back({ai, bi, ao, bo, g});
+  void apply_line(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g,
+                  double mean_dist, int64_t nlinks) {
+    apply_contact(ai, bi, ao, bo, mean_dist, nlinks);
+    put_oriented(ai, bi, ao, bo, g, -1);
+    put_oriented(bi, ai, rr(bo), rr(ao), g, -1);                            // clm.go:238
+  }
+  // only < 0: whatever the key's shard; else only when the key belongs to shard `only` (one thread per shard)
+  void put_oriented(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g, int only) {
+    const uint64_t key = okey(ai, bi, ao, bo);
+    const size_t sh = shard_of(key);
+    if (only >= 0 && sh != static_cast<size_t>(only)) return;
+    OShard &o = osh[sh];
+    bool fresh;
+    const int64_t at = *o.map.insert(key, static_cast<int64_t>(o.v.size()), &fresh);
+    if (fresh) o.v.push_back({ai, bi, ao, bo, g});
+    else o.v[at].g = g;
   }
 };
 
@@ -241,6 +284,7 @@ int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm
   if (rc != AHX_OK) { delete clm; return rc; }
   Mapped m;
   if (!m.open(clmfile)) { set_global_error(std::string("cannot open clmfile `") + clmfile + "`"); delete clm; return AHX_ERR_IO; }
+  const auto t_start = std::chrono::steady_clock::now();
   if (nthreads <= 0) nthreads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
   nthreads = static_cast<int>(std::min<size_t>(static_cast<size_t>(nthreads), m.n / (1 << 16) + 1));
   std::vector<size_t> cut(nthreads + 1);
@@ -257,11 +301,42 @@ int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm
   for (int t = 0; t < nthreads; ++t)
     th.emplace_back([&, t] { ok[t] = parse_chunk(*clm, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t]); });
   for (auto &x : th) x.join();
+  const auto t_parse = std::chrono::steady_clock::now();
   for (int t = 0; t < nthreads; ++t)
     if (!ok[t]) { set_global_error(errs[t]); delete clm; return AHX_ERR_IO; }
-  for (auto &part : parts)
-    for (auto &pl : part) clm->apply_line(pl.ai, pl.bi, pl.ao, pl.bo, pl.g, pl.sumlog, pl.nlinks);
+  size_t nlines = 0;
+  for (auto &part : parts) nlines += part.size();
+  // the two maps are independent: one thread applies `contacts`, S threads one shard of `orientedContacts`
+  // each (every thread walks all lines in file order and keeps the keys of its shard)
+  const int S = std::max(1, std::min(nthreads - 1, 8));
+  clm->osh.assign(static_cast<size_t>(S), ahx_clm::OShard{});
+  {
+    std::vector<std::thread> ap;
+    ap.emplace_back([&] {
+      clm->cmap.reserve(nlines / 2 + 16); clm->contacts.reserve(nlines / 2 + 16);
+      for (auto &part : parts)
+        for (auto &pl : part) clm->apply_contact(pl.ai, pl.bi, pl.ao, pl.bo, pl.sumlog, pl.nlinks);
+    });
+    for (int sh = 0; sh < S; ++sh)
+      ap.emplace_back([&, sh] {
+        ahx_clm::OShard &o = clm->osh[sh];
+        o.map.reserve(2 * nlines / S + nlines / (4 * S) + 16); o.v.reserve(2 * nlines / S + nlines / (4 * S) + 16);
+        for (auto &part : parts)
+          for (auto &pl : part) {
+            clm->put_oriented(pl.ai, pl.bi, pl.ao, pl.bo, pl.g, sh);
+            clm->put_oriented(pl.bi, pl.ai, rr(pl.bo), rr(pl.ao), pl.g, sh);
+          }
+      });
+    for (auto &x : ap) x.join();
+  }
+  const auto t_apply = std::chrono::steady_clock::now();
   rc = ahx_clm_finalize(clm);
+  if (getenv("AHX_CLM_TIMING")) {
+    const auto t_fin = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "ahx_clm_parse: %.1f MB, %d threads: tokenise+log %.1f ms, apply %.1f ms, finalize %.1f ms\n", m.n / 1e6, nthreads,
+            ms(t_start, t_parse), ms(t_parse, t_apply), ms(t_apply, t_fin));
+  }
   if (rc != AHX_OK) { delete clm; return rc; }
   *out = clm;
   return AHX_OK;
@@ -297,13 +372,15 @@ int ahx_clm_finalize(ahx_clm *clm) {
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
   const size_t E = keys.size();
+  FlatMap rows;
+  rows.reserve(E);
+  for (size_t e = 0; e < E; ++e) { bool fresh; rows.insert(keys[e], static_cast<int64_t>(e), &fresh); }
   auto row_of = [&](int32_t a, int32_t b) -> int64_t {
-    const uint64_t k = pair_key(std::min(a, b), std::max(a, b));
-    auto it = std::lower_bound(keys.begin(), keys.end(), k);
-    return (it != keys.end() && *it == k) ? static_cast<int64_t>(it - keys.begin()) : -1;
+    const int64_t *r = rows.find(pair_key(std::min(a, b), std::max(a, b)));
+    return r ? *r : -1;
   };
   clm->pa.resize(E); clm->pb.resize(E); clm->nl.assign(E, 0); clm->strand.assign(E, 0);
-  clm->slots.assign(E * 8, -1); clm->hist.clear();
+  clm->slots.assign(E * 8, -1); clm->hist.clear(); { size_t no = 0; for (auto &sh : clm->osh) no += sh.v.size(); clm->hist.reserve(no * AHX_BB); }
   for (size_t e = 0; e < E; ++e) { clm->pa[e] = static_cast<int32_t>(keys[e] >> 32); clm->pb[e] = static_cast<int32_t>(keys[e] & 0xffffffffu); }
   // M(): P[ai][bi] = P[bi][ai] = nlinks per map entry (clm.go:440-445).  Go's map
   // order is random; when both (a,b) and (b,a) keys exist (never written by
@@ -315,16 +392,22 @@ int ahx_clm_finalize(ahx_clm *clm) {
     clm->nl[e] = static_cast<int32_t>(c.nlinks);
     clm->strand[e] = static_cast<int8_t>(c.strand);
   }
-  for (auto &o : clm->oriented) {
-    if (o.ai == o.bi) continue;                       // Q[a][a] is never read (i<j are distinct contigs)
-    const bool sa = o.ao == '-', sb = o.bo == '-';
-    if ((!sa && o.ao != '+') || (!sb && o.bo != '+')) continue;  // can never equal a Signs byte
-    const int64_t e = row_of(o.ai, o.bi);
-    if (e < 0) continue;
-    const int dir = o.ai < o.bi ? 0 : 1;
-    const int32_t h = static_cast<int32_t>(clm->hist.size() / AHX_BB);
-    clm->hist.insert(clm->hist.end(), o.g.begin(), o.g.end());
-    clm->slots[e * 8 + dir * 4 + 2 * (sa ? 1 : 0) + (sb ? 1 : 0)] = h;
+  // histograms in (row, slot) order, whatever the insertion order (and the sharding) was
+  std::vector<const ahx_clm::Oriented *> ref(E * 8, nullptr);
+  for (auto &sh : clm->osh)
+    for (auto &o : sh.v) {
+      if (o.ai == o.bi) continue;                       // Q[a][a] is never read (i<j are distinct contigs)
+      const bool sa = o.ao == '-', sb = o.bo == '-';
+      if ((!sa && o.ao != '+') || (!sb && o.bo != '+')) continue;  // can never equal a Signs byte
+      const int64_t e = row_of(o.ai, o.bi);
+      if (e < 0) continue;
+      const int dir = o.ai < o.bi ? 0 : 1;
+      ref[e * 8 + dir * 4 + 2 * (sa ? 1 : 0) + (sb ? 1 : 0)] = &o;
+    }
+  for (size_t i = 0; i < ref.size(); ++i) {
+    if (!ref[i]) continue;
+    clm->slots[i] = static_cast<int32_t>(clm->hist.size() / AHX_BB);
+    clm->hist.insert(clm->hist.end(), ref[i]->g.begin(), ref[i]->g.end());
   }
   clm->finalized = true;
   return AHX_OK;

@@ -546,10 +546,35 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
         // entries are byte offsets into X when N * 4T fits 16 bits (one instruction less per gather), else contig indices
         if (g.scaled) sweep(std::true_type{}); else sweep(std::false_type{});
       }
+      // warp totals of the T accumulators by a transposing butterfly: at the first log2(T) levels a lane
+      // keeps half of its tours and hands the other half to its partner, so T tours cost
+      // T - 1 + 5 - log2(T) exchanges instead of 5 T (fixed shape: deterministic)
+      if constexpr (T == 4) {
+        const bool b4 = lane & 16, b3 = lane & 8;
+        double k0 = b4 ? acc[2] : acc[0], k1 = b4 ? acc[3] : acc[1];
+        k0 += __shfl_xor_sync(0xffffffffu, b4 ? acc[0] : acc[2], 16);
+        k1 += __shfl_xor_sync(0xffffffffu, b4 ? acc[1] : acc[3], 16);
+        double s = b3 ? k1 : k0;
+        s += __shfl_xor_sync(0xffffffffu, b3 ? k0 : k1, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if ((lane & 7) == 0) m.partial[(buf * kRC + wid) * T + (lane >> 3)] = s;      // lanes 0, 8, 16, 24: tours 0..3
+      } else if constexpr (T == 2) {
+        const bool b4 = lane & 16;
+        double s = b4 ? acc[1] : acc[0];
+        s += __shfl_xor_sync(0xffffffffu, b4 ? acc[0] : acc[1], 16);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if ((lane & 15) == 0) m.partial[(buf * kRC + wid) * T + (lane >> 4)] = s;     // lanes 0, 16: tours 0, 1
+      } else {
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const double s = warp_sum(acc[t]);
-        if (lane == 0) m.partial[(buf * kRC + wid) * T + t] = s;
+        for (int t = 0; t < T; ++t) {
+          const double s = warp_sum(acc[t]);
+          if (lane == 0) m.partial[(buf * kRC + wid) * T + t] = s;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&m.done[buf]);

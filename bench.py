@@ -36,7 +36,7 @@ except Exception:
     pass
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the evaluate kernel, from the committed
 # ncu --set full capture of (workload, P) -- profiles/r1r_ncu_full_summary.txt
-NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64225024 + 642560}
+NCU_DRAM_BYTES_PER_LAUNCH = {("config3", 8000): 64223232 + 508160}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 

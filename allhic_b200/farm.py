@@ -47,6 +47,7 @@ def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir
                 if not order:
                     break
                 g = order.pop(0)
+                seq = len(groups) - len(order) - 1          # dispatch order: 0 = first group handed out
             refile, clmfile = groups[g]
             if proc is None or proc.poll() is not None:
                 proc = subprocess.Popen([binary, "optimize-many", "-", "--device", "0", *flags], stdin=subprocess.PIPE,
@@ -65,7 +66,7 @@ def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir
                 pass
             dt = time.perf_counter() - t0
             scores = re.findall(r"max_score=([0-9.eE+-]+)", "".join(out))
-            results[g] = dict(group=g, device=dev, seconds=dt, n_contigs=_count_contigs(refile),
+            results[g] = dict(group=g, device=dev, seq=seq, seconds=dt, n_contigs=_count_contigs(refile),
                               final_score=float(scores[-1]) if scores else None, ok=ok)
     finally:
         if proc is not None and proc.poll() is None:
@@ -80,7 +81,7 @@ def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir
 
 def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None, persistent=True):
     """groups: list of (refile, clmfile); devices: CUDA device indices to farm over.
-    Returns a list of dicts (group, device, seconds, final_score, n_contigs, ok) in input order."""
+    Returns a list of dicts (group, device, seq = dispatch order, seconds, final_score, n_contigs, ok) in input order."""
     order = sorted(range(len(groups)), key=lambda g: -_count_contigs(groups[g][0]) ** 2)
     lock = threading.Lock()
     results = [None] * len(groups)
@@ -99,6 +100,7 @@ def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None, pers
                 if not order:
                     return
                 g = order.pop(0)
+                seq = len(groups) - len(order) - 1
             refile, clmfile = groups[g]
             t0 = time.perf_counter()
             env = _device_env(dev)
@@ -109,7 +111,7 @@ def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None, pers
             if log_dir:
                 with open(os.path.join(log_dir, "group%02d.stderr" % g), "w") as f:
                     f.write(p.stderr)
-            results[g] = dict(group=g, device=dev, seconds=dt, n_contigs=_count_contigs(refile),
+            results[g] = dict(group=g, device=dev, seq=seq, seconds=dt, n_contigs=_count_contigs(refile),
                               final_score=float(scores[-1]) if scores else None,
                               ok=p.returncode == 0 and "Success" in p.stderr)
 

@@ -14,9 +14,14 @@ NCCL and over gloo in the CPU tests.
 `engine` only needs ga_begin / ga_advance / ga_get_elites / ga_put_migrants /
 ga_best / ga_end, so the protocol is testable on CPU with a stand-in engine.
 """
+import os
+import time
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+_TIMING = bool(os.environ.get("AHX_ISLAND_TIMING"))   # per-phase wall times of exchange() on stderr at close()
 
 
 def _device_for(group):
@@ -34,13 +39,16 @@ class IslandGA:
         self.params = params
         self.dev = _device_for(group)
         self.exchanges = 0
+        self._t = [0.0] * 4
         self.eng.ga_begin(np.ascontiguousarray(init_tour, np.int32), params)
 
     def exchange(self, stopped=0):
         """All-gather elites (and this island's EarlyStop flag, so the stop decision costs no second
         collective); replace this island's worst by everyone else's best.  Returns (fitness of all
         elites [world, n_elite], True when every island has stopped)."""
+        t0 = time.perf_counter()
         tours, fit = self.eng.ga_get_elites(self.n_elite)
+        t1 = time.perf_counter()
         payload = torch.empty(self.n_elite, self.L + 3, dtype=torch.int32)
         payload[:, : self.L] = torch.from_numpy(tours)
         payload[:, self.L:self.L + 2] = torch.from_numpy(fit.view(np.int32).reshape(self.n_elite, 2))   # f64 bits as 2 x int32
@@ -49,10 +57,13 @@ class IslandGA:
         gathered = torch.empty(self.world * self.n_elite, self.L + 3, dtype=torch.int32, device=self.dev)
         dist.all_gather_into_tensor(gathered, payload, group=self.group)
         g = gathered.cpu().numpy().reshape(self.world, self.n_elite, self.L + 3)
+        t2 = time.perf_counter()
         others = np.concatenate([g[r, :, : self.L] for r in range(self.world) if r != self.rank], axis=0) if self.world > 1 else None
         if others is not None and len(others):
             self.eng.ga_put_migrants(np.ascontiguousarray(others, np.int32))
         self.exchanges += 1
+        t3 = time.perf_counter()
+        self._t[0] += t1 - t0; self._t[1] += t2 - t1; self._t[2] += t3 - t2
         fits = np.ascontiguousarray(g[:, :, self.L:self.L + 2]).view(np.float64).reshape(self.world, self.n_elite)
         return fits, bool(np.all(g[:, 0, self.L + 2] != 0))
 
@@ -63,7 +74,9 @@ class IslandGA:
         done, st = 0, None
         while done < max_gens:
             n = min(self.migrate_every, max_gens - done)
+            t0 = time.perf_counter()
             st = self.eng.ga_advance(n)
+            self._t[3] += time.perf_counter() - t0
             done += n
             if self.world > 1:
                 fits, all_stopped = self.exchange(st.stopped)
@@ -85,6 +98,11 @@ class IslandGA:
         return t.cpu().numpy(), float(allbest[owner].item()), st
 
     def close(self):
+        if _TIMING and self.exchanges:
+            import sys
+            k = 1e3 / self.exchanges
+            print("island %d: %d exchanges, ms each: ga_advance %.3f  get_elites %.3f  copy+all_gather+copy %.3f  put_migrants %.3f"
+                  % (self.rank, self.exchanges, self._t[3] * k, self._t[0] * k, self._t[1] * k, self._t[2] * k), file=sys.stderr)
         self.eng.ga_end()
 
 

@@ -5,15 +5,15 @@
 // One CTA per SM (kRThreads = 768 threads, up to ~215 KB of shared memory):
 //   table   uint32[E_res]   nonzero pairs of M as the byte offsets of the two contigs in X,
 //                           (a*4T) | (b*4T) << 16 (N*4T < 64 KB whenever X fits), in the
-//                           bank-conflict-free order of order_pairs() for this T, padded
-//                           with (0, 1, nlinks 0) entries to a multiple of kRCT * kRUnroll
-//                           and stored so that a thread's 4 entries of an iteration are one
+//                           (nearly) bank-conflict-free order of order_pairs() for this T,
+//                           rounded up with (0, 1, nlinks 0) entries to a multiple of
+//                           kRCT * kRUnroll and stored so that a thread's 4 entries of an iteration are one
 //                           LDS.128; loaded ONCE per CTA by TMA bulk copies -- or, STREAM
 //                           mode, streamed for every batch through a ring of kRStages tiles
 //   nl8     uint8[E_res]    nlinks of the entry (a pair with more than 255 links is split
 //                           over several entries: sum_i n_i / d == n / d up to rounding)
 //   X[2]    uint32[N*T]     2*mid of contig c in tour t at X[c*T + t], double buffered
-//   sizes   uint32[N]       contig sizes, staged here when they fit (else read from global)
+//   sizes   uint32[N + 1]   contig sizes, staged here when they fit (else read from global); entry N = 0
 // Roles:
 //   8 producer warps  build X[buf] for batch k+1 (T tours: vector loads of the rows,
 //                     two-pass prefix sum of the sizes, scatter 2*cum+size to contig

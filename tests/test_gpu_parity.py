@@ -92,6 +92,28 @@ def test_eval_m_tours_per_cta(syn, T, path, monkeypatch):
     assert close(eng.eval_m(sub), orc.population_evaluate(sub.astype(np.int64), nthreads=4))
 
 
+@pytest.mark.parametrize("n", [2, 3, 9, 31, 32, 33, 65, 129, 250, 513, 1024])
+def test_eval_m_random_shapes(built_lib, tmp_path, n):
+    """Ragged shapes against the oracle: group sizes around the producers' group widths (8, 32 and 128
+    positions), populations that leave batches partly empty, sub-tours of arbitrary length, both index
+    widths, tours given in one call and row by row."""
+    import allhic_b200 as A
+    from allhic_b200 import synth
+    g = synth.generate(n, 9000 + n, pairs_per_contig=120 if n > 100 else 400, mean_size=40_000 if n > 300 else 100_000)
+    ids, clmf = synth.write(g, str(tmp_path / ("r%d" % n)))
+    clm = A.CLM(clmf, ids); eng = A.Engine(0); eng.load(clm); orc = O.OracleCLM(clmf, ids)
+    rng = np.random.default_rng(n)
+    for P in (1, 3, 4, 7, 150, 593):
+        for L in sorted({n, max(1, n - 1), max(1, n // 2), min(n, 5)}):
+            tours = np.stack([rng.permutation(n)[:L] for _ in range(P)]).astype(np.int32)
+            want = orc.population_evaluate(tours.astype(np.int64), nthreads=4)
+            got = eng.eval_m(tours)
+            assert close(got, want), (n, P, L)
+            assert close(eng.eval_m(tours.astype(np.uint16)), want), (n, P, L, "u16")
+            assert ((want == 0) == (got == 0)).all()                # an empty window sum is exactly 0, never -0 or 1e-52
+    eng.close()
+
+
 def test_eval_m_limit_window_and_subtours(syn):
     eng, clm, orc = syn
     n = clm.N

@@ -402,6 +402,27 @@ def test_ga_mutation_heavy_and_tiny_populations(fix):
         eng.ga_end()
 
 
+@pytest.mark.parametrize("n", [5, 33, 65, 129, 250])
+def test_ga_ragged_group_sizes(built_lib, tmp_path, n):
+    """The persistent GA kernel on group sizes that leave its 32/T-contig groups ragged, with small odd
+    populations: every individual stays consistent with its stored tour, the best matches the oracle."""
+    import allhic_b200 as A
+    from allhic_b200 import synth
+    g = synth.generate(n, 9100 + n, pairs_per_contig=400)
+    ids, clmf = synth.write(g, str(tmp_path / ("g%d" % n)))
+    clm = A.CLM(clmf, ids); eng = A.Engine(0); eng.load(clm); orc = O.OracleCLM(clmf, ids)
+    rng = np.random.default_rng(n)
+    for npop, mp in ((10, 0.5), (37, 0.2), (301, 0.9)):
+        init = rng.permutation(n).astype(np.int32)
+        eng.ga_begin(init, eng.ga_params(npop=npop, ngen=1 << 30, max_gens=1 << 40, seed=n + npop, mut_prob=mp))
+        st = eng.ga_advance(60)
+        assert st.generations == 60 and eng.ga_selfcheck() == 0, (n, npop)
+        best, score = eng.ga_best()
+        assert sorted(best.tolist()) == list(range(n)) and close(score, -orc.evaluate(best.astype(np.int64)))
+        eng.ga_end()
+    eng.close()
+
+
 def test_ga_large_population_stays_on_the_persistent_kernel(fix):
     """Populations beyond one mask word per thread (2P > 32 * 768) run the chunked block scans."""
     eng, clm, orc = fix

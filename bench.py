@@ -309,6 +309,7 @@ def main():
                             "fp64": "DFMA microbenchmark measured live by this run (ahx_probe_fp64; MEASURED_PEAKS.json has no fp64 figure)",
                             "hbm": "MEASURED_PEAKS.json hbm_gbs"}[bound],
             "kernel": {3: "eval_m_res_kernel (table streamed)", 2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[kind], "tours_per_batch": tpb,
+            "pair_table_entries": eng.pair_table_entries(tpb) if kind in (2, 3) else None,
             "algorithmic_per_tour": {"stored_pairs_E": E, "fp64_flop": flop_per_pair * E, "smem_gather_bytes": 8 * E,
                                      "in_window_pairs_E_act": e_act, "hbm_bytes": 4 * L + 8},
             "issue_model": {"issue_cycles_per_pair_term": 16.06, "note": "SASS of the consumer loop: 5 fp64 (2 issue cycles each, term_probe.cu) + 6.06 other instructions per (pair, tour); "

@@ -64,6 +64,10 @@ def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir
                     out.append(line)
             except (BrokenPipeError, OSError):
                 pass
+            if not ok:                                  # the worker died on this group (logFatal): start a fresh one for the next
+                proc.kill()
+                proc.wait()
+                proc = None
             dt = time.perf_counter() - t0
             scores = re.findall(r"max_score=([0-9.eE+-]+)", "".join(out))
             results[g] = dict(group=g, device=dev, seq=seq, seconds=dt, n_contigs=_count_contigs(refile),

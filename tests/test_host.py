@@ -175,3 +175,7 @@ fi
     assert all(c[1] in ("0", "1") for c in calls)                                        # each process sees one GPU
     if persistent:
         assert len({c[2] for c in calls}) <= 2                                           # one process per device, reused
+        # a worker that dies on a group fails that group only; the next group gets a fresh worker
+        fake.write_text(fake.read_text().replace('while read re clm; do', 'while read re clm; do case "$re" in *g2.ids) exit 3;; esac;'))
+        res = farm.optimize_groups(groups, devices=[0], binary=str(fake), persistent=True)
+        assert [r["ok"] for r in res] == [True, True, False, True]

@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libahx.so")
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_NODEVICE, ERR_IO = -1, -2, -3, -4, -5, -6
+ISLAND_HANDLE_BYTES = 64
 
 
 class AhxError(RuntimeError):
@@ -20,7 +21,8 @@ class AhxError(RuntimeError):
 class GAParams(C.Structure):
     _fields_ = [("npop", C.c_int32), ("ngen", C.c_int32), ("max_gens", C.c_int64), ("mut_prob", C.c_double),
                 ("seed", C.c_uint64), ("tournament_k", C.c_int32), ("log_every", C.c_int32), ("phase", C.c_int32),
-                ("island", C.c_int32)]
+                ("island", C.c_int32), ("n_islands", C.c_int32), ("migrate_every", C.c_int32), ("n_elite", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class GAStats(C.Structure):
@@ -38,6 +40,7 @@ SIGNATURES = {
     "ahx_version": (C.c_int, []),
     "ahx_last_error": (C.c_char_p, [_vp]),
     "ahx_clm_parse": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_vp)]),
+    "ahx_clm_parse_groups": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int32, C.c_int, C.POINTER(_vp)]),
     "ahx_clm_new": (C.c_int, [C.c_int32, _p64, C.POINTER(_vp)]),
     "ahx_clm_add_line": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint8, C.c_uint8, _p64, C.c_int64]),
     "ahx_clm_finalize": (C.c_int, [_vp]),
@@ -74,10 +77,18 @@ SIGNATURES = {
     "ahx_ga_best": (C.c_int, [_vp, _vp, _pd]),
     "ahx_ga_get_elites": (C.c_int, [_vp, C.c_int32, _vp, _vp]),
     "ahx_ga_put_migrants": (C.c_int, [_vp, C.c_int32, _vp]),
+    "ahx_ga_island_export": (C.c_int, [_vp, _vp]),
+    "ahx_ga_island_connect": (C.c_int, [_vp, _vp]),
+    "ahx_ga_island_connect_local": (C.c_int, [C.POINTER(_vp), C.c_int32]),
+    "ahx_ga_run_islands": (C.c_int, [C.POINTER(_vp), C.c_int32, C.POINTER(GAParams), C.c_int32, _vp, _vp, C.POINTER(GAStats), GA_CALLBACK, _vp]),
+    "ahx_ga_island_epochs": (C.c_int64, [_vp]),
     "ahx_ga_selfcheck": (C.c_int, [_vp, _p64]),
     "ahx_ga_kernel": (C.c_int, [_vp]),
     "ahx_ga_end": (C.c_int, [_vp]),
     "ahx_mutate": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "ahx_mutate_remap": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "ahx_test_plan_mutations": (C.c_int, [C.c_uint64, C.c_int32, C.c_int64, C.c_int32, C.c_double, C.c_int32, _vp]),
+    "ahx_test_tournaments": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
     "ahx_flip_whole": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _pd, _p32]),
     "ahx_flip_one": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _p64, _p64, _vp, _vp, _p32]),
     "ahx_flip_all": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _pd, _p32]),

@@ -24,6 +24,22 @@ class CLM:
         self._cache = None
 
     @classmethod
+    def parse_groups(cls, clmfile, refiles, nthreads=0):
+        """One pass over a genome-wide CLM for all of its groups (ahx_clm_parse_groups): a list of CLM,
+        each identical to CLM(clmfile, refiles[g])."""
+        l = _ffi.lib()
+        n = len(refiles)
+        arr = (C.c_char_p * n)(*[str(r).encode() for r in refiles])
+        out = (C.c_void_p * n)()
+        _ffi.check(l.ahx_clm_parse_groups(str(clmfile).encode(), arr, n, nthreads, out))
+        res = []
+        for g in range(n):
+            c = cls(_handle=C.c_void_p(out[g]))
+            c.Clmfile, c.REfile = clmfile, refiles[g]
+            res.append(c)
+        return res
+
+    @classmethod
     def from_sizes(cls, sizes):
         """Builder for callers with their own parser (ahx_clm_new + add_line)."""
         l = _ffi.lib()

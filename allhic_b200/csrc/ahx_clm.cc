@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -198,9 +199,14 @@ inline int64_t atoi_or_zero(const char *s, size_t n) {
 struct ParsedLine { int32_t ai, bi; uint8_t ao, bo; std::array<int32_t, AHX_BB> g; double sumlog; int64_t nlinks; };
 
 // Parses lines of [beg,end) (beg at a line start).  Returns false on a line the
-// reference would panic on.
-bool parse_chunk(const ahx_clm &clm, const char *buf, size_t beg, size_t end, size_t total,
-                 std::vector<ParsedLine> *out, std::string *err) {
+// reference would panic on.  resolve(name_a, name_b, hits) lists the (group, ai, bi) that keep
+// the line -- both contigs in that group's REfile, clm.go:211-218; the line's distances are
+// tokenised and histogrammed once, whatever the number of groups.
+struct Hit { int32_t group, ai, bi; };
+template <typename Resolve>
+bool parse_chunk(const Resolve &resolve, const char *buf, size_t beg, size_t end, size_t total,
+                 std::vector<std::vector<ParsedLine>> *out, std::string *err) {
+  std::vector<Hit> hits;
   std::vector<int64_t> dists;
   size_t p = beg;
   while (p < end) {
@@ -223,10 +229,9 @@ bool parse_chunk(const ahx_clm &clm, const char *buf, size_t beg, size_t end, si
     ParsedLine pl;
     pl.ao = static_cast<uint8_t>(buf[s1 - 1]);
     pl.bo = static_cast<uint8_t>(buf[s2 - 1]);
-    auto ia = clm.tig2idx.find(std::string(buf + a, s1 - 1 - a));
-    auto ib = clm.tig2idx.find(std::string(buf + s1 + 1, s2 - 1 - (s1 + 1)));
-    if (ia != clm.tig2idx.end() && ib != clm.tig2idx.end()) {              // clm.go:211-218
-      pl.ai = ia->second; pl.bi = ib->second;
+    hits.clear();
+    resolve(std::string(buf + a, s1 - 1 - a), std::string(buf + s1 + 1, s2 - 1 - (s1 + 1)), &hits);
+    if (!hits.empty()) {                                                   // clm.go:211-218
       size_t q = t2 + 1, wend = q;
       while (wend < b && buf[wend] != '\t') ++wend;
       dists.clear();
@@ -239,7 +244,7 @@ bool parse_chunk(const ahx_clm &clm, const char *buf, size_t beg, size_t end, si
       }
       pl.nlinks = static_cast<int64_t>(dists.size());                      // len(line.links), clm.go:228
       golden_and_sumlog(dists.data(), pl.nlinks, pl.g.data(), &pl.sumlog);
-      out->push_back(pl);
+      for (const Hit &h : hits) { pl.ai = h.ai; pl.bi = h.bi; (*out)[h.group].push_back(pl); }
     }
     p = next;
   }
@@ -277,15 +282,23 @@ int read_re(ahx_clm *clm, const char *refile) {                           // clm
 
 extern "C" {
 
-int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm **out) {
-  if (!clmfile || !refile || !out) { set_global_error("ahx_clm_parse: null argument"); return AHX_ERR_ARG; }
-  auto *clm = new ahx_clm();
-  int rc = read_re(clm, refile);
-  if (rc != AHX_OK) { delete clm; return rc; }
+// One pass over the CLM text for any number of groups: threads tokenise chunks of the file (names
+// resolved against every group's REfile, GoldenArray / SumLog once per kept line), then every group's
+// two maps are filled in file order -- "smallest SumLog wins" / "last line wins" exactly like the
+// single-threaded Go loop (clm.go:221-238) run on that group alone.
+static int parse_groups(const char *clmfile, const char *const *refiles, int32_t n_groups, int nthreads, ahx_clm **out) {
+  std::vector<ahx_clm *> clms(n_groups, nullptr);
+  auto drop = [&] { for (auto *c : clms) delete c; };
+  for (int32_t g = 0; g < n_groups; ++g) {
+    clms[g] = new ahx_clm();
+    const int rc = read_re(clms[g], refiles[g]);
+    if (rc != AHX_OK) { drop(); return rc; }
+  }
   Mapped m;
-  if (!m.open(clmfile)) { set_global_error(std::string("cannot open clmfile `") + clmfile + "`"); delete clm; return AHX_ERR_IO; }
+  if (!m.open(clmfile)) { set_global_error(std::string("cannot open clmfile `") + clmfile + "`"); drop(); return AHX_ERR_IO; }
   const auto t_start = std::chrono::steady_clock::now();
   if (nthreads <= 0) nthreads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+  const int napply = nthreads;
   nthreads = static_cast<int>(std::min<size_t>(static_cast<size_t>(nthreads), m.n / (1 << 16) + 1));
   std::vector<size_t> cut(nthreads + 1);
   cut[0] = 0; cut[nthreads] = m.n;
@@ -294,52 +307,115 @@ int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm
     while (c < m.n && m.p[c] != '\n') ++c;
     cut[t] = std::min(m.n, c + 1);
   }
-  std::vector<std::vector<ParsedLine>> parts(nthreads);
+  // contig name -> every (group, index) that lists it (a partition lists a contig once; overlapping REfiles still work)
+  std::unordered_map<std::string, std::vector<std::pair<int32_t, int32_t>>> where;
+  if (n_groups > 1)
+    for (int32_t g = 0; g < n_groups; ++g)
+      for (auto &kv : clms[g]->tig2idx) where[kv.first].emplace_back(g, kv.second);
+  auto resolve1 = [&](const std::string &a, const std::string &b, std::vector<Hit> *hits) {
+    const auto &idx = clms[0]->tig2idx;
+    auto ia = idx.find(a);
+    if (ia == idx.end()) return;
+    auto ib = idx.find(b);
+    if (ib != idx.end()) hits->push_back({0, ia->second, ib->second});
+  };
+  auto resolveN = [&](const std::string &a, const std::string &b, std::vector<Hit> *hits) {
+    auto ia = where.find(a);
+    if (ia == where.end()) return;
+    auto ib = where.find(b);
+    if (ib == where.end()) return;
+    for (auto &x : ia->second)
+      for (auto &y : ib->second) if (x.first == y.first) hits->push_back({x.first, x.second, y.second});
+  };
+  std::vector<std::vector<std::vector<ParsedLine>>> parts(nthreads, std::vector<std::vector<ParsedLine>>(n_groups));   // [chunk][group]
   std::vector<std::string> errs(nthreads);
   std::vector<char> ok(nthreads, 1);
-  std::vector<std::thread> th;
-  for (int t = 0; t < nthreads; ++t)
-    th.emplace_back([&, t] { ok[t] = parse_chunk(*clm, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t]); });
-  for (auto &x : th) x.join();
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        ok[t] = n_groups == 1 ? parse_chunk(resolve1, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t])
+                              : parse_chunk(resolveN, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t]);
+      });
+    for (auto &x : th) x.join();
+  }
   const auto t_parse = std::chrono::steady_clock::now();
   for (int t = 0; t < nthreads; ++t)
-    if (!ok[t]) { set_global_error(errs[t]); delete clm; return AHX_ERR_IO; }
-  size_t nlines = 0;
-  for (auto &part : parts) nlines += part.size();
-  // the two maps are independent: one thread applies `contacts`, S threads one shard of `orientedContacts`
-  // each (every thread walks all lines in file order and keeps the keys of its shard)
-  const int S = std::max(1, std::min(nthreads - 1, 8));
-  clm->osh.assign(static_cast<size_t>(S), ahx_clm::OShard{});
-  {
+    if (!ok[t]) { set_global_error(errs[t]); drop(); return AHX_ERR_IO; }
+  // the two maps of a group are independent: one thread applies `contacts`, S threads one shard of
+  // `orientedContacts` each (every thread walks the group's lines in file order and keeps its shard's keys);
+  // several groups: the groups are spread over the threads instead, one shard each
+  std::vector<int> rcs(n_groups, AHX_OK);
+  std::vector<std::string> ferr(n_groups);
+  auto apply_group = [&](int32_t g, int S) {
+    ahx_clm *clm = clms[g];
+    size_t nlines = 0;
+    for (auto &part : parts) nlines += part[g].size();
+    clm->osh.assign(static_cast<size_t>(S), ahx_clm::OShard{});
     std::vector<std::thread> ap;
-    ap.emplace_back([&] {
+    auto contacts = [&, clm, nlines] {
       clm->cmap.reserve(nlines / 2 + 16); clm->contacts.reserve(nlines / 2 + 16);
       for (auto &part : parts)
-        for (auto &pl : part) clm->apply_contact(pl.ai, pl.bi, pl.ao, pl.bo, pl.sumlog, pl.nlinks);
-    });
-    for (int sh = 0; sh < S; ++sh)
-      ap.emplace_back([&, sh] {
-        ahx_clm::OShard &o = clm->osh[sh];
-        o.map.reserve(2 * nlines / S + nlines / (4 * S) + 16); o.v.reserve(2 * nlines / S + nlines / (4 * S) + 16);
-        for (auto &part : parts)
-          for (auto &pl : part) {
-            clm->put_oriented(pl.ai, pl.bi, pl.ao, pl.bo, pl.g, sh);
-            clm->put_oriented(pl.bi, pl.ai, rr(pl.bo), rr(pl.ao), pl.g, sh);
-          }
+        for (auto &pl : part[g]) clm->apply_contact(pl.ai, pl.bi, pl.ao, pl.bo, pl.sumlog, pl.nlinks);
+    };
+    auto shard = [&, clm, nlines, S](int sh) {
+      ahx_clm::OShard &o = clm->osh[sh];
+      o.map.reserve(2 * nlines / S + nlines / (4 * S) + 16); o.v.reserve(2 * nlines / S + nlines / (4 * S) + 16);
+      for (auto &part : parts)
+        for (auto &pl : part[g]) {
+          clm->put_oriented(pl.ai, pl.bi, pl.ao, pl.bo, pl.g, sh);
+          clm->put_oriented(pl.bi, pl.ai, rr(pl.bo), rr(pl.ao), pl.g, sh);
+        }
+    };
+    if (S == 1) { contacts(); shard(0); }
+    else {
+      ap.emplace_back(contacts);
+      for (int sh = 0; sh < S; ++sh) ap.emplace_back(shard, sh);
+      for (auto &x : ap) x.join();
+    }
+  };
+  std::chrono::steady_clock::time_point t_apply;
+  if (n_groups == 1) {
+    apply_group(0, std::max(1, std::min(napply - 1, 8)));
+    t_apply = std::chrono::steady_clock::now();
+    rcs[0] = ahx_clm_finalize(clms[0]);
+    if (rcs[0] != AHX_OK) ferr[0] = global_error();
+  } else {
+    std::vector<std::thread> gt;
+    std::atomic<int32_t> next{0};
+    for (int t = 0; t < std::min<int>(napply, n_groups); ++t)
+      gt.emplace_back([&] {
+        for (int32_t g = next++; g < n_groups; g = next++) {
+          apply_group(g, 1);
+          for (auto &part : parts) std::vector<ParsedLine>().swap(part[g]);
+          rcs[g] = ahx_clm_finalize(clms[g]);
+          if (rcs[g] != AHX_OK) ferr[g] = global_error();
+        }
       });
-    for (auto &x : ap) x.join();
+    for (auto &x : gt) x.join();
+    t_apply = std::chrono::steady_clock::now();
   }
-  const auto t_apply = std::chrono::steady_clock::now();
-  rc = ahx_clm_finalize(clm);
   if (getenv("AHX_CLM_TIMING")) {
     const auto t_fin = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    fprintf(stderr, "ahx_clm_parse: %.1f MB, %d threads: tokenise+log %.1f ms, apply %.1f ms, finalize %.1f ms\n", m.n / 1e6, nthreads,
+    fprintf(stderr, "ahx_clm_parse: %.1f MB, %d group(s), %d threads: tokenise+log %.1f ms, apply %.1f ms, finalize %.1f ms\n", m.n / 1e6, n_groups, nthreads,
             ms(t_start, t_parse), ms(t_parse, t_apply), ms(t_apply, t_fin));
   }
-  if (rc != AHX_OK) { delete clm; return rc; }
-  *out = clm;
+  for (int32_t g = 0; g < n_groups; ++g)
+    if (rcs[g] != AHX_OK) { set_global_error(ferr[g]); drop(); return rcs[g]; }
+  for (int32_t g = 0; g < n_groups; ++g) out[g] = clms[g];
   return AHX_OK;
+}
+
+int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm **out) {
+  if (!clmfile || !refile || !out) { set_global_error("ahx_clm_parse: null argument"); return AHX_ERR_ARG; }
+  return parse_groups(clmfile, &refile, 1, nthreads, out);
+}
+
+int ahx_clm_parse_groups(const char *clmfile, const char *const *refiles, int32_t n_groups, int nthreads, ahx_clm **out) {
+  if (!clmfile || !refiles || !out || n_groups < 1) { set_global_error("ahx_clm_parse_groups: bad argument"); return AHX_ERR_ARG; }
+  for (int32_t g = 0; g < n_groups; ++g) if (!refiles[g]) { set_global_error("ahx_clm_parse_groups: null REfile"); return AHX_ERR_ARG; }
+  return parse_groups(clmfile, refiles, n_groups, nthreads, out);
 }
 
 int ahx_clm_new(int32_t n_tigs, const int64_t *sizes, ahx_clm **out) {

@@ -739,7 +739,8 @@ int ahx_create(int device, ahx_ctx **out) {
   ctx->l2_bytes = static_cast<size_t>(prop.l2CacheSize);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess) {
+      (e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess ||
+      (e = cudaHostAlloc(&ctx->h_pin, 4096, cudaHostAllocDefault)) != cudaSuccess) {
     int rc = cuda_fail(nullptr, e, "ahx_create");
     delete ctx;
     return rc;
@@ -756,7 +757,11 @@ int ahx_create(int device, ahx_ctx **out) {
 void ahx_destroy(ahx_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);          // this context's work only: other contexts of the process keep running
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  for (auto &kv : ctx->isl_opened) cudaIpcCloseMemHandle(kv.second);
+  ctx->d_mbox.release(); ctx->d_isl.release();
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); for (auto &b : ctx->d_rpairs) b.release(); for (auto &b : ctx->d_rraw) b.release(); for (auto &b : ctx->d_rnl8) b.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();
   ctx->d_tours.release(); ctx->d_res_tours.release(); ctx->d_res_scores.release(); ctx->d_tours16.release(); ctx->d_scores.release(); ctx->d_signs.release(); ctx->d_xglobal.release();

@@ -40,6 +40,33 @@ struct GaState {
   int pad;
 };
 
+// Island model (include/ahx.h "Islands"): what the persistent GA kernel needs to reach the
+// other islands.  Lives in device memory; mbox[i] is island i's mailbox as mapped into THIS
+// device's address space (peer access in one process, CUDA IPC across processes).
+constexpr int kMaxIslands = 32;
+struct GaIslands {
+  unsigned char *mbox[kMaxIslands];
+  double g_best;                 // best fitness over all islands as of the last exchange
+  long long g_updated;           // generation (an exchange point) at which g_best last improved
+  unsigned long long epochs;     // exchanges completed
+  long long timeout_ns;          // how long an island waits for its peers before giving up
+  int err;                       // 1: a peer did not show up in time
+  int pad;
+  // decisions of an exchange, written by CTA 0 and read by every CTA after the grid barrier
+  double x_hof_fit; long long x_updated; int x_stop; int x_pad;
+};
+// Mailbox layout: one flag per source island (32 bytes apart), then [source][parity] slots of
+//   double hof_fit; double fit[n_elite] (padded to 16 B); int tour[n_elite][L]; uint32 X[n_elite][N]
+__host__ __device__ inline size_t isl_align16(size_t x) { return (x + 15) & ~static_cast<size_t>(15); }
+__host__ __device__ inline size_t isl_flags_bytes(int W) { return (32 * static_cast<size_t>(W) + 127) & ~static_cast<size_t>(127); }
+__host__ __device__ inline size_t isl_head_bytes(int n_elite) { return isl_align16(8 + 8 * static_cast<size_t>(n_elite)); }
+__host__ __device__ inline size_t isl_slot_bytes(int n_elite, int L, int N) {
+  return isl_head_bytes(n_elite) + isl_align16(4 * static_cast<size_t>(n_elite) * (static_cast<size_t>(L) + N));
+}
+__host__ __device__ inline size_t isl_mbox_bytes(int W, int n_elite, int L, int N) {
+  return isl_flags_bytes(W) + 2 * static_cast<size_t>(W) * isl_slot_bytes(n_elite, L, N);
+}
+
 }  // namespace ahx
 
 struct ahx_ctx {
@@ -48,6 +75,10 @@ struct ahx_ctx {
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
   std::vector<cudaEvent_t> chunk_ev;
   std::string err;
+  // 4 KB of pinned host memory for small read-backs: a copy to pageable memory keeps the calling thread
+  // inside the driver until the stream reaches it, which stalls other threads' launches on this device
+  // (islands of one process wait for each other's kernels)
+  void *h_pin = nullptr;
   int sm_count = 0;
   size_t smem_optin = 0, l2_bytes = 0;
   int64_t launches = 0;
@@ -115,6 +146,11 @@ struct ahx_ctx {
   ahx::DevBuf<unsigned long long> d_gmin;
   ahx::DevBuf<uint32_t> d_gmask;              // mutation masks of two generations
   ahx::DevBuf<uint32_t> d_xpool;              // coordinate row of every pool row
+  // islands: own mailbox, the table of peer mailboxes, IPC mappings opened so far (handle bytes -> pointer)
+  ahx::DevBuf<unsigned char> d_mbox;
+  ahx::DevBuf<ahx::GaIslands> d_isl;
+  bool isl_connected = false;
+  std::vector<std::pair<std::string, void *>> isl_opened;
   std::vector<int32_t> ga_active_set;  // sorted contig ids of the initial tour
   double ga_ms = 0.0;
 

@@ -495,7 +495,7 @@ __global__ void scatter_rows_kernel(int *__restrict__ pop, const int *__restrict
 }
 // After migrants were written and scored: refresh the hall of fame from fit[0..P).
 __global__ void __launch_bounds__(1024) hof_refresh_kernel(const double *__restrict__ fit, const int *__restrict__ pop, const int *__restrict__ rowof,
-                                                           int P, int L, int *hof, GaState *st, int n_new_evals) {
+                                                           int P, int L, int *hof, GaState *st, int n_new_evals, long long max_gens) {
   __shared__ double sf[32];
   __shared__ int si[32];
   __shared__ int s_best, s_improved;
@@ -515,7 +515,8 @@ __global__ void __launch_bounds__(1024) hof_refresh_kernel(const double *__restr
       if (sf[w] < bf || (sf[w] == bf && si[w] < bi)) { bf = sf[w]; bi = si[w]; }
     s_best = bi; s_improved = bf < st->hof_fit;
     st->evals += n_new_evals;
-    if (s_improved) { st->hof_fit = bf; st->updated = st->gen; st->stop = 0; }
+    // an improvement restarts EarlyStop's patience (evaluate.go:304-306) -- but not a run that ended on max_gens
+    if (s_improved) { st->hof_fit = bf; st->updated = st->gen; if (st->gen < max_gens) st->stop = 0; }
   }
   __syncthreads();
   if (s_improved) {
@@ -528,15 +529,37 @@ __global__ void mutate_kernel(const int *__restrict__ in, int L, int op, int p, 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) out[i] = in[mut_source(op, p, q, dir, L, i)];
 }
 
+// SplitMix-style whitening of (seed, island) into the Philox key
+static Philox philox_key(uint64_t seed, int32_t island) {
+  uint64_t z = seed + 0x9e3779b97f4a7c15ULL * (static_cast<uint64_t>(static_cast<uint32_t>(island)) + 1);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
+  return Philox{static_cast<uint32_t>(z), static_cast<uint32_t>(z >> 32)};
+}
+
+// ---- test hooks: the product kernels' operator code and random decisions on their own -------
+// One mutation through remap_of + slot_source / slot_coord (what ga_persist_kernel runs).
+__global__ void mutate_remap_kernel(const int *__restrict__ pt, const uint32_t *__restrict__ px, const uint32_t *__restrict__ s32, uint32_t total2,
+                                    int L, int N, MutPlan mp, int *__restrict__ ct, uint32_t *__restrict__ cx) {
+  __shared__ GaSlot s;
+  if (threadIdx.x == 0) { s.o = 0; s.parent_row = 0; s.child_row = 0; remap_of(mp, L, pt, px, s32, total2, &s); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) ct[i] = pt[slot_source(s, i, L)];
+  for (int c = threadIdx.x; c < N; c += blockDim.x) cx[c] = L < N ? slot_coord<true>(s, c, px[c]) : slot_coord<false>(s, c, px[c]);
+}
+// winners[2 * pair + which] = tournament_pair(...) for pairs 0 .. n_pairs-1 of generation gen
+__global__ void tournaments_kernel(const double *__restrict__ fit, int P, int k, Philox ph, long long gen, int n_pairs, int *__restrict__ winners) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * n_pairs)
+    winners[i] = tournament_pair(fit, P, k, ph, static_cast<uint32_t>(gen), static_cast<uint32_t>(gen >> 32), static_cast<uint32_t>(i >> 1), i & 1);
+}
+
 static GaDev make_dev(ahx_ctx *ctx) {
   GaDev g{};
   const ahx_ga_params &p = ctx->ga_prm;
   g.P = p.npop; g.L = ctx->ga_L; g.N = ctx->N; g.E = static_cast<int>(ctx->E); g.k = p.tournament_k;
   g.mut_prob = p.mut_prob;
-  // SplitMix-style whitening of (seed, island) into the Philox key
-  uint64_t z = p.seed + 0x9e3779b97f4a7c15ULL * (static_cast<uint64_t>(static_cast<uint32_t>(p.island)) + 1);
-  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
-  g.key0 = static_cast<uint32_t>(z); g.key1 = static_cast<uint32_t>(z >> 32);
+  const Philox key = philox_key(p.seed, p.island);
+  g.key0 = key.k0; g.key1 = key.k1;
   g.ngen = p.ngen; g.max_gens = p.max_gens;
   g.sizes = ctx->d_sizes.p;
   g.coo = ctx->coo16 ? static_cast<const void *>(ctx->d_coo16.p) : static_cast<const void *>(ctx->d_coo32.p);
@@ -589,7 +612,7 @@ static std::vector<uint32_t> tour_coordinates(const ahx_ctx *ctx, int32_t L, con
 static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double mut_prob) {
   GaResCfg c;
   if (const char *env = getenv("AHX_GA_RES")) if (!atoi(env)) return c;
-  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res[0] <= 0 || L != ctx->N) return c;
+  if (!ctx->x32_ok || !ctx->coo16 || ctx->E_res[0] <= 0 || L > ctx->N) return c;
   const double expect = std::max(1.0, P * mut_prob);
   const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
   const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
@@ -629,6 +652,8 @@ __global__ void ga_res_init_kernel(GaRes q, const int *__restrict__ init, const 
       s.stop = (q.max_gens <= 0 || 0 - s.updated > q.ngen) ? 1 : 0;
       s.ticket = 0; s.best_idx = 0;
       *q.st = s;
+      q.isl->g_best = f0[0]; q.isl->g_updated = 0; q.isl->epochs = 0; q.isl->err = 0;
+      q.isl->x_hof_fit = f0[0]; q.isl->x_updated = 0; q.isl->x_stop = s.stop;
     }
   }
 }
@@ -639,17 +664,20 @@ static GaRes make_res(ahx_ctx *ctx) {
   q.P = d.P; q.L = d.L; q.k = d.k; q.nbmax = ctx->ga_nbmax;
   q.mut_prob = d.mut_prob; q.key0 = d.key0; q.key1 = d.key1; q.ngen = d.ngen; q.max_gens = d.max_gens;
   q.xpool = ctx->d_xpool.p; q.sizes32 = ctx->d_sizes32.p;
-  { long long tot = 0; for (int64_t z : ctx->h_sizes) tot += z; q.total2 = static_cast<uint32_t>(2 * tot); }
+  { long long tot = 0; for (int32_t c : ctx->ga_active_set) tot += ctx->h_sizes[c]; q.total2 = static_cast<uint32_t>(2 * tot); }
   q.pool = ctx->d_pop[0].p; q.rowof[0] = ctx->d_rowof[0].p; q.rowof[1] = ctx->d_rowof[1].p;
   q.fit[0] = ctx->d_fit[0].p; q.fit[1] = ctx->d_fit[1].p; q.hof = ctx->d_hof.p; q.st = ctx->d_state.p;
   q.gbar = ctx->d_gbar.p;
   q.used = ctx->d_used.p; q.gmin = ctx->d_gmin.p; q.gmask = ctx->d_gmask.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
+  const ahx_ga_params &p = ctx->ga_prm;
+  q.n_islands = p.n_islands > 1 ? p.n_islands : 1; q.island = p.island; q.migrate_every = p.migrate_every; q.n_elite = p.n_elite;
+  q.isl = ctx->d_isl.p;
   return q;
 }
 
-template <int T, bool STREAM>
-static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
-  auto kern = ga_persist_kernel<T, STREAM>;
+template <int T, bool STREAM, bool SUB>
+static cudaError_t launch_persist_ts(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
+  auto kern = ga_persist_kernel<T, STREAM, SUB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->ga_smem));
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
@@ -658,6 +686,11 @@ static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t
   GaRes q = make_res(ctx);
   void *args[] = {&g, &q, &n_gens};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(ctx->ga_G), dim3(kRThreads), args, ctx->ga_smem, s);
+}
+
+template <int T, bool STREAM>
+static cudaError_t launch_persist_t(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
+  return ctx->ga_L < ctx->N ? launch_persist_ts<T, STREAM, true>(ctx, n_gens, s) : launch_persist_ts<T, STREAM, false>(ctx, n_gens, s);
 }
 
 static int launch_persist(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
@@ -721,8 +754,18 @@ static int launch_generation(ahx_ctx *ctx, const GaDev &g, cudaStream_t s) {
 }
 
 static int read_state(ahx_ctx *ctx, GaState *hs) {
-  AHX_CUDA(ctx, cudaMemcpyAsync(hs, ctx->d_state.p, sizeof(GaState), cudaMemcpyDeviceToHost, ctx->stream));
+  static_assert(sizeof(GaState) + sizeof(GaIslands) <= 4096, "pinned scratch");
+  AHX_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, ctx->d_state.p, sizeof(GaState), cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(hs, ctx->h_pin, sizeof(GaState));
+  return AHX_OK;
+}
+// island bookkeeping of the active run (after the stream has drained)
+static int read_islands(ahx_ctx *ctx, GaIslands *h) {
+  void *pin = static_cast<unsigned char *>(ctx->h_pin) + sizeof(GaState);
+  AHX_CUDA(ctx, cudaMemcpyAsync(pin, ctx->d_isl.p, sizeof(GaIslands), cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(h, pin, sizeof(GaIslands));
   return AHX_OK;
 }
 
@@ -754,6 +797,10 @@ void ahx_ga_default_params(ahx_ga_params *p) {
   p->log_every = 500;     // evaluate.go:294
   p->phase = 1;
   p->island = 0;
+  p->n_islands = 1;       // evaluate.go:269 ga.NPops
+  p->migrate_every = 50;
+  p->n_elite = 2;
+  p->reserved = 0;
 }
 
 int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_t *init_tour) {
@@ -768,13 +815,38 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   if (prm->npop < 2 || prm->npop - 2 < prm->tournament_k - 1) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: npop too small for 2 tournaments of k contestants");
   if (!(prm->mut_prob >= 0.0 && prm->mut_prob <= 1.0) || prm->ngen < 0 || prm->max_gens < 0 || prm->log_every < 0)
     return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: bad parameter");
+  const int W = prm->n_islands > 1 ? prm->n_islands : 1;
+  if (W > 1) {
+    const long long m = static_cast<long long>(prm->n_elite) * (W - 1);
+    if (W > kMaxIslands || prm->island < 0 || prm->island >= W || prm->migrate_every < 1 || prm->n_elite < 1 || m > kIslMaxMigrants || 2 * m > prm->npop)
+      return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: bad island parameters (need 0 <= island < n_islands <= 32, migrate_every >= 1, 1 <= n_elite, n_elite * (n_islands - 1) <= min(64, npop / 2))");
+  }
   ctx->ga_prm = *prm; ctx->ga_L = L;
+  ctx->isl_connected = false;
   {
     const GaResCfg rc = ga_res_config(ctx, prm->npop, L, prm->mut_prob);
     ctx->ga_res = rc.T > 0;
     if (ctx->ga_res) { ctx->ga_T = rc.T; ctx->ga_G = rc.G; ctx->ga_nbmax = rc.nbmax; ctx->ga_smem = rc.smem; ctx->ga_stream = rc.stream; }
   }
+  if (W > 1 && !ctx->ga_res)
+    return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: the in-kernel island exchange needs the persistent GA kernel (full tour, 32-bit coordinates, 16-bit contig indices); "
+                                  "use ahx_ga_get_elites / ahx_ga_put_migrants for a host-mediated exchange on this group");
   if (ctx->ga_res) {
+    AHX_CUDA(ctx, ctx->d_isl.reserve(1));
+    {
+      GaIslands h{};
+      long long ms = 20000;
+      if (const char *env = getenv("AHX_ISLAND_TIMEOUT_MS")) { const long long v = atoll(env); if (v > 0) ms = v; }
+      h.timeout_ns = ms * 1000000LL;
+      if (W > 1) {
+        const size_t mb = isl_mbox_bytes(W, prm->n_elite, L, ctx->N);
+        AHX_CUDA(ctx, ctx->d_mbox.reserve(mb));
+        AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_mbox.p, 0, mb, ctx->stream));
+        h.mbox[prm->island] = ctx->d_mbox.p;
+      }
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_isl.p, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+      AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h is stack-owned
+    }
     const size_t PL2 = 2 * static_cast<size_t>(prm->npop) * L;
     AHX_CUDA(ctx, ctx->d_pop[0].reserve(PL2));
     for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); AHX_CUDA(ctx, ctx->d_rowof[i].reserve(prm->npop)); }
@@ -829,24 +901,48 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   return AHX_OK;
 }
 
+// One launch of the persistent kernel for up to `batch` generations, asynchronous; persist_finish waits for it,
+// reads the state back and accounts the time.  Split so that ahx_ga_run_islands can have all islands' kernels
+// in flight before it waits for any of them (they wait for each other at the exchange points).
+static int persist_start(ahx_ctx *ctx, int64_t batch) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+  if ((rc = launch_persist(ctx, batch, ctx->stream)) != AHX_OK) return rc;
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  return AHX_OK;
+}
+static int persist_finish(ahx_ctx *ctx, GaState *hs) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if ((rc = read_state(ctx, hs)) != AHX_OK) return rc;
+  float ms = 0.f;
+  AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  ctx->ga_ms += ms;
+  if (ctx->ga_prm.n_islands > 1) {
+    GaIslands h{};
+    if ((rc = read_islands(ctx, &h)) != AHX_OK) return rc;
+    if (h.err) return fail(ctx, AHX_ERR_STATE, "island exchange timed out: a peer island did not reach the exchange point (AHX_ISLAND_TIMEOUT_MS)");
+  }
+  return AHX_OK;
+}
+constexpr int64_t kPersistChunk = 8192;   // generations per launch; the kernel leaves its loop by itself when EarlyStop fires
+
 int ahx_ga_advance(ahx_ctx *ctx, int64_t n_gens, ahx_ga_stats *stats) {
   int rc = enter(ctx, true);
   if (rc != AHX_OK) return rc;
   if (!ctx->ga_active) return fail(ctx, AHX_ERR_STATE, "ahx_ga_advance: no active GA run");
   if (n_gens < 0) return fail(ctx, AHX_ERR_ARG, "ahx_ga_advance: negative n_gens");
+  if (ctx->ga_prm.n_islands > 1 && !ctx->isl_connected && n_gens > 0)
+    return fail(ctx, AHX_ERR_STATE, "ahx_ga_advance: islands are not connected (ahx_ga_island_connect / _connect_local)");
   const GaDev g = make_dev(ctx);
   GaState hs{};
   if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
   int64_t left = n_gens;
   while (ctx->ga_res && left > 0 && !hs.stop) {
-    const int64_t batch = std::min<int64_t>(left, 8192);  // the kernel leaves its generation loop by itself when EarlyStop fires
-    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-    if ((rc = launch_persist(ctx, batch, ctx->stream)) != AHX_OK) return rc;
-    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-    if ((rc = read_state(ctx, &hs)) != AHX_OK) return rc;
-    float ms = 0.f;
-    AHX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
-    ctx->ga_ms += ms;
+    const int64_t batch = std::min<int64_t>(left, kPersistChunk);
+    if ((rc = persist_start(ctx, batch)) != AHX_OK) return rc;
+    if ((rc = persist_finish(ctx, &hs)) != AHX_OK) return rc;
     left -= batch;
   }
   while (!ctx->ga_res && left > 0 && !hs.stop) {
@@ -863,6 +959,92 @@ int ahx_ga_advance(ahx_ctx *ctx, int64_t n_gens, ahx_ga_stats *stats) {
   }
   fill_stats(ctx, hs, stats);
   return AHX_OK;
+}
+
+// ---- islands: wiring (include/ahx.h "Islands") ------------------------------------------
+static int island_table(ahx_ctx *ctx, void *const *mbox) {
+  const int W = ctx->ga_prm.n_islands;
+  AHX_CUDA(ctx, cudaMemcpy(ctx->d_isl.p, mbox, sizeof(void *) * W, cudaMemcpyHostToDevice));   // GaIslands::mbox is the first member
+  ctx->isl_connected = true;
+  return AHX_OK;
+}
+static int island_ready(ahx_ctx *ctx, const char *who) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!ctx->ga_active || ctx->ga_prm.n_islands <= 1 || !ctx->ga_res)
+    return fail(ctx, AHX_ERR_STATE, std::string(who) + ": no active island run (ahx_ga_begin with n_islands > 1 first)");
+  return AHX_OK;
+}
+
+int ahx_ga_island_export(ahx_ctx *ctx, void *handle) {
+  int rc = island_ready(ctx, "ahx_ga_island_export");
+  if (rc != AHX_OK) return rc;
+  if (!handle) return fail(ctx, AHX_ERR_ARG, "ahx_ga_island_export: null handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == AHX_ISLAND_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  AHX_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_mbox.p));
+  memcpy(handle, &h, sizeof h);
+  return AHX_OK;
+}
+
+int ahx_ga_island_connect(ahx_ctx *ctx, const void *handles) {
+  int rc = island_ready(ctx, "ahx_ga_island_connect");
+  if (rc != AHX_OK) return rc;
+  if (!handles) return fail(ctx, AHX_ERR_ARG, "ahx_ga_island_connect: null handles");
+  const int W = ctx->ga_prm.n_islands;
+  void *mbox[kMaxIslands] = {};
+  for (int i = 0; i < W; ++i) {
+    if (i == ctx->ga_prm.island) { mbox[i] = ctx->d_mbox.p; continue; }
+    const std::string key(static_cast<const char *>(handles) + static_cast<size_t>(i) * AHX_ISLAND_HANDLE_BYTES, AHX_ISLAND_HANDLE_BYTES);
+    for (auto &kv : ctx->isl_opened) if (kv.first == key) mbox[i] = kv.second;     // a mapping of this allocation is already open
+    if (!mbox[i]) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, key.data(), sizeof h);
+      AHX_CUDA(ctx, cudaIpcOpenMemHandle(&mbox[i], h, cudaIpcMemLazyEnablePeerAccess));
+      ctx->isl_opened.emplace_back(key, mbox[i]);
+    }
+  }
+  return island_table(ctx, mbox);
+}
+
+int ahx_ga_island_connect_local(ahx_ctx **ctxs, int32_t n) {
+  if (!ctxs || n < 1) { set_global_error("ahx_ga_island_connect_local: bad argument"); return AHX_ERR_ARG; }
+  for (int i = 0; i < n; ++i) {
+    int rc = island_ready(ctxs[i], "ahx_ga_island_connect_local");
+    if (rc != AHX_OK) return rc;
+    if (ctxs[i]->ga_prm.n_islands != n || ctxs[i]->ga_prm.island != i) return fail(ctxs[i], AHX_ERR_ARG, "ahx_ga_island_connect_local: ctxs[i] must run island i of n");
+  }
+  // islands that share a GPU must be able to run side by side: their cooperative grids wait for each other
+  for (int i = 0; i < n; ++i) {
+    int ctas = 0;
+    for (int j = 0; j < n; ++j) if (ctxs[j]->device == ctxs[i]->device) ctas += ctxs[j]->ga_G;
+    if (ctas > ctxs[i]->sm_count) return fail(ctxs[i], AHX_ERR_ARG, "ahx_ga_island_connect_local: the islands placed on one GPU need more CTAs than it has SMs (they must be co-resident)");
+  }
+  for (int i = 0; i < n; ++i) {
+    ahx_ctx *ctx = ctxs[i];
+    AHX_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *mbox[kMaxIslands] = {};
+    for (int j = 0; j < n; ++j) {
+      mbox[j] = ctxs[j]->d_mbox.p;
+      if (ctxs[j]->device == ctx->device) continue;
+      int can = 0;
+      AHX_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[j]->device));
+      if (!can) return fail(ctx, AHX_ERR_CUDA, "ahx_ga_island_connect_local: no peer access between the islands' GPUs");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaDeviceEnablePeerAccess");
+    }
+    int rc = island_table(ctx, mbox);
+    if (rc != AHX_OK) return rc;
+  }
+  return AHX_OK;
+}
+
+int64_t ahx_ga_island_epochs(ahx_ctx *ctx) {
+  if (!ctx || !ctx->ga_active || !ctx->ga_res || enter(ctx, true) != AHX_OK) return 0;
+  GaIslands h{};
+  if (read_islands(ctx, &h) != AHX_OK) return 0;
+  return static_cast<int64_t>(h.epochs);
 }
 
 int ahx_ga_best(ahx_ctx *ctx, int32_t *best_tour, double *best_score) {
@@ -965,7 +1147,7 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
     AHX_CUDA(ctx, cudaGetLastError());
     if ((rc = launch_eval_m_sparse(ctx, ctx->d_pop[0].p, nullptr, ctx->d_sel_rows.p, n, L, ctx->d_row_fit.p, ctx->stream)) != AHX_OK) return rc;
     scatter_fit_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_row_fit.p, ctx->d_sel_rows.p, ctx->d_sel_idx.p, n, ctx->d_fit[cur].p);
-    hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[0].p, ctx->d_rowof[cur].p, P, L, ctx->d_hof.p, ctx->d_state.p, n);
+    hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[0].p, ctx->d_rowof[cur].p, P, L, ctx->d_hof.p, ctx->d_state.p, n, ctx->ga_prm.max_gens);
     ctx->launches += 2;
     AHX_CUDA(ctx, cudaGetLastError());
     AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // freerows is stack-owned
@@ -975,7 +1157,7 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
   ctx->launches += 2;
   AHX_CUDA(ctx, cudaGetLastError());
   if ((rc = launch_eval_m_sparse(ctx, ctx->d_pop[cur].p, nullptr, ctx->d_sel_idx.p, n, L, ctx->d_fit[cur].p, ctx->stream)) != AHX_OK) return rc;
-  hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[cur].p, nullptr, P, L, ctx->d_hof.p, ctx->d_state.p, n);
+  hof_refresh_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_fit[cur].p, ctx->d_pop[cur].p, nullptr, P, L, ctx->d_hof.p, ctx->d_state.p, n, ctx->ga_prm.max_gens);
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1030,6 +1212,7 @@ int ahx_ga_end(ahx_ctx *ctx) {
   int rc = enter(ctx, false);
   if (rc != AHX_OK) return rc;
   ctx->ga_active = false;
+  ctx->isl_connected = false;
   return AHX_OK;
 }
 
@@ -1061,6 +1244,124 @@ int ahx_ga_run(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_t 
     if (stats) *stats = st;
   }
   ahx_ga_end(ctx);
+  return rc;
+}
+
+int ahx_mutate_remap(ahx_ctx *ctx, int32_t L, const int32_t *tour_in, int32_t op, int32_t p, int32_t q, int32_t dir, int32_t *tour_out,
+                     uint32_t *coords_out) {
+  int rc = enter(ctx, true);
+  if (rc != AHX_OK) return rc;
+  if (!tour_in || !tour_out || op < 0 || op > 3) return fail(ctx, AHX_ERR_ARG, "ahx_mutate_remap: bad argument");
+  if (!ctx->x32_ok || L < 2) return fail(ctx, AHX_ERR_ARG, "ahx_mutate_remap: needs a group with 32-bit coordinates (what the persistent GA kernel runs on) and L >= 2");
+  if ((rc = validate_tour(ctx, L, tour_in, "ahx_mutate_remap")) != AHX_OK) return rc;
+  if (op == 1 ? (p < 1 || p >= L) : (p < 0 || q < p || q >= L)) return fail(ctx, AHX_ERR_ARG, "ahx_mutate_remap: positions out of range");
+  const std::vector<uint32_t> x0 = tour_coordinates(ctx, L, tour_in);
+  long long tot = 0; for (int32_t i = 0; i < L; ++i) tot += ctx->h_sizes[tour_in[i]];
+  const int32_t N = ctx->N;
+  DevBuf<int32_t> a, b; DevBuf<uint32_t> xa, xb;
+  AHX_CUDA(ctx, a.reserve(L)); AHX_CUDA(ctx, b.reserve(L)); AHX_CUDA(ctx, xa.reserve(N)); AHX_CUDA(ctx, xb.reserve(N));
+  AHX_CUDA(ctx, cudaMemcpyAsync(a.p, tour_in, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, cudaMemcpyAsync(xa.p, x0.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, ctx->stream));
+  const MutPlan mp{1, op, p, op == 1 ? 0 : q, dir};
+  mutate_remap_kernel<<<1, 256, 0, ctx->stream>>>(a.p, xa.p, ctx->d_sizes32.p, static_cast<uint32_t>(2 * tot), L, ctx->N, mp, b.p, xb.p);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaMemcpyAsync(tour_out, b.p, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, ctx->stream));
+  if (coords_out) AHX_CUDA(ctx, cudaMemcpyAsync(coords_out, xb.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  a.release(); b.release(); xa.release(); xb.release();
+  return AHX_OK;
+}
+
+int ahx_test_plan_mutations(uint64_t seed, int32_t island, int64_t gen, int32_t n, double mut_prob, int32_t L, int32_t *out) {
+  if (n < 0 || L < 2 || !out) { set_global_error("ahx_test_plan_mutations: bad argument"); return AHX_ERR_ARG; }
+  const Philox ph = philox_key(seed, island);
+  for (int32_t o = 0; o < n; ++o) {
+    const MutPlan m = plan_mutation(ph, static_cast<uint32_t>(gen), static_cast<uint32_t>(gen >> 32), static_cast<uint32_t>(o), mut_prob, L);
+    out[5 * o] = m.mutated; out[5 * o + 1] = m.op; out[5 * o + 2] = m.p; out[5 * o + 3] = m.q; out[5 * o + 4] = m.dir;
+  }
+  return AHX_OK;
+}
+
+int ahx_test_tournaments(ahx_ctx *ctx, uint64_t seed, int32_t island, int64_t gen, int32_t P, const double *fit, int32_t k, int32_t n_pairs,
+                         int32_t *winners) {
+  int rc = enter(ctx, false);
+  if (rc != AHX_OK) return rc;
+  if (!fit || !winners || n_pairs < 0 || k < 1 || k > kMaxContestants || P < 2 || P - 2 < k - 1) return fail(ctx, AHX_ERR_ARG, "ahx_test_tournaments: bad argument");
+  if (n_pairs == 0) return AHX_OK;
+  DevBuf<double> f; DevBuf<int32_t> w;
+  AHX_CUDA(ctx, f.reserve(P)); AHX_CUDA(ctx, w.reserve(2 * static_cast<size_t>(n_pairs)));
+  AHX_CUDA(ctx, cudaMemcpyAsync(f.p, fit, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+  tournaments_kernel<<<(2 * n_pairs + 255) / 256, 256, 0, ctx->stream>>>(f.p, P, k, philox_key(seed, island), gen, n_pairs, w.p);
+  ctx->launches++;
+  AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaMemcpyAsync(winners, w.p, sizeof(int32_t) * 2 * static_cast<size_t>(n_pairs), cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  f.release(); w.release();
+  return AHX_OK;
+}
+
+int ahx_ga_run_islands(ahx_ctx **ctxs, int32_t n, const ahx_ga_params *prm, int32_t L, const int32_t *init_tour, int32_t *best_tour,
+                       ahx_ga_stats *stats, ahx_ga_callback cb, void *user) {
+  if (!ctxs || n < 1 || !prm) { set_global_error("ahx_ga_run_islands: bad argument"); return AHX_ERR_ARG; }
+  if (n == 1) {
+    ahx_ga_params p1 = *prm;
+    p1.n_islands = 1; p1.island = 0;
+    return ahx_ga_run(ctxs[0], &p1, L, init_tour, best_tour, stats, cb, user);
+  }
+  int rc = AHX_OK, begun = 0;
+  for (int i = 0; i < n && rc == AHX_OK; ++i) {
+    ahx_ga_params pi = *prm;
+    pi.n_islands = n; pi.island = i;
+    if ((rc = ahx_ga_begin(ctxs[i], &pi, L, init_tour)) == AHX_OK) ++begun;
+    else ctxs[0]->err = ctxs[i]->err;
+  }
+  if (rc == AHX_OK && (rc = ahx_ga_island_connect_local(ctxs, n)) != AHX_OK)
+    for (int i = 1; i < n; ++i) if (!ctxs[i]->err.empty() && ctxs[0]->err.empty()) ctxs[0]->err = ctxs[i]->err;
+  std::vector<int32_t> hof(L);
+  std::vector<GaState> hs(n);
+  auto best_island = [&]() {   // the best hall of fame; lowest island on ties
+    int b = 0;
+    for (int i = 1; i < n; ++i) if (hs[i].hof_fit < hs[b].hof_fit) b = i;
+    return b;
+  };
+  auto report = [&](int64_t gen) -> int {
+    if (!cb) return AHX_OK;
+    const int b = best_island();
+    double score = 0.0;
+    const int r = ahx_ga_best(ctxs[b], hof.data(), &score);
+    if (r != AHX_OK) return r;
+    cb(user, prm->phase, gen, score, hof.data(), L);
+    return AHX_OK;
+  };
+  for (int i = 0; i < n && rc == AHX_OK; ++i) rc = read_state(ctxs[i], &hs[i]);
+  if (rc == AHX_OK) rc = report(0);   // ga.init's callback at generation 0
+  const int64_t period = prm->log_every > 0 ? prm->log_every : 500;
+  while (rc == AHX_OK && !hs[0].stop) {
+    const int64_t next = (hs[0].gen / period + 1) * period;
+    int64_t left = next - hs[0].gen;
+    while (rc == AHX_OK && left > 0 && !hs[0].stop) {
+      const int64_t batch = std::min<int64_t>(left, kPersistChunk);
+      for (int i = 0; i < n && rc == AHX_OK; ++i) rc = persist_start(ctxs[i], batch);     // every island's kernel in flight ...
+      for (int i = 0; i < n; ++i) {                                                        // ... before waiting for any
+        const int r = persist_finish(ctxs[i], &hs[i]);
+        if (r != AHX_OK && rc == AHX_OK) { rc = r; ctxs[0]->err = ctxs[i]->err; }
+      }
+      left -= batch;
+    }
+    if (rc == AHX_OK && prm->log_every > 0 && hs[0].gen % period == 0) rc = report(hs[0].gen);
+  }
+  if (rc == AHX_OK) {
+    const int b = best_island();
+    double score = 0.0;
+    rc = ahx_ga_best(ctxs[b], best_tour, &score);   // r.Tour = ga.HallOfFame[0] (evaluate.go:313), over all populations
+    if (stats) {
+      fill_stats(ctxs[b], hs[b], stats);
+      stats->evaluations = 0; stats->device_ms = 0.0;
+      for (int i = 0; i < n; ++i) { stats->evaluations += hs[i].evals; stats->device_ms = std::max(stats->device_ms, ctxs[i]->ga_ms); }
+    }
+  }
+  for (int i = 0; i < begun; ++i) ahx_ga_end(ctxs[i]);
   return rc;
 }
 

@@ -44,7 +44,7 @@ struct GaRes {
   int *pool;            // [2P][L]   tours
   uint32_t *xpool;      // [2P][N]   coordinates 2*mid of every contig in that tour (N == L)
   const uint32_t *sizes32;
-  uint32_t total2;      // 2 * sum(sizes)
+  uint32_t total2;      // 2 * sum(sizes of the tour's contigs)
   int *rowof[2];        // [P]
   double *fit[2];       // [P]
   int *hof;             // [L]
@@ -54,6 +54,9 @@ struct GaRes {
   unsigned long long *gmin;   // [3] order-preserving key of the best fitness evaluated while building generation g (index g % 3)
   int *gidx;            // lowest offspring index holding that fitness (0x7fffffff when idle)
   uint32_t *gmask;      // [2][ceil(P/32)] mutation masks of generations g (index g & 1), filled one generation ahead
+  // islands (include/ahx.h "Islands"); n_islands <= 1: single population
+  int n_islands, island, migrate_every, n_elite;
+  GaIslands *isl;
 };
 
 // One mutated offspring: where it comes from, where it goes, and its mutation in two
@@ -113,9 +116,35 @@ __device__ __forceinline__ void remap_of(const MutPlan &mp, int L, const int *pt
 }
 
 
+constexpr int kIslMaxMigrants = 64;          // n_elite * (n_islands - 1) at most
+// island scratch in shared memory: per-warp (key, index) pairs of the block-wide selection, the last
+// winner, the selected individuals (elites, then worst) and the migrants' pool rows
+constexpr size_t kIslScratchBytes = 16 * (kRThreads / 32) + 32 + 4 * (3 * kIslMaxMigrants) + 16;
+// The two elementwise maps of a slot (the operator code the persistent kernel runs; ahx_mutate_remap
+// applies exactly these to one tour for the bit-exact operator tests).
+// coordinate of contig c in the child, from its coordinate x in the parent:
+// SUB: the tour covers a subset of the contigs; the others keep the "inactive" coordinate.
+template <bool SUB = false>
+__device__ __forceinline__ uint32_t slot_coord(const GaSlot &s, int c, uint32_t x) {
+  uint32_t y = (x - s.xlo < s.xlen) ? s.xa * x + s.xb : x + s.xb0;
+  y = c == s.m1 ? s.v1 : y;
+  y = c == s.m2 ? s.v2 : y;
+  if (SUB) y = x == kInactiveX ? x : y;
+  return y;
+}
+// parent position that feeds child position i:
+__device__ __forceinline__ int slot_source(const GaSlot &s, int i, int L) {
+  int src = static_cast<unsigned>(i - s.lo) < static_cast<unsigned>(s.len) ? s.a * i + s.b : i;
+  src = i == s.sp ? s.sv : src;
+  src = i == s.sp2 ? s.sv2 : src;
+  src -= src >= L ? L : 0;
+  return src;
+}
+
 inline size_t ga_res_extra_bytes(int P, int T, int nbmax) {
   const size_t wm = (static_cast<size_t>(P) + 31) / 32, wr = (2 * static_cast<size_t>(P) + 31) / 32;
-  return res_align16(4 * (2 * wm + 2 * wr)) + sizeof(GaSlot) * static_cast<size_t>(nbmax) * T + 4 * (kRThreads / 32 + 1) + 64;
+  return res_align16(4 * (2 * wm + 2 * wr)) + res_align16(sizeof(GaSlot) * static_cast<size_t>(nbmax) * T) + res_align16(4 * (kRThreads / 32 + 1)) +
+         res_align16(kIslScratchBytes) + 64;
 }
 
 // order-preserving map double -> uint64 (for atomicMin on fitness values) and back
@@ -127,7 +156,7 @@ __device__ __forceinline__ double key_fit(unsigned long long k) {
   return __longlong_as_double(static_cast<long long>((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k));
 }
 
-template <int T>
+template <int T, bool SUB = false>
 struct GaSrc {
   const int *pool; int *pool_w; const uint32_t *xpool; uint32_t *xpool_w; const GaSlot *slots; double *fitn; unsigned long long *gmin;
   // Lane l works on tour t = l mod T and on contig (then position) base + l / T: 32/T consecutive
@@ -148,9 +177,7 @@ struct GaSrc {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int c = c0 + u * NW * CPI;
-        uint32_t y = (x[u] - s.xlo < s.xlen) ? s.xa * x[u] + s.xb : x[u] + s.xb0;
-        y = c == s.m1 ? s.v1 : y;
-        y = c == s.m2 ? s.v2 : y;
+        const uint32_t y = slot_coord<SUB>(s, c, x[u]);
         if (c < N) { X[static_cast<size_t>(c) * T + t] = y; if (live) cx[c] = y; }
       }
     }
@@ -163,11 +190,7 @@ struct GaSrc {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int i = i0 + u * NW * CPI;
-          int src = static_cast<unsigned>(i - s.lo) < static_cast<unsigned>(s.len) ? s.a * i + s.b : i;
-          src = i == s.sp ? s.sv : src;
-          src = i == s.sp2 ? s.sv2 : src;
-          src -= src >= L ? L : 0;
-          v[u] = i < L ? __ldcg(pt + src) : 0;
+          v[u] = i < L ? __ldcg(pt + slot_source(s, i, L)) : 0;
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) { const int i = i0 + u * NW * CPI; if (i < L) ct[i] = v[u]; }
@@ -274,7 +297,212 @@ __device__ __forceinline__ uint32_t ga_load_mask(const GaRes &q, const uint32_t 
   return block_scan_array(mpref, WM, scan_tmp);
 }
 
-template <int T, bool STREAM>
+// Bit mask of the pool rows a generation references (from its byte map in global memory, filled
+// while that generation was built) and the exclusive word prefix of the FREE rows, for mask_select.
+__device__ __forceinline__ void ga_row_map(const GaRes &q, const unsigned char *used_cur, uint32_t *rused, uint32_t *rpref, uint32_t *scan_tmp) {
+  const int tid = threadIdx.x, WR = (2 * q.P + 31) / 32;
+  for (int wi = tid; wi < WR; wi += kRThreads) {
+    uint32_t w = 0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(used_cur + static_cast<size_t>(wi) * 32);
+    const int nvalid = min(32, 2 * q.P - wi * 32);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (nvalid <= h * 16) break;
+      const uint4 v = __ldcg(src + h);                       // the map is padded to a multiple of 32 bytes
+      const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) w |= ((x[i] >> (8 * b)) & 1u) << (h * 16 + i * 4 + b);
+    }
+    rused[wi] = w;
+    w = ~w;
+    if (nvalid < 32) w &= (1u << nvalid) - 1u;
+    rpref[wi] = __popc(w);
+  }
+  __syncthreads();
+  block_scan_array(rpref, WR, scan_tmp);   // at least P of the 2P rows are free
+  __syncthreads();
+}
+
+// ---- islands: the exchange step, inside the kernel ------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct IslScratch {
+  unsigned long long *wkey;   // [warps]
+  int *widx;                  // [warps]
+  unsigned long long *last;   // [1] key of the previous winner
+  int *last_idx;              // [1] (and [2]: time-out flag)
+  int *sel;                   // [2 * kIslMaxMigrants] selected individuals
+  int *rows;                  // [kIslMaxMigrants] pool rows of the migrants
+};
+__device__ __forceinline__ IslScratch isl_scratch(unsigned char *p) {
+  IslScratch s;
+  s.wkey = reinterpret_cast<unsigned long long *>(p); p += 8 * (kRThreads / 32);
+  s.last = reinterpret_cast<unsigned long long *>(p); p += 8;
+  s.widx = reinterpret_cast<int *>(p); p += 4 * (kRThreads / 32);
+  s.last_idx = reinterpret_cast<int *>(p); p += 16;
+  s.sel = reinterpret_cast<int *>(p); p += 4 * 2 * kIslMaxMigrants;
+  s.rows = reinterpret_cast<int *>(p);
+  return s;
+}
+
+// The k individuals with the smallest (key, index), ascending, into out[0..k): key = fit_key(fitness)
+// (best first, lowest index on ties) or its complement (worst first, lowest index on ties).  Whole block.
+__device__ __forceinline__ void isl_select_k(const double *fit, int P, int k, bool worst, int *out, const IslScratch &sc) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned long long lk = 0; int li = -1;                       // previous winner: candidates must be strictly greater
+  for (int r = 0; r < k; ++r) {
+    unsigned long long bk = ~0ULL; int bi = 0x7fffffff;
+    for (int i = tid; i < P; i += kRThreads) {
+      unsigned long long key = fit_key(__ldcg(fit + i));
+      if (worst) key = ~key;
+      const bool after = r == 0 || key > lk || (key == lk && i > li);
+      if (after && (key < bk || (key == bk && i < bi))) { bk = key; bi = i; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, d);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+      if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+    }
+    if (lane == 0) { sc.wkey[wid] = bk; sc.widx[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kRThreads / 32; ++w)
+        if (sc.wkey[w] < bk || (sc.wkey[w] == bk && sc.widx[w] < bi)) { bk = sc.wkey[w]; bi = sc.widx[w]; }
+      out[r] = bi; *sc.last = bk; *sc.last_idx = bi;
+    }
+    __syncthreads();
+    lk = *sc.last; li = *sc.last_idx;
+  }
+}
+
+// One exchange at generation `gen` (a multiple of migrate_every; `cur` = gen & 1 is the population just
+// built).  Called by every thread of every CTA after the generation's bookkeeping.  Export: CTA c writes
+// this island's elites into the mailbox of island (island + 1 + c) mod W.  Import: CTA 0 waits for the
+// other islands' flags of this epoch, replaces the worst individuals, refreshes the hall of fame and the
+// row map and takes the collective stop decision; one grid barrier publishes it.
+__device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long long gen, double &hof_fit, long long &updated, int &stop,
+                                                   unsigned int &nsync, uint32_t *rused, uint32_t *rpref, uint32_t *scan_tmp, unsigned char *isl_smem) {
+  const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x, W = q.n_islands, ne = q.n_elite, L = q.L;
+  const int cur = static_cast<int>(gen & 1);
+  int *rowc = q.rowof[cur]; double *fitc = q.fit[cur];
+  GaIslands *isl = q.isl;
+  const unsigned long long epoch = static_cast<unsigned long long>(gen / q.migrate_every);
+  const int par = static_cast<int>(epoch & 1);
+  const size_t flags_b = isl_flags_bytes(W), head_b = isl_head_bytes(ne), slot_b = isl_slot_bytes(ne, L, N);
+  const IslScratch sc = isl_scratch(isl_smem);
+  const bool exporter = cta < W - 1;
+  if (exporter || cta == 0) isl_select_k(fitc, q.P, ne, false, sc.sel, sc);          // elites: the same list in every CTA that needs it
+  for (int c = cta; c < W - 1; c += G) {
+    const int dst = (q.island + 1 + c) % W;
+    unsigned char *slot = isl->mbox[dst] + flags_b + (static_cast<size_t>(q.island) * 2 + par) * slot_b;
+    double *head = reinterpret_cast<double *>(slot);
+    if (tid == 0) head[0] = hof_fit;
+    if (tid < ne) head[1 + tid] = __ldcg(fitc + sc.sel[tid]);
+    int *dt = reinterpret_cast<int *>(slot + head_b);
+    uint32_t *dx = reinterpret_cast<uint32_t *>(dt + static_cast<size_t>(ne) * L);
+    for (int e = 0; e < ne; ++e) {
+      const int row = __ldcg(rowc + sc.sel[e]);
+      const int *pt = q.pool + static_cast<size_t>(row) * L;
+      const uint32_t *px = q.xpool + static_cast<size_t>(row) * N;
+      for (int i = tid; i < L; i += kRThreads) dt[static_cast<size_t>(e) * L + i] = __ldcg(pt + i);
+      for (int i = tid; i < N; i += kRThreads) dx[static_cast<size_t>(e) * N + i] = __ldcg(px + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) st_release_sys_u64(reinterpret_cast<unsigned long long *>(isl->mbox[dst] + 32 * static_cast<size_t>(q.island)), epoch);
+  }
+  if (cta == 0) {
+    const unsigned char *mine = isl->mbox[q.island];
+    if (tid == 0) sc.last_idx[2] = 0;
+    __syncthreads();
+    if (tid < W && tid != q.island) {
+      const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(mine + 32 * static_cast<size_t>(tid));
+      const long long t0 = global_timer_ns();
+      unsigned int spins = 0;
+      while (ld_acquire_sys_u64(flag) < epoch) {
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > isl->timeout_ns) { sc.last_idx[2] = 1; break; }
+      }
+    }
+    __syncthreads();
+    const bool timed_out = sc.last_idx[2] != 0;
+    const int m = ne * (W - 1);
+    double g_best = isl->g_best; long long g_updated = isl->g_updated;
+    int win = -1;                                                                 // thread 0: the migrant that beats the hall of fame
+    if (!timed_out) {
+      isl_select_k(fitc, q.P, m, true, sc.sel + kIslMaxMigrants, sc);             // worst first
+      ga_row_map(q, q.used + static_cast<size_t>(gen % 3) * ((2 * static_cast<size_t>(q.P) + 31) / 32 * 32), rused, rpref, scan_tmp);
+      const int WR = (2 * q.P + 31) / 32;
+      if (tid < m) sc.rows[tid] = mask_select(rused, rpref, WR, static_cast<uint32_t>(tid), true, 2 * q.P);
+      __syncthreads();
+      // migrant j: elite j % ne of the (j / ne)-th OTHER island, in island order
+      for (int j = 0; j < m; ++j) {
+        const int s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1, e = j % ne;
+        const unsigned char *slot = mine + flags_b + (static_cast<size_t>(src) * 2 + par) * slot_b;
+        const int *st = reinterpret_cast<const int *>(slot + head_b);
+        const uint32_t *sx = reinterpret_cast<const uint32_t *>(st + static_cast<size_t>(ne) * L);
+        int *pt = q.pool + static_cast<size_t>(sc.rows[j]) * L;
+        uint32_t *px = q.xpool + static_cast<size_t>(sc.rows[j]) * N;
+        for (int i = tid; i < L; i += kRThreads) pt[i] = __ldcg(st + static_cast<size_t>(e) * L + i);
+        for (int i = tid; i < N; i += kRThreads) px[i] = __ldcg(sx + static_cast<size_t>(e) * N + i);
+        if (tid == 0) {
+          const double f = __ldcg(reinterpret_cast<const double *>(slot) + 1 + e);
+          const int ind = sc.sel[kIslMaxMigrants + j];
+          rowc[ind] = sc.rows[j]; fitc[ind] = f;
+          if (f < hof_fit) { hof_fit = f; updated = gen; win = j; }                 // a migrant beats the hall of fame (first of equals)
+        }
+      }
+      if (tid == 0) {
+        double nb = hof_fit;
+        for (int s = 0; s < W; ++s)
+          if (s != q.island) nb = fmin(nb, __ldcg(reinterpret_cast<const double *>(mine + flags_b + (static_cast<size_t>(s) * 2 + par) * slot_b)));
+        if (nb < g_best) { g_best = nb; g_updated = gen; }
+      }
+    }
+    if (tid == 0) {
+      sc.last_idx[1] = win;
+      isl->g_best = g_best; isl->g_updated = g_updated; isl->epochs = epoch;
+      if (timed_out) { isl->err = 1; stop = 1; }
+      else if (gen - g_updated > q.ngen || gen >= q.max_gens) stop = 1;
+      isl->x_stop = stop;
+    }
+    __syncthreads();
+    if (!timed_out) {
+      if (sc.last_idx[1] >= 0) {                                                      // hall of fame <- the winning migrant's row
+        const int *best_row = q.pool + static_cast<size_t>(sc.rows[sc.last_idx[1]]) * L;
+        for (int i = tid; i < L; i += kRThreads) q.hof[i] = best_row[i];
+      }
+      // exact row map of the edited generation (fresh rows are allocated from its complement)
+      unsigned char *used_cur = q.used + static_cast<size_t>(gen % 3) * ((2 * static_cast<size_t>(q.P) + 31) / 32 * 32);
+      uint32_t *z = reinterpret_cast<uint32_t *>(used_cur);
+      for (size_t i = tid; i < (2 * static_cast<size_t>(q.P) + 31) / 32 * 8; i += kRThreads) z[i] = 0u;
+      __syncthreads();
+      for (int i = tid; i < q.P; i += kRThreads) used_cur[__ldcg(rowc + i)] = 1;
+    }
+    if (tid == 0) { isl->x_hof_fit = hof_fit; isl->x_updated = updated; }
+  }
+  ++nsync;
+  grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
+  hof_fit = __ldcg(&isl->x_hof_fit); updated = __ldcg(&isl->x_updated); stop = __ldcg(&isl->x_stop);
+}
+
+// SUB: the tours cover a subset of the group's contigs (L < N: a resumed run whose tour file lists fewer
+// contigs, clm.go:400-417); the evaluate side then uses the sub-tour window test (res_pair_terms).
+template <int T, bool STREAM, bool SUB>
 __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaRes q, long long n_gens) {
   extern __shared__ __align__(128) unsigned char smem_res[];
   const ResSmem m = res_carve<T, STREAM>(smem_res, g);
@@ -282,7 +510,8 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
   const int WM = (q.P + 31) / 32, WR = (2 * q.P + 31) / 32;
   uint32_t *mflag = reinterpret_cast<uint32_t *>(m.extra), *mpref = mflag + WM, *rused = mpref + WM, *rpref = rused + WR;
   GaSlot *slots = reinterpret_cast<GaSlot *>(m.extra + res_align16(4ull * (2 * WM + 2 * WR)));
-  uint32_t *scan_tmp = reinterpret_cast<uint32_t *>(slots + static_cast<size_t>(q.nbmax) * T);   // kRThreads/32 + 1 words
+  uint32_t *scan_tmp = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(slots) + res_align16(sizeof(GaSlot) * static_cast<size_t>(q.nbmax) * T));   // kRThreads/32 + 1 words
+  unsigned char *isl_smem = reinterpret_cast<unsigned char *>(scan_tmp) + res_align16(4 * (kRThreads / 32 + 1));
   res_init<STREAM>(m, g, true);
   int kdone = 0;
   bool table_ready = g.E_res == 0;
@@ -314,28 +543,7 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     unsigned char *used_old = q.used + static_cast<size_t>((gen + 2) % 3) * ub;        // generation gen-1's map: nobody reads it any more
     unsigned long long *gmin_new = q.gmin + (gen + 1) % 3;
     // ---- rows the current generation references -> free-row select structure
-    for (int wi = tid; wi < WR; wi += kRThreads) {
-      uint32_t w = 0;
-      const uint4 *src = reinterpret_cast<const uint4 *>(used_cur + static_cast<size_t>(wi) * 32);
-      const int nvalid = min(32, 2 * q.P - wi * 32);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        if (nvalid <= h * 16) break;
-        const uint4 v = __ldcg(src + h);                       // the map is padded to a multiple of 32 bytes
-        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) w |= ((x[i] >> (8 * b)) & 1u) << (h * 16 + i * 4 + b);
-      }
-      rused[wi] = w;
-      w = ~w;
-      if (nvalid < 32) w &= (1u << nvalid) - 1u;
-      rpref[wi] = __popc(w);
-    }
-    __syncthreads();
-    block_scan_array(rpref, WR, scan_tmp);   // at least P of the 2P rows are free
-    __syncthreads();
+    ga_row_map(q, used_cur, rused, rpref, scan_tmp);
     AHX_TICK(0);   // row map -> free-row select
     // ---- slot table of the mutated offspring this CTA scores
     const uint32_t Mcur = M;
@@ -380,8 +588,8 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     __syncthreads();
     AHX_TICK(1);   // slots + clones
     // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
-    GaSrc<T> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
-    res_run_batches<T, false, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
+    GaSrc<T, SUB> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
+    res_run_batches<T, SUB, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
     const long long ngen_now = gen + 1;
     __syncthreads();
     AHX_TICK(2);   // build + score
@@ -410,14 +618,19 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
       }
     }
     evals += Mcur;
-    if (ngen_now - updated > q.ngen || ngen_now >= q.max_gens) stop = 1;
+    // EarlyStop (evaluate.go:304-306); with islands it is a collective decision taken at the exchange points
+    if ((q.n_islands <= 1 && ngen_now - updated > q.ngen) || ngen_now >= q.max_gens) stop = 1;
     gen = ngen_now;
     AHX_TICK(4);   // mask load + hall of fame
+    if (q.n_islands > 1 && gen % q.migrate_every == 0) {
+      ga_island_exchange(q, g.N, gen, hof_fit, updated, stop, nsync, rused, rpref, scan_tmp, isl_smem);
+      AHX_TICK(5);   // island exchange
+    }
   }
 #ifdef AHX_GA_TIMING
   if (tid == 0 && (cta == 0 || cta == G - 1))
-    printf("cta %d (%d batches/gen at the end): rowmap %lld  slots %lld  build+score %lld  barrier %lld  mask+hof %lld cycles over %lld generations\n",
-           cta, 0, tph[0], tph[1], tph[2], tph[3], tph[4], n_gens);
+    printf("cta %d (%d batches/gen at the end): rowmap %lld  slots %lld  build+score %lld  barrier %lld  mask+hof %lld  exchange %lld cycles over %lld generations\n",
+           cta, 0, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], n_gens);
 #endif
   if (cta == 0 && tid == 0) {
     q.st->gen = gen; q.st->updated = updated; q.st->evals = evals; q.st->hof_fit = hof_fit; q.st->stop = stop;

@@ -1,12 +1,22 @@
 // allhic-b200: `optimize` sub-command with the reference's flags (allhic.go:160-190), and
-// `optimize-many`: the same run for a list of groups in ONE process and one device context --
-// what `pipeline` does with its sequential loop over the groups' REfiles (allhic.go:285-293).
-// Creating a CUDA context costs about a second (several when 8 processes start at once), as
-// much as the whole optimisation of a small group.
+// `optimize-many`: the same run for a list of groups in ONE process -- what `pipeline` does with
+// its sequential loop over the groups' REfiles (allhic.go:285-293), except that
+//   * the process drives every GPU of the box (--gpus N) and keeps --jobs J groups in flight per
+//     GPU, each on its own context and stream: at the CLI's default population (100) one group
+//     fills 25 of a B200's 148 SMs, so several groups run side by side; one CUDA start-up for all;
+//   * groups that name the same clmfile (pipeline hands the genome-wide CLM to every group) share
+//     ONE parse of it (ahx_clm_parse_groups).
+// Every group's .tour file and stdout text are the same as a separate `optimize` run's.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ahx.h"
@@ -23,13 +33,53 @@ static void usage() {
           "      --resume         Resume from existing tour file\n"
           "      --seed int       Random seed (default 42)\n"
           "      --skipGA         Skip GA step\n"
-          "      --device int     CUDA device (default 0)\n");
+          "      --device int     first CUDA device (default 0)\n"
+          "      --gpus int       optimize: island model, one population of --npop per GPU (default 1);\n"
+          "                       optimize-many: farm the groups over this many GPUs (default 1)\n"
+          "      --migrate int    islands: generations between exchanges (default 50)\n"
+          "      --elite int      islands: elites sent to every other island per exchange (default 2)\n"
+          "      --jobs int       optimize-many: groups in flight per GPU (default 1)\n");
 }
+
+namespace {
+
+struct Group { int idx; std::string re, clm; long ntigs = 0; ahx_clm *parsed = nullptr; };
+
+long count_contigs(const std::string &refile) {
+  FILE *f = fopen(refile.c_str(), "r");
+  if (!f) return 0;
+  long n = 0; char line[65536];
+  while (fgets(line, sizeof line, f)) { const char *p = line; while (*p == ' ' || *p == '\t') ++p; if (*p && *p != '\n' && *p != '#') ++n; }
+  fclose(f);
+  return n;
+}
+
+// Runs one group; its stdout text goes to `text` (emitted in one piece by the caller).
+bool run_group(const allhic::Optimizer &flags, Group &g, const std::vector<ahx_ctx *> &ctxs, std::string *text) {
+  char *buf = nullptr; size_t len = 0;
+  FILE *mem = open_memstream(&buf, &len);
+  bool ok = true;
+  try {
+    allhic::Optimizer q = flags;                                   // same flags (and seed) for every group, like `pipeline`
+    q.REfile = g.re; q.Clmfile = g.clm; q.Ctxs = ctxs; q.Out = mem; q.Parsed = g.parsed;
+    g.parsed = nullptr;
+    q.Run();
+  } catch (const allhic::FatalError &) {
+    ok = false;                                                    // log.Fatal of this group only
+  }
+  fclose(mem);
+  text->assign(buf ? buf : "", len);
+  free(buf);
+  return ok;
+}
+
+}  // namespace
 
 int main(int argc, char **argv) {
   if (argc < 2 || (strcmp(argv[1], "optimize") != 0 && strcmp(argv[1], "optimize-many") != 0)) { usage(); return 2; }
   const bool many = strcmp(argv[1], "optimize-many") == 0;
   allhic::Optimizer p;
+  int jobs = 1;
   std::vector<std::string> pos;
   for (int i = 2; i < argc; ++i) {
     std::string a = argv[i], v;
@@ -43,32 +93,109 @@ int main(int argc, char **argv) {
     else if (a == "--ngen") p.NGen = atoi(val().c_str());
     else if (a == "--mutapb") p.MutProb = atof(val().c_str());
     else if (a == "--device") p.Device = atoi(val().c_str());
+    else if (a == "--gpus") p.Gpus = atoi(val().c_str());
+    else if (a == "--migrate") p.MigrateEvery = atoi(val().c_str());
+    else if (a == "--elite") p.NElite = atoi(val().c_str());
+    else if (a == "--jobs") jobs = atoi(val().c_str());
     else if (a.rfind("--", 0) == 0) { fprintf(stderr, "unknown flag: %s\n", a.c_str()); usage(); return 2; }
     else pos.push_back(a);
   }
-  if (many) {
-    if (pos.size() != 1) { fprintf(stderr, "optimize-many accepts 1 arg, received %zu\n", pos.size()); usage(); return 2; }
-    FILE *list = pos[0] == "-" ? stdin : fopen(pos[0].c_str(), "r");
-    if (!list) { fprintf(stderr, "cannot open %s\n", pos[0].c_str()); return 1; }
+  if (p.Gpus < 1 || jobs < 1) { usage(); return 2; }
+  if (!many) {
+    if (pos.size() != 2) { fprintf(stderr, "accepts 2 arg(s), received %zu\n", pos.size()); usage(); return 2; }   // cobra.ExactArgs(2)
+    p.REfile = pos[0];
+    p.Clmfile = pos[1];
+    try { p.Run(); } catch (const allhic::FatalError &) { return 1; }   // log.Fatal -> os.Exit(1)
+    return 0;
+  }
+
+  if (pos.size() != 1) { fprintf(stderr, "optimize-many accepts 1 arg, received %zu\n", pos.size()); usage(); return 2; }
+  FILE *list = pos[0] == "-" ? stdin : fopen(pos[0].c_str(), "r");
+  if (!list) { fprintf(stderr, "cannot open %s\n", pos[0].c_str()); return 1; }
+  const int ngpus = p.Gpus;
+  p.Gpus = 1;                                                      // here --gpus farms groups; every group is one population
+  const int nworkers = ngpus * jobs;
+  char line[8192];
+
+  if (nworkers == 1) {
+    // one group at a time, as they arrive (a driver may feed stdin and wait for each AHX_GROUP_DONE)
     ahx_ctx *ctx = nullptr;
     if (ahx_create(p.Device, &ctx) != AHX_OK) { fprintf(stderr, "%s\n", ahx_last_error(nullptr)); return 1; }
-    char line[8192];
+    int failed = 0;
     for (int idx = 0; fgets(line, sizeof line, list);) {
       char re[4096], clm[4096];
       if (sscanf(line, "%4095s %4095s", re, clm) != 2) continue;   // blank line
-      allhic::Optimizer q = p;                                       // same flags (and seed) for every group, like `pipeline`
-      q.REfile = re; q.Clmfile = clm; q.Ctx = ctx;
-      q.Run();
-      printf("AHX_GROUP_DONE %d %s\n", idx++, re);
+      Group g{idx, re, clm};
+      std::string text;
+      const bool ok = run_group(p, g, {ctx}, &text);
+      fwrite(text.data(), 1, text.size(), stdout);
+      printf("%s %d %s\n", ok ? "AHX_GROUP_DONE" : "AHX_GROUP_FAILED", idx++, re);
       fflush(stdout);
+      failed += !ok;
     }
     ahx_destroy(ctx);
     if (list != stdin) fclose(list);
-    return 0;
+    return failed ? 1 : 0;
   }
-  if (pos.size() != 2) { fprintf(stderr, "accepts 2 arg(s), received %zu\n", pos.size()); usage(); return 2; }   // cobra.ExactArgs(2)
-  p.REfile = pos[0];
-  p.Clmfile = pos[1];
-  p.Run();
-  return 0;
+
+  // ---- several groups in flight: read the whole list, share CLM parses, largest group first
+  std::vector<Group> groups;
+  while (fgets(line, sizeof line, list)) {
+    char re[4096], clm[4096];
+    if (sscanf(line, "%4095s %4095s", re, clm) != 2) continue;
+    Group g{static_cast<int>(groups.size()), re, clm};
+    g.ntigs = count_contigs(g.re);
+    groups.push_back(g);
+  }
+  if (list != stdin) fclose(list);
+  {
+    std::map<std::string, std::vector<int>> by_clm;
+    for (auto &g : groups) by_clm[g.clm].push_back(g.idx);
+    for (auto &kv : by_clm) {
+      if (kv.second.size() < 2) continue;
+      const auto t0 = std::chrono::steady_clock::now();
+      std::vector<const char *> res;
+      for (int i : kv.second) res.push_back(groups[i].re.c_str());
+      std::vector<ahx_clm *> out(res.size(), nullptr);
+      if (ahx_clm_parse_groups(kv.first.c_str(), res.data(), static_cast<int32_t>(res.size()), 0, out.data()) != AHX_OK) {
+        fprintf(stderr, "%s\n", ahx_last_error(nullptr));                    // the groups then fail one by one on their own parse
+        continue;
+      }
+      for (size_t k = 0; k < out.size(); ++k) groups[kv.second[k]].parsed = out[k];
+      allhic::logNotice("Parsed clmfile `%s` once for %zu groups in %.2f s", kv.first.c_str(), out.size(),
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+  }
+  std::vector<int> order(groups.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].ntigs > groups[b].ntigs; });   // ~N^2 work: longest first
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed{0};
+  std::mutex out_mu;
+  std::vector<std::thread> workers;
+  for (int w = 0; w < nworkers; ++w)
+    workers.emplace_back([&, w] {
+      const int dev = p.Device + w % ngpus;
+      ahx_ctx *ctx = nullptr;
+      if (ahx_create(dev, &ctx) != AHX_OK) { fprintf(stderr, "%s\n", ahx_last_error(nullptr)); return; }
+      for (size_t k = next++; k < order.size(); k = next++) {
+        Group &g = groups[order[k]];
+        allhic::logSetTag("[group " + std::to_string(g.idx) + "] ");
+        allhic::Optimizer q = p;
+        q.Device = dev;
+        std::string text;
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = run_group(q, g, {ctx}, &text);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::lock_guard<std::mutex> lk(out_mu);
+        fwrite(text.data(), 1, text.size(), stdout);
+        printf("%s %d %s device=%d seconds=%.3f\n", ok ? "AHX_GROUP_DONE" : "AHX_GROUP_FAILED", g.idx, g.re.c_str(), dev, dt);
+        fflush(stdout);
+        failed += !ok;
+      }
+      ahx_destroy(ctx);
+    });
+  for (auto &t : workers) t.join();
+  for (auto &g : groups) if (g.parsed) ahx_clm_free(g.parsed);   // groups no worker reached (every worker failed to start)
+  return failed ? 1 : (next.load() >= order.size() ? 0 : 1);
 }

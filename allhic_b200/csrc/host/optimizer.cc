@@ -12,21 +12,26 @@
 
 namespace allhic {
 
-static void vlog(const char *level, const char *fmt, va_list ap) {
-  // same shape as the reference's go-logging format (base.go:106-108): time, level, message on stderr
-  char ts[16];
+static thread_local std::string g_tag;
+void logSetTag(const std::string &tag) { g_tag = tag; }
+
+static std::string vlog(const char *level, const char *fmt, va_list ap) {
+  // same shape as the reference's go-logging format (base.go:106-108): time, level, message on stderr;
+  // one write per line so that lines of concurrent groups do not interleave
+  char ts[16], msg[4096];
   const time_t now = time(nullptr);
   struct tm tmv;
   localtime_r(&now, &tmv);
   strftime(ts, sizeof ts, "%H:%M:%S", &tmv);
-  fprintf(stderr, "%s | %s ", ts, level);
-  vfprintf(stderr, fmt, ap);
-  fputc('\n', stderr);
+  vsnprintf(msg, sizeof msg, fmt, ap);
+  std::string line = std::string(ts) + " | " + level + " " + g_tag + msg + "\n";
+  fwrite(line.data(), 1, line.size(), stderr);
+  return msg;
 }
 void logNotice(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vlog("NOTICE", fmt, ap); va_end(ap); }
-void logFatal(const char *fmt, ...) {   // log.Fatal: message + exit(1) (base.go:349-362)
-  va_list ap; va_start(ap, fmt); vlog("CRITIC", fmt, ap); va_end(ap);
-  exit(1);
+void logFatal(const char *fmt, ...) {   // log.Fatal: message, then the run ends (base.go:349-362)
+  va_list ap; va_start(ap, fmt); std::string m = vlog("CRITIC", fmt, ap); va_end(ap);
+  throw FatalError{m};
 }
 
 std::string RemoveExt(const std::string &filename) {   // strings.TrimSuffix(filename, path.Ext(filename))
@@ -40,19 +45,26 @@ void CLM::check(int rc, const char *what) {
   if (rc != AHX_OK) logFatal("%s: %s", what, ahx_last_error(ctx_));
 }
 
-CLM::CLM(const std::string &clmfile, const std::string &refile, int device, ahx_ctx *shared) : REfile(refile), Clmfile(clmfile) {
+CLM::CLM(const std::string &clmfile, const std::string &refile, int device, const std::vector<ahx_ctx *> &shared, ahx_clm *parsed, FILE *out)
+    : REfile(refile), Clmfile(clmfile), clm_(parsed), out_(out) {
   logNotice("Parse REfile `%s`", refile.c_str());
   logNotice("Parse clmfile `%s`", clmfile.c_str());
-  if (ahx_clm_parse(clmfile.c_str(), refile.c_str(), 0, &clm_) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));   // mustOpen -> log.Fatal
+  if (!clm_ && ahx_clm_parse(clmfile.c_str(), refile.c_str(), 0, &clm_) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));   // mustOpen -> log.Fatal
   const int n = ahx_clm_ntigs(clm_);
   for (int i = 0; i < n; ++i) Tigs.push_back({i, ahx_clm_tig_name(clm_, i), ahx_clm_tig_size(clm_, i), true});
-  if (shared) { ctx_ = shared; own_ctx_ = false; }
-  else if (ahx_create(device, &ctx_) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));
-  check(ahx_load_clm(ctx_, clm_), "ahx_load_clm");
+  if (!shared.empty()) { islands_ = shared; own_ctx_ = false; }
+  else {
+    ahx_ctx *c = nullptr;
+    if (ahx_create(device, &c) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));
+    islands_.push_back(c);
+  }
+  ctx_ = islands_[0];
+  for (ahx_ctx *c : islands_)
+    if (ahx_load_clm(c, clm_) != AHX_OK) logFatal("ahx_load_clm: %s", ahx_last_error(c));
 }
 
 CLM::~CLM() {
-  if (ctx_ && own_ctx_) ahx_destroy(ctx_);
+  if (own_ctx_) for (ahx_ctx *c : islands_) ahx_destroy(c);
   if (clm_) ahx_clm_free(clm_);
 }
 
@@ -165,14 +177,14 @@ void CLM::parseTourFile(const std::string &filename) {
     Signs[idx] = static_cast<uint8_t>(word.back());
     Tigs[idx].IsActive = true;
   }
-  printTour(stdout, Tour, "INIT");
+  printTour(out_, Tour, "INIT");
 }
 
-struct GaCbCtx { CLM *clm; FILE *fw; };
+struct GaCbCtx { CLM *clm; FILE *fw; FILE *out; };
 
 static void ga_progress(void *user, int32_t phase, int64_t gen, double best, const int32_t *tour, int32_t L) {
   auto *c = static_cast<GaCbCtx *>(user);
-  printf("Current iteration GA%d-%lld: max_score=%.5f\n", phase, static_cast<long long>(gen), best);   // evaluate.go:295
+  fprintf(c->out, "Current iteration GA%d-%lld: max_score=%.5f\n", phase, static_cast<long long>(gen), best);   // evaluate.go:295
   allhic::Tour t;
   t.Tigs.assign(tour, tour + L);
   char label[96];
@@ -190,8 +202,14 @@ allhic::Tour CLM::GARun(FILE *fwtour, Optimizer *opt, int phase) {
             static_cast<long long>(opt->Seed), AHX_LIMIT);
   std::vector<int32_t> best(Tour.Len());
   ahx_ga_stats st;
-  GaCbCtx cb{this, fwtour};
-  check(ahx_ga_run(ctx_, &prm, Tour.Len(), Tour.Tigs.data(), best.data(), &st, ga_progress, &cb), "ahx_ga_run");
+  GaCbCtx cb{this, fwtour, out_};
+  if (islands_.size() > 1) {   // one island per GPU; the exchange runs inside the GA kernels (include/ahx.h "Islands")
+    prm.migrate_every = opt->MigrateEvery; prm.n_elite = opt->NElite;
+    logNotice("Island model: %zu populations of %d, %d elites to every other island every %d generations", islands_.size(), opt->NPop, opt->NElite, opt->MigrateEvery);
+    check(ahx_ga_run_islands(islands_.data(), static_cast<int32_t>(islands_.size()), &prm, Tour.Len(), Tour.Tigs.data(), best.data(), &st, ga_progress, &cb), "ahx_ga_run_islands");
+  } else {
+    check(ahx_ga_run(ctx_, &prm, Tour.Len(), Tour.Tigs.data(), best.data(), &st, ga_progress, &cb), "ahx_ga_run");
+  }
   Tour.Tigs = best;   // r.Tour = ga.HallOfFame[0]
   return Tour;
 }
@@ -207,7 +225,18 @@ void CLM::OptimizeOrientations(FILE *fwtour, int phase, const char **tag1, const
 
 void Optimizer::Run() {
   std::mt19937_64 rng(static_cast<uint64_t>(Seed));
-  CLM clm(Clmfile, REfile, Device, Ctx);
+  std::vector<ahx_ctx *> own;   // --gpus N without borrowed contexts: devices Device .. Device + N - 1
+  struct Cleanup { std::vector<ahx_ctx *> &v; ~Cleanup() { for (ahx_ctx *c : v) ahx_destroy(c); } } cleanup{own};
+  if (Ctxs.empty() && Gpus > 1) {
+    for (int i = 0; i < Gpus; ++i) {
+      ahx_ctx *c = nullptr;
+      if (ahx_create(Device + i, &c) != AHX_OK) logFatal("%s", ahx_last_error(nullptr));
+      own.push_back(c);
+    }
+  }
+  ahx_clm *parsed = Parsed;
+  Parsed = nullptr;
+  CLM clm(Clmfile, REfile, Device, Ctxs.empty() ? own : Ctxs, parsed, Out);
   const std::string tourfile = RemoveExt(REfile) + ".tour";
   struct stat sb;
   if (Resume && stat(tourfile.c_str(), &sb) == 0) {   // optimize.go:44-51
@@ -221,7 +250,7 @@ void Optimizer::Run() {
   logNotice("Optimization history logged to `%s`", tourfile.c_str());
   FILE *fwtour = fopen(tourfile.c_str(), "w");   // os.Create; the reference ignores the error
   OutTourFile = tourfile;
-  clm.printTour(stdout, clm.Tour, "INIT");
+  clm.printTour(Out, clm.Tour, "INIT");
   clm.printTour(fwtour, clm.Tour, "INIT");
   if (RunGA)
     for (int phase = 1; phase < 3; ++phase) clm.OptimizeOrdering(fwtour, this, phase);
@@ -233,7 +262,7 @@ void Optimizer::Run() {
       break;
     }
   }
-  clm.printTour(stdout, clm.Tour, "FINAL");
+  clm.printTour(Out, clm.Tour, "FINAL");
   logNotice("Success");
   if (fwtour) fclose(fwtour);
 }

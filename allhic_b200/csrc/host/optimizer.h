@@ -38,9 +38,12 @@ class CLM {
   allhic::Tour Tour;
   std::vector<uint8_t> Signs;
 
-  // NewCLM (clm.go:121): parse both files and upload the group to `device`.  `shared`: a context the
-  // caller owns and reuses from group to group (`optimize-many`); else one is created and destroyed here.
-  CLM(const std::string &clmfile, const std::string &refile, int device, ahx_ctx *shared = nullptr);
+  // NewCLM (clm.go:121): parse both files and upload the group to `device`.  `shared`: contexts the
+  // caller owns and reuses from group to group (`optimize-many`; more than one = one island per context);
+  // else one is created and destroyed here.  `parsed`: this group's share of a genome-wide CLM that the
+  // caller parsed once for all groups (ahx_clm_parse_groups); ownership passes to the CLM.
+  CLM(const std::string &clmfile, const std::string &refile, int device, const std::vector<ahx_ctx *> &shared = {},
+      ahx_clm *parsed = nullptr, FILE *out = stdout);
   ~CLM();
   CLM(const CLM &) = delete;
   CLM &operator=(const CLM &) = delete;
@@ -60,8 +63,10 @@ class CLM {
 
  private:
   ahx_clm *clm_ = nullptr;
-  ahx_ctx *ctx_ = nullptr;
+  ahx_ctx *ctx_ = nullptr;                 // islands_[0]: scores, flips, the single-population GA
+  std::vector<ahx_ctx *> islands_;         // one context per GPU of the island model (size 1: none)
   bool own_ctx_ = true;
+  FILE *out_ = stdout;                     // where the reference writes to os.Stdout
   void check(int rc, const char *what);
 };
 
@@ -73,14 +78,24 @@ struct Optimizer {       // optimize.go:21-35
   int NGen = 5000;       // base.go:69
   double MutProb = 0.2;  // base.go:71
   int Device = 0;
-  ahx_ctx *Ctx = nullptr;   // borrowed device context (optimize-many); nullptr: Run() makes its own
+  // Island model over several GPUs (--gpus N; eaopt's NPops, which the reference pins to 1, evaluate.go:269):
+  // NPop individuals per island, an exchange of NElite elites every MigrateEvery generations.
+  int Gpus = 1, MigrateEvery = 50, NElite = 2;
+  std::vector<ahx_ctx *> Ctxs;   // borrowed device contexts (optimize-many / islands); empty: Run() makes its own
+  ahx_clm *Parsed = nullptr;     // pre-parsed group (shared genome-wide parse); Run() hands it to the CLM
+  FILE *Out = stdout;            // os.Stdout of this run (a buffer when several groups run at once)
   std::string OutTourFile;
   void Run();            // optimize.go:38
 };
 
 std::string RemoveExt(const std::string &filename);   // base.go:125
 void logNotice(const char *fmt, ...);
+// log.Fatal (base.go:349-362): message, then the run ends.  Thrown as an exception so that
+// `optimize-many` loses the failing group only; `optimize` turns it into exit(1) like the reference.
+struct FatalError { std::string msg; };
 [[noreturn]] void logFatal(const char *fmt, ...);
+// tag prepended to this thread's log lines (the group, when several run at once)
+void logSetTag(const std::string &tag);
 
 }  // namespace allhic
 

@@ -178,6 +178,46 @@ class Engine:
         t = np.ascontiguousarray(tours, np.int32)
         self._ck(self._l.ahx_ga_put_migrants(self.h, t.shape[0], _ptr(t)))
 
+    # ---- islands (include/ahx.h "Islands"): the exchange runs inside the GA kernel over peer memory
+    def ga_island_export(self):
+        """64-byte CUDA IPC handle of this island's mailbox (after ga_begin with n_islands > 1)."""
+        h = np.zeros(_ffi.ISLAND_HANDLE_BYTES, np.uint8)
+        self._ck(self._l.ahx_ga_island_export(self.h, _ptr(h)))
+        return h
+
+    def ga_island_connect(self, handles):
+        """handles: [n_islands, 64] uint8, island order (all-gathered over any host transport)."""
+        h = np.ascontiguousarray(handles, np.uint8)
+        self._ck(self._l.ahx_ga_island_connect(self.h, _ptr(h)))
+
+    def ga_island_epochs(self):
+        return int(self._l.ahx_ga_island_epochs(self.h))
+
+    @staticmethod
+    def ga_island_connect_local(engines):
+        """Islands of ONE process (one Engine per island, island order): peer access instead of CUDA IPC."""
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        rc = _ffi.lib().ahx_ga_island_connect_local(arr, len(engines))
+        for e in engines:
+            if rc != _ffi.OK and _ffi.lib().ahx_last_error(e.h):
+                _ffi.check(rc, e.h)
+        _ffi.check(rc, engines[0].h)
+
+    @staticmethod
+    def ga_run_islands(engines, init_tour, params, callback=None):
+        """CLM.GARun as an island model over the engines' GPUs, driven by this thread (ahx_ga_run_islands)."""
+        t = np.ascontiguousarray(init_tour, np.int32)
+        best = np.empty_like(t)
+        st = GAStats()
+
+        def _cb(user, phase, gen, score, tour_p, L):
+            if callback:
+                callback(phase, gen, score, np.ctypeslib.as_array(tour_p, shape=(L,)).copy())
+        cb = GA_CALLBACK(_cb)
+        arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+        _ffi.check(_ffi.lib().ahx_ga_run_islands(arr, len(engines), C.byref(params), len(t), _ptr(t), _ptr(best), C.byref(st), cb, None), engines[0].h)
+        return best, st
+
     def ga_selfcheck(self):
         """Number of individuals of the current generation whose stored state is inconsistent (0 = sound)."""
         n = C.c_int64()
@@ -196,6 +236,26 @@ class Engine:
         out = np.empty_like(t)
         self._ck(self._l.ahx_mutate(self.h, len(t), _ptr(t), op, p, q, dir, _ptr(out)))
         return out
+
+    def mutate_remap(self, tour, op, p=0, q=0, dir=0):
+        """The same mutation through the persistent GA kernel's operator code; returns (child tour, child 2*mid per contig)."""
+        t = np.ascontiguousarray(tour, np.int32)
+        out = np.empty_like(t); x = np.empty(len(t), np.uint32)
+        self._ck(self._l.ahx_mutate_remap(self.h, len(t), _ptr(t), op, p, q, dir, _ptr(out), _ptr(x)))
+        return out, x
+
+    @staticmethod
+    def plan_mutations(seed, island, gen, n, mut_prob, L):
+        """[n, 5] = mutated, op, p, q, dir of the kernels' mutation plan (host-side evaluation of the same code)."""
+        out = np.empty((n, 5), np.int32)
+        _ffi.check(_ffi.lib().ahx_test_plan_mutations(seed, island, gen, n, mut_prob, L, _ptr(out)))
+        return out
+
+    def tournaments(self, fit, k, n_pairs, seed=1, island=0, gen=0):
+        f = np.ascontiguousarray(fit, np.float64)
+        w = np.empty((n_pairs, 2), np.int32)
+        self._ck(self._l.ahx_test_tournaments(self.h, seed, island, gen, len(f), _ptr(f), k, n_pairs, _ptr(w)))
+        return w
 
     # ---- orientation (orientation.go:31-120)
     def flip_whole(self, tour, signs):

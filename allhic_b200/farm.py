@@ -5,12 +5,16 @@ allhic.go:285-293).  Each group is a full `allhic-b200 optimize` run (the C++
 host over the C ABI) pinned to one GPU; groups are handed out
 longest-processing-time-first (weight ~ N^2) to whichever GPU is free.
 
-`persistent=True` (default) keeps ONE `allhic-b200 optimize-many -` process per
-GPU and feeds it groups over stdin as it reports them done: the CUDA context --
-about a second to create, several when eight processes start together, i.e. as
-much as the optimisation of a small group itself -- is made once per GPU
-instead of once per group.  `persistent=False` starts one `optimize` process
-per group.
+`jobs=J` (default 6) runs ONE `allhic-b200 optimize-many --gpus G --jobs J`
+process for the whole box: a worker thread per (GPU, job slot), each with its
+own context and stream.  At the CLI's default population (100) a group's
+persistent GA kernel occupies 25 of a B200's 148 SMs, so ~6 groups run side by
+side on one GPU; CUDA starts once instead of once per GPU process (eight
+processes starting together take ~5 s each), and groups that name the same
+genome-wide clmfile share one parse of it.  `jobs=0` keeps the older modes:
+`persistent=True` one `optimize-many -` process per GPU fed over stdin,
+`persistent=False` one `optimize` process per group.  All modes leave
+identical .tour files.
 """
 import os
 import re
@@ -53,18 +57,18 @@ def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir
                 proc = subprocess.Popen([binary, "optimize-many", "-", "--device", "0", *flags], stdin=subprocess.PIPE,
                                         stdout=subprocess.PIPE, stderr=errf, text=True, bufsize=1, env=_device_env(dev))
             t0 = time.perf_counter()
-            out, ok = [], False
+            out, ok, answered = [], False, False
             try:
                 proc.stdin.write("%s %s\n" % (refile, clmfile))
                 proc.stdin.flush()
                 for line in proc.stdout:
-                    if line.startswith("AHX_GROUP_DONE "):
-                        ok = True
+                    if line.startswith("AHX_GROUP_DONE ") or line.startswith("AHX_GROUP_FAILED "):   # FAILED: log.Fatal of this group only
+                        ok, answered = line.startswith("AHX_GROUP_DONE "), True
                         break
                     out.append(line)
             except (BrokenPipeError, OSError):
                 pass
-            if not ok:                                  # the worker died on this group (logFatal): start a fresh one for the next
+            if not answered:                            # the worker died on this group: start a fresh one for the next
                 proc.kill()
                 proc.wait()
                 proc = None
@@ -83,9 +87,47 @@ def _persistent_worker(dev, groups, order, lock, results, flags, binary, log_dir
             errf.close()
 
 
-def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None, persistent=True):
+def _one_process(groups, devices, flags, binary, log_dir, jobs):
+    """`optimize-many --gpus G --jobs J` over a list file; parses its per-group blocks of stdout."""
+    import tempfile
+    env = dict(os.environ)
+    vis = [x for x in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+    env["CUDA_VISIBLE_DEVICES"] = ",".join(vis[d] if d < len(vis) else str(d) for d in devices)
+    with tempfile.NamedTemporaryFile("w", suffix=".list", delete=False) as f:
+        f.write("".join("%s %s\n" % g for g in groups))
+        listfile = f.name
+    errf = open(os.path.join(log_dir, "optimize-many.stderr"), "w") if log_dir else subprocess.DEVNULL
+    results = [None] * len(groups)
+    try:
+        proc = subprocess.Popen([binary, "optimize-many", listfile, "--device", "0", "--gpus", str(len(devices)), "--jobs", str(jobs), *flags],
+                                stdout=subprocess.PIPE, stderr=errf, text=True, bufsize=1, env=env)
+        block, seq = [], 0
+        for line in proc.stdout:
+            m = re.match(r"AHX_GROUP_(DONE|FAILED) (\d+) (\S+) device=(\d+) seconds=([0-9.]+)", line)
+            if not m:
+                block.append(line)
+                continue
+            g = int(m.group(2))
+            scores = re.findall(r"max_score=([0-9.eE+-]+)", "".join(block))
+            results[g] = dict(group=g, device=devices[int(m.group(4))], seq=seq, seconds=float(m.group(5)), n_contigs=_count_contigs(groups[g][0]),
+                              final_score=float(scores[-1]) if scores else None, ok=m.group(1) == "DONE")
+            block, seq = [], seq + 1
+        proc.wait()
+    finally:
+        os.unlink(listfile)
+        if log_dir:
+            errf.close()
+    for g in range(len(groups)):
+        if results[g] is None:
+            results[g] = dict(group=g, device=None, seq=None, seconds=0.0, n_contigs=_count_contigs(groups[g][0]), final_score=None, ok=False)
+    return results
+
+
+def optimize_groups(groups, devices, flags=(), binary=BINARY, log_dir=None, persistent=True, jobs=6):
     """groups: list of (refile, clmfile); devices: CUDA device indices to farm over.
     Returns a list of dicts (group, device, seq = dispatch order, seconds, final_score, n_contigs, ok) in input order."""
+    if jobs and jobs > 0:
+        return _one_process(groups, list(devices), flags, binary, log_dir, jobs)
     order = sorted(range(len(groups)), key=lambda g: -_count_contigs(groups[g][0]) ** 2)
     lock = threading.Lock()
     results = [None] * len(groups)

@@ -11,8 +11,19 @@ individuals by the other islands' elites.  The exchange is the only
 collective; it runs over NCCL (NVLink/NVSwitch) when the process group is
 NCCL and over gloo in the CPU tests.
 
+Two exchange paths behind the same class:
+  device   (product path) the exchange runs INSIDE libahx's persistent GA kernel: every
+           island's kernel writes its elites into the other islands' mailboxes over NVLink
+           peer memory and imports theirs, no host round trip and no relaunch (include/ahx.h
+           "Islands").  The host only wires the mailboxes once per run: an all-gather of the
+           64-byte CUDA IPC handles, which is also the barrier between consecutive runs.
+  host     ga_get_elites -> all-gather -> ga_put_migrants between ga_advance calls; kept for
+           groups the persistent kernel cannot hold (sub-tours, > 65535 contigs) and for the
+           CPU protocol tests.
+
 `engine` only needs ga_begin / ga_advance / ga_get_elites / ga_put_migrants /
-ga_best / ga_end, so the protocol is testable on CPU with a stand-in engine.
+ga_best / ga_end (plus ga_island_export / ga_island_connect for the device path), so the
+protocol is testable on CPU with a stand-in engine.
 """
 import os
 import time
@@ -40,7 +51,30 @@ class IslandGA:
         self.dev = _device_for(group)
         self.exchanges = 0
         self._t = [0.0] * 4
-        self.eng.ga_begin(np.ascontiguousarray(init_tour, np.int32), params)
+        init = np.ascontiguousarray(init_tour, np.int32)
+        self.mode = "host"
+        if self.world > 1 and hasattr(engine, "ga_island_export") and not os.environ.get("AHX_ISLANDS_HOST"):
+            params.n_islands, params.migrate_every, params.n_elite = self.world, self.migrate_every, self.n_elite
+            try:
+                self.eng.ga_begin(init, params)
+                self.mode = "device"
+            except Exception as e:                      # group not on the persistent kernel: every rank falls back alike
+                if "persistent" not in str(e):
+                    raise
+                params.n_islands = 0
+        if self.mode == "host":
+            if hasattr(params, "n_islands"):
+                params.n_islands = 0
+            self.eng.ga_begin(init, params)
+        else:
+            self._connect()
+
+    def _connect(self):
+        """All-gather the islands' mailbox handles and map them (once per run)."""
+        mine = torch.from_numpy(np.ascontiguousarray(self.eng.ga_island_export(), np.uint8)).to(self.dev)
+        allh = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        self.eng.ga_island_connect(allh.cpu().numpy().reshape(self.world, -1))
 
     def exchange(self, stopped=0):
         """All-gather elites (and this island's EarlyStop flag, so the stop decision costs no second
@@ -72,6 +106,12 @@ class IslandGA:
         `max_gens` generations ran.  Returns (best_tour, best_score, stats) with the
         global best replicated on every rank."""
         done, st = 0, None
+        if self.mode == "device":
+            t0 = time.perf_counter()
+            st = self.eng.ga_advance(max_gens)           # exchanges and the collective EarlyStop happen inside the kernel
+            self._t[3] += time.perf_counter() - t0
+            self.exchanges = self.eng.ga_island_epochs() if hasattr(self.eng, "ga_island_epochs") else 0
+            done = max_gens
         while done < max_gens:
             n = min(self.migrate_every, max_gens - done)
             t0 = time.perf_counter()
@@ -93,7 +133,7 @@ class IslandGA:
         owner = int(torch.argmax(allbest).item())
         t = torch.from_numpy(np.ascontiguousarray(tour, np.int32)).to(self.dev)
         dist.broadcast(t, src=dist.get_global_rank(self.group, owner) if self.group is not None else owner, group=self.group)
-        if self.world > 1:
+        if self.world > 1 and self.mode == "host":
             st = self.eng.ga_advance(0)      # statistics after the last migrants
         return t.cpu().numpy(), float(allbest[owner].item()), st
 

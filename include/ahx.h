@@ -68,6 +68,13 @@ const char *ahx_last_error(const ahx_ctx *ctx);
  * ------------------------------------------------------------------------- */
 /* Multi-threaded parser for `allhic optimize <REfile> <clmfile>` inputs. */
 int ahx_clm_parse(const char *clmfile, const char *refile, int nthreads, ahx_clm **out);
+/* The same for all linkage groups of one genome in ONE pass over the CLM text: `pipeline` hands the
+ * same genome-wide clmfile to every group's Optimizer (allhic.go:285-293) and each NewCLM filters it by
+ * its own REfile (clm.go:211-218) -- k groups, k full parses.  Here the file is read and tokenised once,
+ * a line's GoldenArray / SumLog computed once, and out[g] is exactly what ahx_clm_parse(clmfile,
+ * refiles[g]) returns.  refiles: e.g. partition's <prefix>.counts_<RE>.<k>g<j>.txt (partition.go:205-215). */
+int ahx_clm_parse_groups(const char *clmfile, const char *const *refiles, int32_t n_groups, int nthreads,
+                         ahx_clm **out /* n_groups */);
 /* Builder for a host that keeps its own parser (the Go readClm loop): create
  * with the REfile's sizes, then feed CLM lines in file order. */
 int ahx_clm_new(int32_t n_tigs, const int64_t *sizes, ahx_clm **out);
@@ -168,7 +175,16 @@ typedef struct ahx_ga_params {
   int32_t tournament_k;  /* SelTournament.NContestants (3, evaluate.go:273)       */
   int32_t log_every;     /* callback period   (500, evaluate.go:294)              */
   int32_t phase;         /* label only        (GA%d, optimize.go:64)              */
-  int32_t island;        /* RNG stream id of this island (0 for a single GPU)     */
+  int32_t island;        /* this island's id = its RNG stream (0 for a single GPU) */
+  /* Island model.  eaopt's multi-population switch, which the reference pins to one
+   * population (ga.NPops = 1, evaluate.go:269): n_islands populations of npop individuals each, one
+   * per GPU.  Every migrate_every generations each island sends its n_elite best individuals to every
+   * other island, which replace that island's worst (see "Islands" below).  n_islands <= 1: single
+   * population, the other two fields are ignored. */
+  int32_t n_islands;     /* ga.NPops                                              */
+  int32_t migrate_every; /* generations between exchanges (eaopt MigFrequency)    */
+  int32_t n_elite;       /* individuals sent to each other island per exchange    */
+  int32_t reserved;
 } ahx_ga_params;
 
 typedef struct ahx_ga_stats {
@@ -202,6 +218,47 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours /* n*L */)
  * (permutation of the active contigs, fitness within 1e-12 of a fresh Tour.Evaluate, stored
  * coordinates equal to the tour's) and counts the individuals that fail. */
 int ahx_ga_selfcheck(ahx_ctx *ctx, int64_t *n_bad);
+/* ------------------------------------------------------------------------- *
+ * Islands: the exchange step runs INSIDE the persistent GA kernel.  Every island owns a
+ * mailbox in its GPU's memory; at generation g = e * migrate_every each island's kernel
+ * stores its n_elite best individuals (tour row, coordinate row, fitness) and its best-ever
+ * fitness straight into every other island's mailbox over NVLink peer memory, publishes a
+ * release flag, waits for the other islands' flags of the same epoch e and replaces its
+ * worst individuals (worst first) by the migrants in island order -- no host round trip, no
+ * re-scoring (a score is a pure function of the tour), no kernel relaunch.  EarlyStop
+ * (evaluate.go:304-306) becomes a collective decision taken at the exchange points from the
+ * exchanged best-ever values: stop when the best over all islands has not improved for more
+ * than ngen generations; every island takes the same decision at the same generation.
+ * Same (seed, npop, n_islands, migrate_every, n_elite) => bit-identical run.
+ *
+ * Wiring, after ahx_ga_begin on every island (params.n_islands > 1) and before the first
+ * ahx_ga_advance:
+ *   one process per GPU:  ahx_ga_island_export on every island, all-gather the 64-byte
+ *                         handles on the host (any transport), ahx_ga_island_connect with all
+ *                         n_islands handles in island order (CUDA IPC).  The all-gather is
+ *                         also the barrier that orders one run's mailbox after the previous one's.
+ *   one process, n GPUs:  ahx_ga_island_connect_local (peer access), or simply
+ *                         ahx_ga_run_islands, which does begin / connect / advance / end for
+ *                         all islands from the calling thread.
+ * All islands must then be advanced by the same number of generations (their kernels wait
+ * for each other at every exchange point; a peer that never shows up is an AHX_ERR_STATE
+ * after AHX_ISLAND_TIMEOUT_MS, default 20000).  Requires the persistent GA kernel
+ * (ahx_ga_kernel() >= 2); ahx_ga_get_elites / ahx_ga_put_migrants remain for a
+ * host-mediated exchange on the other paths.
+ * ------------------------------------------------------------------------- */
+#define AHX_ISLAND_HANDLE_BYTES 64
+int ahx_ga_island_export(ahx_ctx *ctx, void *handle /* AHX_ISLAND_HANDLE_BYTES */);
+int ahx_ga_island_connect(ahx_ctx *ctx, const void *handles /* n_islands x AHX_ISLAND_HANDLE_BYTES */);
+int ahx_ga_island_connect_local(ahx_ctx **ctxs /* n_islands contexts of this process, island order */, int32_t n);
+/* CLM.GARun as an island model on n GPUs driven by the calling thread: ctxs[i] (one per GPU, the
+ * same group loaded in each) runs island i with params->npop individuals.  The callback gets the
+ * best tour over all islands; best_tour / stats describe the best island's hall of fame
+ * (stats->evaluations and device_ms: summed / max over islands). */
+int ahx_ga_run_islands(ahx_ctx **ctxs, int32_t n, const ahx_ga_params *params, int32_t L, const int32_t *init_tour,
+                       int32_t *best_tour, ahx_ga_stats *stats, ahx_ga_callback cb, void *user);
+/* Exchanges completed by the active run's kernel so far (0 without islands). */
+int64_t ahx_ga_island_epochs(ahx_ctx *ctx);
+
 /* Which generation loop the active run uses: 3 persistent kernel with the pair table streamed,
  * 2 persistent kernel with the table in shared memory, 1 two kernels per generation (32-bit
  * coordinates), 0 the fp64 kernels; -1 when no run is active. */
@@ -213,6 +270,25 @@ int ahx_ga_end(ahx_ctx *ctx);
  * (p,q; dir!=0 moves q to p), 3 MutInversion(p,q). */
 int ahx_mutate(ahx_ctx *ctx, int32_t L, const int32_t *tour_in, int32_t op, int32_t p, int32_t q,
                int32_t dir, int32_t *tour_out);
+
+/* Test hooks for the code the persistent GA kernel actually runs:
+ * ahx_mutate_remap     the same mutation through the kernel's operator code -- remap_of() turns the
+ *                      operator into a branch-free index map for the tour row and an elementwise map
+ *                      of the parent's stored coordinates (no prefix sum); coords_out (optional,
+ *                      n_tigs words) receives 2*mid (evaluate.go:120-126) of every contig of the
+ *                      child as derived that way.  Needs a loaded group and a full tour (L = n_tigs).
+ * ahx_test_plan_mutations  host-side evaluation of the kernels' mutation plan for offspring 0..n-1 of
+ *                      generation gen (eaopt's rng.Float64() < MutRate, then Tour.Mutate's draw,
+ *                      evaluate.go:221-232, randomTwoInts, evaluate.go:146-154):
+ *                      out[5*o..] = mutated, op (-1 none), p, q, dir.
+ * ahx_test_tournaments winners[2*pair + which] of the kernels' SelTournament{k} for pairs
+ *                      0..n_pairs-1 of generation gen over the fitness array fit[P] (device). */
+int ahx_mutate_remap(ahx_ctx *ctx, int32_t L, const int32_t *tour_in, int32_t op, int32_t p, int32_t q,
+                     int32_t dir, int32_t *tour_out, uint32_t *coords_out);
+int ahx_test_plan_mutations(uint64_t seed, int32_t island, int64_t gen, int32_t n, double mut_prob, int32_t L,
+                            int32_t *out /* n x 5 */);
+int ahx_test_tournaments(ahx_ctx *ctx, uint64_t seed, int32_t island, int64_t gen, int32_t P, const double *fit,
+                         int32_t k, int32_t n_pairs, int32_t *winners /* n_pairs x 2 */);
 
 /* ------------------------------------------------------------------------- *
  * Orientation heuristics, orientation.go:31-120.  signs (n_tigs bytes) is

@@ -618,14 +618,32 @@ static void orc_two_ints(orc_rng *r, int64_t n, int64_t *p, int64_t *q) {
   *p = orc_intn(r, n); *q = orc_intn(r, n);
   if (*p > *q) { int64_t x = *p; *p = *q; *q = x; }
 }
-/* evaluate.go:221-232 Tour.Mutate */
-static void orc_mutate(int64_t *t, int64_t L, orc_rng *r) {
+/* evaluate.go:221-232 Tour.Mutate: the draws (which operator, where), then the operator.
+ * op: 0 MutPermute, 1 MutSplice (p = k), 2 MutInsertion, 3 MutInversion, -1 nothing to do. */
+static void orc_mutate_draw(orc_rng *r, int64_t L, int *op, int64_t *p, int64_t *q, int *front) {
   double rd = orc_float64(r);
-  int64_t p, q;
-  if (rd < 0.2) { if (L <= 1) return; orc_two_ints(r, L, &p, &q); orc_mut_permute(t, L, p, q); }
-  else if (rd < .4) { int64_t k = orc_intn(r, L - 1) + 1; orc_mut_splice(t, L, k); }
-  else if (rd < .7) { orc_two_ints(r, L, &p, &q); if (p == q) return; orc_mut_insertion(t, L, p, q, orc_float64(r) < .5); }
-  else { orc_two_ints(r, L, &p, &q); orc_mut_inversion(t, L, p, q); }
+  *op = -1; *p = 0; *q = 0; *front = 0;
+  if (rd < 0.2) { if (L <= 1) return; orc_two_ints(r, L, p, q); *op = 0; }
+  else if (rd < .4) { *p = orc_intn(r, L - 1) + 1; *op = 1; }
+  else if (rd < .7) { orc_two_ints(r, L, p, q); *op = 2; if (*p == *q) return; *front = orc_float64(r) < .5; }
+  else { orc_two_ints(r, L, p, q); *op = 3; }
+}
+static void orc_mutate(int64_t *t, int64_t L, orc_rng *r) {
+  int op, front; int64_t p, q;
+  orc_mutate_draw(r, L, &op, &p, &q, &front);
+  if (op == 0) orc_mut_permute(t, L, p, q);
+  else if (op == 1) orc_mut_splice(t, L, p);
+  else if (op == 2) { if (p != q) orc_mut_insertion(t, L, p, q, front); }
+  else if (op == 3) orc_mut_inversion(t, L, p, q);
+}
+/* test support: n draws of Tour.Mutate's decisions for a tour of length L; out: n x 4 = op, p, q, front */
+void orc_mutate_sample(int64_t L, uint64_t seed, int64_t n, int64_t *out) {
+  orc_rng r; orc_rng_seed(&r, seed);
+  for (int64_t i = 0; i < n; i++) {
+    int op, front; int64_t p, q;
+    orc_mutate_draw(&r, L, &op, &p, &q, &front);
+    out[4 * i] = op; out[4 * i + 1] = p; out[4 * i + 2] = q; out[4 * i + 3] = front;
+  }
 }
 
 /* ---- GA: evaluate.go:258-315 wired onto an eaopt v0.4.2 emulation ---------- */
@@ -662,6 +680,12 @@ static void orc_tournament2(const double *fit, int64_t P, int k, orc_rng *r, int
     }
     if (round == 0) { *w1 = best; banned = best; } else *w2 = best;
   }
+}
+
+/* test support: n draws of SelTournament{k}.Apply(2, ...) over fit[P]; w: n x 2 winners */
+void orc_tournament_sample(const double *fit, int64_t P, int k, uint64_t seed, int64_t n, int64_t *w) {
+  orc_rng r; orc_rng_seed(&r, seed);
+  for (int64_t i = 0; i < n; i++) orc_tournament2(fit, P, k, &r, &w[2 * i], &w[2 * i + 1]);
 }
 
 /* Runs GARun for one phase starting from c's current tour; on return c's tour

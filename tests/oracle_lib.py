@@ -68,6 +68,8 @@ def lib():
         "orc_mut_insertion": (None, [p64, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
         "orc_mut_inversion": (None, [p64, C.c_int64, C.c_int64, C.c_int64]),
         "orc_shuffle": (None, [p64, C.c_int64, C.c_uint64]),
+        "orc_mutate_sample": (None, [C.c_int64, C.c_uint64, C.c_int64, p64]),
+        "orc_tournament_sample": (None, [pd, C.c_int64, C.c_int, C.c_uint64, C.c_int64, p64]),
         "orc_ga_run": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_int64, C.c_double, C.c_int, C.c_int, C.POINTER(GAResult)]),
         "orc_evaluate_q": (C.c_double, [vp]),
         "orc_evaluate_q_lookup": (C.c_double, [vp, p64]),
@@ -266,3 +268,18 @@ def mutate(tour, op, p=0, q=0, k=0, front=0):
     else:
         raise ValueError(op)
     return t
+
+
+def mutate_sample(L, seed, n):
+    """n draws of Tour.Mutate's decisions (evaluate.go:221-232): [n, 4] = op, p, q, front."""
+    out = np.zeros((n, 4), np.int64)
+    lib().orc_mutate_sample(L, seed, n, _p(out, C.c_int64))
+    return out
+
+
+def tournament_sample(fit, k, seed, n):
+    """n draws of eaopt SelTournament{k}.Apply(2): [n, 2] winners."""
+    f = np.ascontiguousarray(fit, np.float64)
+    out = np.zeros((n, 2), np.int64)
+    lib().orc_tournament_sample(_p(f, C.c_double), len(f), k, seed, n, _p(out, C.c_int64))
+    return out

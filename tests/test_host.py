@@ -165,7 +165,7 @@ fi
         ids.write_text("#Contig\tRECounts\tLength\n" + "".join("t%d\t1\t100\n" % i for i in range(n)))
         (tmp_path / ("g%d.clm" % g)).write_text("")
         groups.append((str(ids), str(tmp_path / ("g%d.clm" % g))))
-    res = farm.optimize_groups(groups, devices=[0, 1], binary=str(fake), persistent=persistent, log_dir=str(tmp_path))
+    res = farm.optimize_groups(groups, devices=[0, 1], binary=str(fake), persistent=persistent, log_dir=str(tmp_path), jobs=0)
     assert [r["group"] for r in res] == [0, 1, 2, 3] and all(r["ok"] for r in res)
     assert [r["n_contigs"] for r in res] == [5, 50, 20, 35]
     assert all(r["final_score"] is not None and r["device"] in (0, 1) for r in res)
@@ -177,5 +177,117 @@ fi
         assert len({c[2] for c in calls}) <= 2                                           # one process per device, reused
         # a worker that dies on a group fails that group only; the next group gets a fresh worker
         fake.write_text(fake.read_text().replace('while read re clm; do', 'while read re clm; do case "$re" in *g2.ids) exit 3;; esac;'))
-        res = farm.optimize_groups(groups, devices=[0], binary=str(fake), persistent=True)
+        res = farm.optimize_groups(groups, devices=[0], binary=str(fake), persistent=True, jobs=0)
         assert [r["ok"] for r in res] == [True, True, False, True]
+
+
+def test_farm_one_process_for_the_whole_box(tmp_path):
+    """jobs > 0: ONE `optimize-many --gpus G --jobs J` process (threads inside the host binary); the farm
+    passes the list file and the device set, and reads each group's block of stdout up to its
+    AHX_GROUP_DONE / AHX_GROUP_FAILED line, in completion order."""
+    import stat
+    from allhic_b200 import farm
+    fake = tmp_path / "fake-allhic"
+    fake.write_text("""#!/bin/sh
+echo "$@ | $CUDA_VISIBLE_DEVICES" > %s/argv.log
+i=0
+while read re clm; do lines="$lines $i:$re"; i=$((i+1)); done < "$2"
+for x in $(echo $lines | tr ' ' '\\n' | sort -r); do
+  i=${x%%%%:*}; re=${x#*:}
+  echo "Current iteration GA2-500: max_score=0.7$i"
+  if [ $i = 1 ]; then echo "AHX_GROUP_FAILED $i $re device=1 seconds=0.250"; else echo "AHX_GROUP_DONE $i $re device=$((i %% 2)) seconds=1.500"; fi
+done
+""" % tmp_path)
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    groups = []
+    for g, n in enumerate([5, 50, 20]):
+        ids = tmp_path / ("g%d.ids" % g)
+        ids.write_text("#Contig\tRECounts\tLength\n" + "".join("t%d\t1\t100\n" % i for i in range(n)))
+        groups.append((str(ids), str(tmp_path / "genome.clm")))
+    res = farm.optimize_groups(groups, devices=[2, 5], flags=("--ngen", "7"), binary=str(fake), jobs=3, log_dir=str(tmp_path))
+    argv, vis = (tmp_path / "argv.log").read_text().strip().split(" | ")
+    assert vis == "2,5" and argv.startswith("optimize-many ") and argv.endswith("--device 0 --gpus 2 --jobs 3 --ngen 7")
+    assert [r["ok"] for r in res] == [True, False, True] and [r["seq"] for r in res] == [2, 1, 0]
+    assert [r["device"] for r in res] == [2, 5, 2] and [r["final_score"] for r in res] == [0.70, 0.71, 0.72]
+    assert res[0]["seconds"] == 1.5 and [r["n_contigs"] for r in res] == [5, 50, 20]
+
+
+def _write_genome(tmp_path, group_ns, seed=5):
+    """A genome-wide CLM as `extract` leaves it for `pipeline` (allhic.go:285-293): the lines of all
+    groups interleaved in one file, plus inter-group pairs and contigs no group lists; one REfile per
+    group named the way partition writes them (`<prefix>.counts_<RE>.<k>g<j>.txt`, partition.go:205-215)."""
+    from allhic_b200 import synth
+    rng = np.random.default_rng(seed)
+    lines, refiles, names_all = [], [], []
+    k = len(group_ns)
+    for j, n in enumerate(group_ns):
+        g = synth.generate(n, 8800 + 13 * j + n, pairs_per_contig=150)
+        names = ["g%dc%04d" % (j, i) for i in range(n)]
+        names_all.append(names)
+        re_j = tmp_path / ("genome.counts_GATC.%dg%d.txt" % (k, j + 1))
+        with open(re_j, "w") as f:
+            f.write("#Contig\tRECounts\tLength\n")
+            for nm, s in zip(names, g["sizes"]):
+                f.write("%s\t%d\t%d\n" % (nm, max(1, int(s) // 256), int(s)))
+        refiles.append(str(re_j))
+        for a, b, blk in zip(g["pa"], g["pb"], g["dists"]):
+            for o, tag in enumerate(("++", "+-", "-+", "--")):
+                lines.append("%s%s %s%s\t%d\t%s\n" % (names[a], tag[0], names[b], tag[1], blk.shape[1], " ".join(map(str, blk[o].tolist()))))
+    for _ in range(300):                       # inter-group pairs and unplaced contigs: no group keeps them
+        ja, jb = rng.choice(k, 2, replace=False) if k > 1 else (0, 0)
+        a = names_all[ja][rng.integers(len(names_all[ja]))]
+        b = names_all[jb][rng.integers(len(names_all[jb]))] if rng.random() < 0.6 else "unplaced%03d" % rng.integers(50)
+        d = rng.integers(1, 500000, rng.integers(3, 9))
+        lines.append("%s+ %s-\t%d\t%s\n" % (a, b, len(d), " ".join(map(str, d))))
+    # repeated lines for one pair (last line wins for the oriented map, smallest SumLog for contacts)
+    a, b = names_all[0][0], names_all[0][1]
+    lines.append("%s+ %s+\t3\t100 200 300\n" % (a, b)); lines.append("%s+ %s+\t2\t90000 80000\n" % (a, b))
+    order = rng.permutation(len(lines) - 2)
+    lines = [lines[i] for i in order] + lines[-2:]
+    clm = tmp_path / "genome.clm"
+    clm.write_text("".join(lines))
+    return str(clm), refiles
+
+
+@pytest.mark.parametrize("nthreads", [1, 3, 0])
+def test_parse_groups_equals_per_group_parses(built_lib, tmp_path, nthreads):
+    """ahx_clm_parse_groups: ONE pass over a genome-wide CLM for all of its groups == k separate
+    NewCLM(clmfile, REfile_g) (clm.go:121, filter at clm.go:211-218) -- every table identical, and
+    identical to the oracle's parse of (clmfile, REfile_g)."""
+    import allhic_b200 as A
+    clmf, refiles = _write_genome(tmp_path, [40, 75, 23, 3])
+    shared = A.CLM.parse_groups(clmf, refiles, nthreads=nthreads)
+    assert len(shared) == 4
+    for g, re_g in enumerate(refiles):
+        single = A.CLM(clmf, re_g, nthreads=2)
+        ts, t1 = shared[g].tables(), single.tables()
+        assert set(ts) == set(t1)
+        for k in ts:
+            assert ts[k].shape == t1[k].shape and (ts[k] == t1[k]).all(), (g, k)
+        assert shared[g].names() == single.names() and (shared[g].sizes() == single.sizes()).all()
+        _check_clm_against_oracle(shared[g], O.OracleCLM(clmf, re_g))
+    assert len(shared[0].tables()["pa"]) > 50
+    # one group through the multi-group entry point is the plain parse
+    one = A.CLM.parse_groups(FIX_CLM, [FIX_IDS])[0]
+    ref = A.CLM(FIX_CLM, FIX_IDS)
+    for k, v in ref.tables().items():
+        assert (one.tables()[k] == v).all()
+    with pytest.raises(A.AhxError) as ei:
+        A.CLM.parse_groups(clmf, refiles[:2] + [str(tmp_path / "missing.txt")])
+    assert ei.value.code == -6
+
+
+def test_parse_groups_with_overlapping_refiles(built_lib, tmp_path):
+    """A contig listed by two REfiles (not something partition writes, but nothing forbids it): each
+    group still sees exactly the lines whose two contigs it lists."""
+    import allhic_b200 as A
+    clmf, refiles = _write_genome(tmp_path, [30, 30])
+    both = tmp_path / "both.txt"
+    both.write_text(open(refiles[0]).read() + "".join(l for l in open(refiles[1]) if not l.startswith("#")))
+    groups = [refiles[0], str(both), refiles[1]]
+    shared = A.CLM.parse_groups(clmf, groups, nthreads=2)
+    for g, re_g in enumerate(groups):
+        t1 = A.CLM(clmf, re_g).tables()
+        for k, v in shared[g].tables().items():
+            assert (v == t1[k]).all(), (g, k)
+    assert len(shared[1].tables()["pa"]) > len(shared[0].tables()["pa"]) + len(shared[2].tables()["pa"])   # + the inter-group pairs

@@ -96,6 +96,7 @@ SIGNATURES = {
     "ahx_probe_l2": (C.c_int, [_vp, C.c_uint64, _pd]),
     "ahx_launch_count": (C.c_int64, [_vp]),
     "ahx_sm_count": (C.c_int, [_vp]),
+    "ahx_last_device_ms": (C.c_double, [_vp]),
 }
 
 _lib = None

@@ -949,10 +949,15 @@ int ahx_eval_q(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tours, int32_t
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_signs.p, signs, static_cast<size_t>(P) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
   if (shared_tour && static_cast<size_t>(ctx->N) + 1024 <= ctx->smem_optin) {
     // one tour, many sign vectors (flipWhole / flipAll / batched orientation search): logs once, then lookups
-    if ((rc = eval_q_shared_tour(ctx, P, L, tours, ctx->d_signs.p, ctx->d_scores.p)) != AHX_OK) return rc;
-  } else if ((rc = launch_eval_q(ctx, ctx->d_tours.p, shared_tour, ctx->d_signs.p, P, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+    if ((rc = eval_q_shared_tour(ctx, P, L, tours, ctx->d_signs.p, ctx->d_scores.p)) != AHX_OK) return rc;   // brackets its kernels with ev_a / ev_b
+  } else {
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    if ((rc = launch_eval_q(ctx, ctx->d_tours.p, shared_tour, ctx->d_signs.p, P, L, ctx->d_scores.p, ctx->stream)) != AHX_OK) return rc;
+    AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+  }
   AHX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scores.p, sizeof(double) * P, cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  AHX_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_a, ctx->ev_b));
   return AHX_OK;
 }
 
@@ -1080,6 +1085,7 @@ int ahx_probe_l2(ahx_ctx *ctx, uint64_t bytes, double *gbs) {
 }
 
 int64_t ahx_launch_count(const ahx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+double ahx_last_device_ms(const ahx_ctx *ctx) { return ctx ? static_cast<double>(ctx->last_ms) : 0.0; }
 int ahx_sm_count(const ahx_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 
 }  // extern "C"

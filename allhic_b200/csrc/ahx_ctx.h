@@ -82,6 +82,8 @@ struct ahx_ctx {
   int sm_count = 0;
   size_t smem_optin = 0, l2_bytes = 0;
   int64_t launches = 0;
+  float last_ms = 0.f;            // CUDA-event time of the kernels of the last ahx_eval_q / ahx_flip_one call (ahx_last_device_ms)
+  bool timing = false;            // ev_a / ev_b bracket the kernels of the call in progress
 
   // ---- loaded linkage group
   bool loaded = false;

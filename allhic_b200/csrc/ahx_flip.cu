@@ -273,6 +273,7 @@ int eval_q_shared_tour(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tour, 
   if (rc != AHX_OK) return rc;
   const int E = static_cast<int>(ctx->E);
   AHX_CUDA(ctx, ctx->d_S4.reserve(static_cast<size_t>(std::max(E, 1)) * 4)); AHX_CUDA(ctx, ctx->d_pairinfo.reserve(std::max(E, 1)));
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
   if (E > 0) {
     pair_scores_kernel<<<(E + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pa.p, ctx->d_pb.p, ctx->d_slots.p, ctx->d_hist.p, E, ctx->d_pos.p,
                                                                  ctx->d_cum.p, ctx->d_S4.p, ctx->d_pairinfo.p);
@@ -282,6 +283,7 @@ int eval_q_shared_tour(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tour, 
   eval_q_lookup_kernel<<<P, kBlock, ctx->N, ctx->stream>>>(ctx->N, E, d_signs, ctx->d_pa.p, ctx->d_pb.p, ctx->d_S4.p, ctx->d_pairinfo.p, d_out);
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
   return AHX_OK;
 }
 
@@ -335,6 +337,7 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   AHX_CUDA(ctx, ctx->d_counts.reserve(2)); AHX_CUDA(ctx, ctx->d_signs.reserve(ctx->N)); AHX_CUDA(ctx, ctx->d_tours.reserve(Lm));
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_signs.p, signs, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
   if (L) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
   if (E > 0) {
     pair_scores_kernel<<<(E + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pa.p, ctx->d_pb.p, ctx->d_slots.p, ctx->d_hist.p, E, ctx->d_pos.p,
                                                                  ctx->d_cum.p, ctx->d_S4.p, ctx->d_pairinfo.p);
@@ -370,6 +373,7 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   }
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
+  AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
   long long counts[2] = {0, 0};
   double fs = 0.0;
   AHX_CUDA(ctx, cudaMemcpyAsync(signs, ctx->d_signs.p, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -378,6 +382,7 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   if (trace && L) AHX_CUDA(ctx, cudaMemcpyAsync(trace, ctx->d_trace.p, sizeof(double) * 2 * L, cudaMemcpyDeviceToHost, ctx->stream));
   if (step_accepted && L) AHX_CUDA(ctx, cudaMemcpyAsync(step_accepted, ctx->d_stepacc.p, L, cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  AHX_CUDA(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev_a, ctx->ev_b));
   if (final_score) *final_score = fs;
   if (n_accepts) *n_accepts = counts[0];
   if (n_rejects) *n_rejects = counts[1];

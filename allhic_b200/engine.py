@@ -240,7 +240,7 @@ class Engine:
     def mutate_remap(self, tour, op, p=0, q=0, dir=0):
         """The same mutation through the persistent GA kernel's operator code; returns (child tour, child 2*mid per contig)."""
         t = np.ascontiguousarray(tour, np.int32)
-        out = np.empty_like(t); x = np.empty(len(t), np.uint32)
+        out = np.empty_like(t); x = np.empty(self.N, np.uint32)
         self._ck(self._l.ahx_mutate_remap(self.h, len(t), _ptr(t), op, p, q, dir, _ptr(out), _ptr(x)))
         return out, x
 
@@ -291,6 +291,10 @@ class Engine:
 
     def launch_count(self):
         return self._l.ahx_launch_count(self.h)
+
+    def last_device_ms(self):
+        """CUDA-event time of the kernels of the last eval_q / flip_one call."""
+        return float(self._l.ahx_last_device_ms(self.h))
 
     def sm_count(self):
         return self._l.ahx_sm_count(self.h)

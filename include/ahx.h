@@ -313,6 +313,9 @@ int ahx_probe_l2(ahx_ctx *ctx, uint64_t bytes, double *gbs);
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t ahx_launch_count(const ahx_ctx *ctx);
 int ahx_sm_count(const ahx_ctx *ctx);
+/* CUDA-event time (ms) of the kernels of the last ahx_eval_q / ahx_flip_one call on this context:
+ * host<->device copies excluded (bench.py's roofline legs of the orientation phase). */
+double ahx_last_device_ms(const ahx_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -92,6 +92,7 @@ SIGNATURES = {
     "ahx_flip_whole": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _pd, _p32]),
     "ahx_flip_one": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _p64, _p64, _vp, _vp, _p32]),
     "ahx_flip_all": (C.c_int, [_vp, C.c_int32, _vp, _vp, _pd, _pd, _p32]),
+    "ahx_flip_all_info": (C.c_int, [_vp, _pd, _p32, _p32, _p32]),
     "ahx_probe_fp64": (C.c_int, [_vp, _pd, _pd]),
     "ahx_probe_l2": (C.c_int, [_vp, C.c_uint64, _pd]),
     "ahx_launch_count": (C.c_int64, [_vp]),

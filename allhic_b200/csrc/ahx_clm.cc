@@ -133,6 +133,7 @@ struct ahx_clm {
   bool finalized = false;
   std::vector<int32_t> pa, pb, nl, slots, hist;
   std::vector<int8_t> strand;
+  std::vector<double> diag;   // O[a][a] from self-pair lines (empty when there are none: `extract` never writes them)
 
   void apply_contact(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, double mean_dist, int64_t nlinks) {
     finalized = false;
@@ -461,8 +462,13 @@ int ahx_clm_finalize(ahx_clm *clm) {
   // M(): P[ai][bi] = P[bi][ai] = nlinks per map entry (clm.go:440-445).  Go's map
   // order is random; when both (a,b) and (b,a) keys exist (never written by
   // `extract`, extract.go:477-481) the later-inserted key wins here.
+  clm->diag.clear();
   for (auto &c : clm->contacts) {
-    if (c.ai == c.bi) continue;
+    if (c.ai == c.bi) {   // a self-pair line: never read by M() / Q() (i < j are distinct contigs), but O() puts it on the diagonal (SetSym(a, a, ...))
+      if (clm->diag.empty()) clm->diag.assign(clm->n, 0.0);
+      clm->diag[c.ai] = static_cast<double>(c.strand) * static_cast<double>(c.nlinks);
+      continue;
+    }
     const int64_t e = row_of(c.ai, c.bi);
     if (c.nlinks > INT32_MAX) { set_global_error("nlinks exceeds int32"); return AHX_ERR_ARG; }
     clm->nl[e] = static_cast<int32_t>(c.nlinks);
@@ -526,6 +532,7 @@ ClmView view_of(const ahx_clm *clm) {
   v.pa = clm->pa.data(); v.pb = clm->pb.data(); v.nl = clm->nl.data(); v.strand = clm->strand.data();
   v.slots = clm->slots.data(); v.H = static_cast<int64_t>(clm->hist.size() / AHX_BB); v.hist = clm->hist.data();
   v.finalized = clm->finalized;
+  v.diag = clm->diag.empty() ? nullptr : clm->diag.data();
   return v;
 }
 }  // namespace ahx

@@ -83,7 +83,6 @@ struct ahx_ctx {
   size_t smem_optin = 0, l2_bytes = 0;
   int64_t launches = 0;
   float last_ms = 0.f;            // CUDA-event time of the kernels of the last ahx_eval_q / ahx_flip_one call (ahx_last_device_ms)
-  bool timing = false;            // ev_a / ev_b bracket the kernels of the call in progress
 
   // ---- loaded linkage group
   bool loaded = false;
@@ -110,6 +109,8 @@ struct ahx_ctx {
   std::vector<int64_t> h_sizes;
   std::vector<int32_t> h_pa, h_pb, h_nl;
   std::vector<int8_t> h_strand;
+  std::vector<double> h_diag;              // O[a][a] of self-pair CLM lines (empty: none)
+  ahx::EigInfo eig{};                      // how the last flipAll's eigenvector was obtained
   std::vector<int32_t> h_deg;              // pairs touching each contig (host copy of the CSR row lengths)
 
   // ---- scratch
@@ -136,6 +137,7 @@ struct ahx_ctx {
   ahx::DevBuf<ahx::GaState> d_state;
   ahx::DevBuf<int32_t> d_plan;         // per-offspring parent/info/p/q, mutated list, count
   bool ga_x32 = false;
+  bool ga_global = false;              // rows and coordinates in global memory (groups beyond the shared-memory kernels)
   int ga_T = 1;
   bool ga_res = false;                 // persistent resident-table kernel (ahx_ga_res.cuh): d_pop[0] is a pool of 2P rows
   bool ga_stream = false;              // ... with the pair table streamed through a ring

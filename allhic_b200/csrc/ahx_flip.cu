@@ -279,7 +279,7 @@ int eval_q_shared_tour(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tour, 
                                                                  ctx->d_cum.p, ctx->d_S4.p, ctx->d_pairinfo.p);
     ctx->launches++;
   }
-  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_q_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->N));
+  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_q_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
   eval_q_lookup_kernel<<<P, kBlock, ctx->N, ctx->stream>>>(ctx->N, E, d_signs, ctx->d_pa.p, ctx->d_pb.p, ctx->d_S4.p, ctx->d_pairinfo.p, d_out);
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
@@ -359,14 +359,14 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
                                                                ctx->d_rec_o.p);
       ctx->launches++;
     }
-    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stream)));
+    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
     flip_one_stream_kernel<<<1, kBlock, smem_stream, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_S4.p,
                                                                 ctx->d_pairinfo.p, ctx->d_step_off.p, ctx->d_rec_d.p, ctx->d_rec_d.p + nrec, ctx->d_rec_o.p,
                                                                 ctx->d_trace.p, ctx->d_stepacc.p, ctx->d_counts.p, d_final);
     AHX_CUDA(ctx, cudaGetLastError());
     AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `off` is stack-owned
   } else {
-    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->N));
+    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
     flip_one_kernel<<<1, 32, ctx->N, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_adj_ptr.p,
                                                    ctx->d_adj_e.p, ctx->d_S4.p, ctx->d_pairinfo.p, ctx->d_trace.p, ctx->d_stepacc.p,
                                                    ctx->d_counts.p, d_final);
@@ -399,9 +399,13 @@ int ahx_flip_all(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   // eigenvector of the largest eigenvalue gives the sign pattern (:42-52).
   std::vector<double> w(ctx->E), v(ctx->N);
   for (int64_t e = 0; e < ctx->E; ++e) w[e] = static_cast<double>(ctx->h_strand[e]) * static_cast<double>(ctx->h_nl[e]);
-  top_eigenvector(ctx->N, ctx->E, ctx->h_pa.data(), ctx->h_pb.data(), w.data(), v.data());
+  top_eigenvector(ctx->N, ctx->E, ctx->h_pa.data(), ctx->h_pb.data(), w.data(), ctx->h_diag.empty() ? nullptr : ctx->h_diag.data(), v.data(), &ctx->eig);
   std::vector<uint8_t> cand(ctx->N);
-  for (int32_t i = 0; i < ctx->N; ++i) cand[i] = v[i] < 0 ? '-' : '+';
+  // `v < 0 => '-'` (orientation.go:47-51); components that are zero up to rounding (contigs without any contact,
+  // the weaker components of a disconnected graph) are '+', as an exact zero is in the reference
+  double vmax = 0.0;
+  for (int32_t i = 0; i < ctx->N; ++i) vmax = std::max(vmax, std::fabs(v[i]));
+  for (int32_t i = 0; i < ctx->N; ++i) cand[i] = v[i] < -1e-12 * vmax ? '-' : '+';
   double sc[2];
   if ((rc = eval_q_two(ctx, L, tour, signs, cand.data(), sc)) != AHX_OK) return rc;
   const bool accept = !(sc[1] < sc[0]);                                           // orientation.go:57
@@ -409,6 +413,15 @@ int ahx_flip_all(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   if (old_score) *old_score = sc[0];
   if (new_score) *new_score = sc[1];
   if (accepted) *accepted = accept ? 1 : 0;
+  return AHX_OK;
+}
+
+int ahx_flip_all_info(const ahx_ctx *ctx, double *residual, int32_t *converged, int32_t *dense, int32_t *matvecs) {
+  if (!ctx) return AHX_ERR_ARG;
+  if (residual) *residual = ctx->eig.residual;
+  if (converged) *converged = ctx->eig.converged ? 1 : 0;
+  if (dense) *dense = ctx->eig.dense ? 1 : 0;
+  if (matvecs) *matvecs = ctx->eig.matvecs;
   return AHX_OK;
 }
 

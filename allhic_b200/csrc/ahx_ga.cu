@@ -435,6 +435,69 @@ ga_apply_kernel(GaDev g, GaPlan pl, int n_eval_ctas, const uint32_t *__restrict_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Generation for groups too large for any kernel that keeps per-contig arrays in shared memory
+// (more than ~26 000 contigs): ga_plan_kernel, then ga_offspring_kernel (Tour.Clone + Tour.Mutate
+// row by row in global memory), then the evaluate launcher on the mutated rows (it falls back to
+// coordinates in global memory by itself, eval_m_sparse_kernel<XGLOBAL>), then ga_finish_kernel
+// (hall of fame + bookkeeping).  One small read-back per generation tells the host how many rows
+// were mutated; a generation of such a group takes milliseconds, the read-back microseconds.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ga_offspring_kernel(GaDev g, GaPlan pl) {
+  GaState *st = g.st;
+  if (*reinterpret_cast<volatile int *>(&st->stop)) return;
+  const long long gen = *reinterpret_cast<volatile long long *>(&st->gen);
+  const int cur = static_cast<int>(gen & 1), o = blockIdx.x;
+  const int info = pl.info[o], op = (info >> 16) & 1 ? static_cast<int>(static_cast<signed char>(info & 0xff)) : -1;
+  const int dir = (info >> 8) & 1, p = pl.p[o], q = pl.q[o];
+  const int *src = g.pop[cur] + static_cast<size_t>(pl.parent[o]) * g.L;
+  int *dst = g.pop[cur ^ 1] + static_cast<size_t>(o) * g.L;
+  for (int i = threadIdx.x; i < g.L; i += blockDim.x) dst[i] = src[mut_source(op, p, q, dir, g.L, i)];
+}
+
+__global__ void __launch_bounds__(1024) ga_finish_kernel(GaDev g, const int *__restrict__ nmut) {
+  __shared__ double sf[32];
+  __shared__ int si[32];
+  __shared__ int s_best, s_flag;
+  __shared__ double s_bestfit;
+  GaState *st = g.st;
+  if (*reinterpret_cast<volatile int *>(&st->stop)) return;
+  const long long gen = st->gen;
+  const int cur = static_cast<int>(gen & 1), tid = threadIdx.x;
+  const double *fitn = g.fit[cur ^ 1];
+  const int *popn = g.pop[cur ^ 1];
+  double bf = __longlong_as_double(0x7ff0000000000000LL); int bi = 0x7fffffff;
+  for (int i = tid; i < g.P; i += blockDim.x) { const double f = fitn[i]; if (f < bf) { bf = f; bi = i; } }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const double of = __shfl_down_sync(0xffffffffu, bf, d);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, d);
+    if (of < bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+  }
+  if ((tid & 31) == 0) { sf[tid >> 5] = bf; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+      if (sf[w] < bf || (sf[w] == bf && si[w] < bi)) { bf = sf[w]; bi = si[w]; }
+    s_best = bi; s_bestfit = bf; s_flag = bf < st->hof_fit;        // updateHallOfFame keeps the best ever
+  }
+  __syncthreads();
+  if (s_flag) {
+    const int *best_row = popn + static_cast<size_t>(s_best) * g.L;
+    for (int i = tid; i < g.L; i += blockDim.x) g.hof[i] = best_row[i];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const long long ngen_now = gen + 1;
+    if (s_flag) { st->hof_fit = s_bestfit; st->updated = ngen_now; }
+    st->best_idx = s_best;
+    st->evals += *nmut;
+    if (ngen_now - st->updated > g.ngen || ngen_now >= g.max_gens) st->stop = 1;   // evaluate.go:304-306
+    __threadfence();
+    st->gen = ngen_now;
+  }
+}
+
 __global__ void ga_init_kernel(GaDev g, const int *__restrict__ init, const double *__restrict__ f0) {
   const size_t total = static_cast<size_t>(g.P) * g.L;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -581,7 +644,7 @@ template <int T, typename Coo>
 static cudaError_t launch_apply(ahx_ctx *ctx, const GaDev &g, const GaPlan &pl, cudaStream_t s) {
   auto kern = ga_apply_kernel<T, Coo>;
   const size_t smem = eval_x32_smem_bytes(T, ctx->coo16, ctx->N, ctx->ga_L);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
   if (e != cudaSuccess) return e;
   const int n_eval = (g.P + T - 1) / T;
   const int n_copy = std::min(g.P, ctx->sm_count * 4);
@@ -678,7 +741,7 @@ static GaRes make_res(ahx_ctx *ctx) {
 template <int T, bool STREAM, bool SUB>
 static cudaError_t launch_persist_ts(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
   auto kern = ga_persist_kernel<T, STREAM, SUB>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->ga_smem));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
   const bool scaled = static_cast<uint64_t>(ctx->N) * 4u * T <= 65535u;   // the table of byte offsets exists (ahx_load)
@@ -727,7 +790,29 @@ __global__ void set_rows_kernel(int *__restrict__ rowof, const int *__restrict__
   if (i < n) rowof[idx[i]] = rows[i];
 }
 
+static int read_state(ahx_ctx *ctx, GaState *hs);
+
 static int launch_generation(ahx_ctx *ctx, const GaDev &g, cudaStream_t s) {
+  if (ctx->ga_global) {
+    GaPlan pl{ctx->d_plan.p, ctx->d_plan.p + g.P, ctx->d_plan.p + 2 * static_cast<size_t>(g.P), ctx->d_plan.p + 3 * static_cast<size_t>(g.P),
+              ctx->d_plan.p + 4 * static_cast<size_t>(g.P), ctx->d_plan.p + 5 * static_cast<size_t>(g.P)};
+    GaState hs{};
+    int rc = read_state(ctx, &hs);
+    if (rc != AHX_OK || hs.stop) return rc;
+    const int cur = static_cast<int>(hs.gen & 1);
+    ga_plan_kernel<<<(g.P + 255) / 256, 256, 0, s>>>(g, pl, reinterpret_cast<unsigned int *>(ctx->d_plan.p + 5 * static_cast<size_t>(g.P) + 1));
+    ga_offspring_kernel<<<g.P, 256, 0, s>>>(g, pl);
+    ctx->launches += 2;
+    AHX_CUDA(ctx, cudaGetLastError());
+    int32_t *nmut_pin = reinterpret_cast<int32_t *>(static_cast<unsigned char *>(ctx->h_pin) + 2048);
+    AHX_CUDA(ctx, cudaMemcpyAsync(nmut_pin, pl.nmut, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    AHX_CUDA(ctx, cudaStreamSynchronize(s));
+    if ((rc = launch_eval_m_sparse(ctx, ctx->d_pop[cur ^ 1].p, nullptr, pl.mlist, *nmut_pin, g.L, ctx->d_fit[cur ^ 1].p, s)) != AHX_OK) return rc;
+    ga_finish_kernel<<<1, 1024, 0, s>>>(g, pl.nmut);
+    ctx->launches++;
+    AHX_CUDA(ctx, cudaGetLastError());
+    return AHX_OK;
+  }
   if (ctx->ga_x32) {
     GaPlan pl{ctx->d_plan.p, ctx->d_plan.p + g.P, ctx->d_plan.p + 2 * static_cast<size_t>(g.P), ctx->d_plan.p + 3 * static_cast<size_t>(g.P),
               ctx->d_plan.p + 4 * static_cast<size_t>(g.P), ctx->d_plan.p + 5 * static_cast<size_t>(g.P)};
@@ -853,7 +938,7 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
     AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1)); AHX_CUDA(ctx, ctx->d_gbar.reserve(2));
     AHX_CUDA(ctx, ctx->d_used.reserve(3 * ((2 * static_cast<size_t>(prm->npop) + 31) / 32 * 32))); AHX_CUDA(ctx, ctx->d_gmin.reserve(3)); AHX_CUDA(ctx, ctx->d_gmask.reserve(2 * ((static_cast<size_t>(prm->npop) + 31) / 32)));
     AHX_CUDA(ctx, ctx->d_tours.reserve(L)); AHX_CUDA(ctx, ctx->d_scores.reserve(1));
-    ctx->ga_ms = 0.0; ctx->ga_x32 = false;
+    ctx->ga_ms = 0.0; ctx->ga_x32 = false; ctx->ga_global = false;
     ctx->ga_active_set.assign(init_tour, init_tour + L);
     std::sort(ctx->ga_active_set.begin(), ctx->ga_active_set.end());
     AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, init_tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
@@ -874,15 +959,18 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
   ctx->ga_x32 = use_x32(ctx, L);
   ctx->ga_T = ctx->ga_x32 ? ga_T(ctx) : 1;
   if (const char *env = getenv("AHX_GA_T")) { const int t = atoi(env); if (ctx->ga_x32 && (t == 1 || t == 2 || t == 4)) ctx->ga_T = t; }
-  if (ctx->ga_x32) {
+  const size_t smem = eval_m_smem_bytes(1, ctx->N, L);
+  // neither fallback kernel can keep its per-contig arrays in shared memory (more than ~26 000 contigs): rows and
+  // coordinates stay in global memory (ga_offspring_kernel + the evaluate launcher + ga_finish_kernel)
+  ctx->ga_global = (!ctx->ga_x32 && smem + 2048 > ctx->smem_optin) || (getenv("AHX_GA_GLOBAL") && atoi(getenv("AHX_GA_GLOBAL")));
+  if (ctx->ga_global) ctx->ga_x32 = false;
+  if (ctx->ga_x32 || ctx->ga_global) {
     AHX_CUDA(ctx, ctx->d_plan.reserve(5 * static_cast<size_t>(prm->npop) + 2));
     AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_plan.p + 5 * static_cast<size_t>(prm->npop), 0, 2 * sizeof(int32_t), ctx->stream));
   }
-  const size_t smem = eval_m_smem_bytes(1, ctx->N, L);
-  if (!ctx->ga_x32 && smem + 2048 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_ga_begin: group too large for the generation kernel's shared memory");
-  if (ctx->ga_x32) { /* attributes are set per launch */ }
-  else if (ctx->coo16) AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  else AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (ctx->ga_x32 || ctx->ga_global) { /* attributes are set per launch */ }
+  else if (ctx->coo16) AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  else AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
   ctx->ga_ms = 0.0;
   const size_t PL = static_cast<size_t>(prm->npop) * L;
   for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_pop[i].reserve(PL)); AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); }

@@ -19,13 +19,17 @@ struct ClmView {
   int32_t n; const int64_t *sizes; int64_t E;
   const int32_t *pa, *pb, *nl; const int8_t *strand; const int32_t *slots;
   int64_t H; const int32_t *hist; bool finalized;
+  const double *diag;   // O[a][a] = strandedness * nlinks of self-pair CLM lines (orientation.go:124-132), or nullptr
 };
 ClmView view_of(const ahx_clm *clm);
 
 // Largest-eigenvalue eigenvector of the sparse symmetric matrix
-// O[a][b] = O[b][a] = w[e] (orientation.go:124-132), Lanczos with full
-// reorthogonalisation.  v: n doubles.  Returns the Ritz value.
-double top_eigenvector(int32_t n, int64_t E, const int32_t *pa, const int32_t *pb, const double *w, double *v);
+// O[a][b] = O[b][a] = w[e], O[a][a] = diag[a] (orientation.go:124-132; diag may be null): Lanczos with
+// full reorthogonalisation, stopped as soon as the top Ritz pair has converged; dense Jacobi for small
+// groups and as the fallback when Lanczos does not converge.  v: n doubles.  Returns the Ritz value.
+struct EigInfo { bool converged = false, dense = false; double residual = 0.0; int restarts = 0, matvecs = 0; };
+double top_eigenvector(int32_t n, int64_t E, const int32_t *pa, const int32_t *pb, const double *w, const double *diag, double *v,
+                       EigInfo *info = nullptr);
 
 }  // namespace ahx
 

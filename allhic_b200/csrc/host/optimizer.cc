@@ -112,6 +112,9 @@ const char *CLM::flipAll() {
   check(ahx_flip_all(ctx_, Tour.Len(), Tour.Tigs.data(), Signs.data(), &a, &b, &acc), "ahx_flip_all");
   const char *tag = acc ? ACCEPT : REJECT;
   flipLog("FLIPALL", a, b, tag);
+  double resid = 0; int32_t conv = 1;
+  ahx_flip_all_info(ctx_, &resid, &conv, nullptr, nullptr);
+  if (!conv) logNotice("FLIPALL: the eigensolver stopped at residual %.3g (near-degenerate top eigenvalues); flipWhole / flipOne refine the signs", resid);
   return tag;
 }
 

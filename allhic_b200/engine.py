@@ -278,6 +278,12 @@ class Engine:
         self._ck(self._l.ahx_flip_all(self.h, len(t), _ptr(t), _ptr(s), C.byref(a), C.byref(b), C.byref(acc)))
         return s, bool(acc.value), a.value, b.value
 
+    def flip_all_info(self):
+        """dict(residual, converged, dense, matvecs) of the last flip_all's eigenvector computation."""
+        r = C.c_double(); c = C.c_int32(); d = C.c_int32(); m = C.c_int32()
+        self._ck(self._l.ahx_flip_all_info(self.h, C.byref(r), C.byref(c), C.byref(d), C.byref(m)))
+        return dict(residual=r.value, converged=bool(c.value), dense=bool(d.value), matvecs=m.value)
+
     # ---- probes
     def probe_fp64(self):
         a = C.c_double(); b = C.c_double()

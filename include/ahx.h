@@ -261,7 +261,8 @@ int64_t ahx_ga_island_epochs(ahx_ctx *ctx);
 
 /* Which generation loop the active run uses: 3 persistent kernel with the pair table streamed,
  * 2 persistent kernel with the table in shared memory, 1 two kernels per generation (32-bit
- * coordinates), 0 the fp64 kernels; -1 when no run is active. */
+ * coordinates), 0 the fp64 kernels (per-contig arrays in shared memory, or -- groups beyond ~26 000
+ * contigs -- tour rows and coordinates in global memory: any group size runs); -1 when no run is active. */
 int ahx_ga_kernel(ahx_ctx *ctx);
 int ahx_ga_end(ahx_ctx *ctx);
 
@@ -304,6 +305,13 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
                  int32_t *accepted);
 int ahx_flip_all(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs,
                  double *old_score, double *new_score, int32_t *accepted);
+
+/* How the last ahx_flip_all on this context found the top eigenvector of O (orientation.go:33-44): relative
+ * residual |O v - lambda v| / |lambda| of the returned vector (0 for the dense decomposition), *dense = 1
+ * when the dense Jacobi path ran (groups of <= 48 contigs, or Lanczos not converged and <= 1500 contigs),
+ * *converged = 0 when Lanczos stopped at its restart limit (near-degenerate top eigenvalues on a large group:
+ * the sign pattern may then differ from a dense decomposition's; the host logs it). */
+int ahx_flip_all_info(const ahx_ctx *ctx, double *residual, int32_t *converged, int32_t *dense, int32_t *matvecs);
 
 /* ------------------------------------------------------------------------- *
  * Roofline probes (measured live by bench.py).

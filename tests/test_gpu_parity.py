@@ -350,7 +350,7 @@ def test_ga_elites_and_migrants(fix):
     eng.ga_end()
 
 
-@pytest.mark.parametrize("path", ["persistent", "persistent-streamed", "two-kernel", "fp64"])
+@pytest.mark.parametrize("path", ["persistent", "persistent-streamed", "two-kernel", "fp64", "global"])
 @pytest.mark.parametrize("gaT", ["1", "2", "4"])
 def test_ga_population_is_consistent_on_every_path(syn, path, gaT, monkeypatch):
     """After many generations every individual must still be what its stored state says:
@@ -365,6 +365,10 @@ def test_ga_population_is_consistent_on_every_path(syn, path, gaT, monkeypatch):
     if path == "fp64":
         monkeypatch.setenv("AHX_EVAL_FP64", "1")
         monkeypatch.setenv("AHX_EVAL_RES", "0")
+    if path == "global":        # what groups beyond ~26 000 contigs run: rows and coordinates in global memory
+        if gaT != "1":
+            pytest.skip("one variant")
+        monkeypatch.setenv("AHX_GA_GLOBAL", "1")
     monkeypatch.setenv("AHX_GA_T", gaT)
     rng = np.random.default_rng(77)
     init = rng.permutation(clm.N).astype(np.int32)
@@ -518,6 +522,82 @@ def test_flip_all_matches_dense_eigensolver(fix):
     if not (same or comp):
         # near-degenerate top eigenvalues: accept any pattern that scores as well
         assert b >= b_o - 1e-9 * abs(b_o)
+
+
+@pytest.mark.parametrize("n", [30, 400])
+def test_flip_all_sign_pattern_vs_jacobi_oracle(built_lib, tmp_path, n):
+    """flipAll at sizes on both sides of the dense/Lanczos switch (<= 48 contigs: dense Jacobi like the reference's
+    mat64.EigenSym; above: sparse Lanczos): the sign pattern against the oracle's dense Jacobi decomposition of O
+    (orientation.go:31-64), strand-mixed contacts, and the solver's own convergence report."""
+    import allhic_b200 as A
+    from allhic_b200 import synth
+    g = synth.generate(n, 9500 + n, pairs_per_contig=200)
+    ids, clmf = synth.write(g, str(tmp_path / ("o%d" % n)))
+    # flip a third of the contigs: rewrite the CLM with swapped orientation tags for those contigs, so that the
+    # kept contact of a pair (smallest SumLog, clm.go:229-236) has mixed strandedness and O has negative entries
+    rng = np.random.default_rng(n)
+    flipped = set(np.flatnonzero(rng.random(n) < 0.33).tolist())
+    rr = {"+": "-", "-": "+"}
+    out = []
+    for row in open(clmf):
+        w = row.rstrip("\n").split("\t")
+        at, bt = w[0].split(" ")
+        a, b = int(at[3:-1]), int(bt[3:-1])
+        ao = rr[at[-1]] if a in flipped else at[-1]
+        bo = rr[bt[-1]] if b in flipped else bt[-1]
+        out.append("%s%s %s%s\t%s\t%s\n" % (at[:-1], ao, bt[:-1], bo, w[1], w[2]))
+    open(clmf, "w").write("".join(out))
+    clm = A.CLM(clmf, ids); eng = A.Engine(0); eng.load(clm); orc = O.OracleCLM(clmf, ids)
+    assert (clm.tables()["strand"] < 0).any() and (clm.tables()["strand"] > 0).any()
+    t = rng.permutation(n).astype(np.int32)
+    plus = np.full(n, ord('+'), np.uint8)
+    orc.set_tour(t); orc.set_signs(plus)
+    acc_o, a_o, b_o = orc.flip_all()
+    s, acc, a, b = eng.flip_all(t, plus)
+    info = eng.flip_all_info()
+    assert info["converged"] and info["dense"] == (n <= 48) and info["residual"] <= 1e-9
+    assert close(a, a_o) and acc == acc_o
+    so = orc.signs()
+    assert (s == so).all() or (s != so).all()              # the eigenvector's global sign is arbitrary (flipWhole settles it)
+    orc.set_signs(s)
+    assert close(b, orc.evaluate_q())
+    # the recovered pattern separates the flipped contigs from the others
+    truth = np.array([ord('-') if i in flipped else ord('+') for i in range(n)], np.uint8)
+    agree = (s == truth).mean()
+    assert agree > 0.95 or agree < 0.05
+    eng.close()
+
+
+def test_flip_all_self_pair_lines_reach_the_diagonal_of_O(built_lib, tmp_path):
+    """A CLM line naming one contig twice lands on the diagonal of O in the reference (SetSym(a, a, ...),
+    orientation.go:124-132) and so changes flipAll's eigenvector; M() and Q() never read it."""
+    import allhic_b200 as A
+    rng = np.random.default_rng(3)
+    n = 9
+    ids = tmp_path / "d.ids"; clmf = tmp_path / "d.clm"
+    ids.write_text("".join("c%d\t1\t%d\n" % (i, rng.integers(1000, 90000)) for i in range(n)))
+    lines = []
+    for a in range(n):
+        for b in range(a + 1, n):
+            if rng.random() < 0.6:
+                d = rng.integers(1, 200000, rng.integers(3, 9))
+                lines.append("c%d%s c%d%s\t%d\t%s\n" % (a, "+-"[rng.integers(2)], b, "+-"[rng.integers(2)], len(d), " ".join(map(str, d))))
+    base = "".join(lines)
+    t = rng.permutation(n).astype(np.int32)
+    plus = np.full(n, ord('+'), np.uint8)
+    pats = []
+    for extra in ("", "c2+ c2-\t400\t%s\n" % " ".join(["5000"] * 400)):
+        clmf.write_text(base + extra)
+        clm = A.CLM(str(clmf), str(ids)); eng = A.Engine(0); eng.load(clm); orc = O.OracleCLM(str(clmf), str(ids))
+        orc.set_tour(t); orc.set_signs(plus)
+        orc.flip_all()
+        s, acc, a, b = eng.flip_all(t, plus)
+        so = orc.signs()
+        assert (s == so).all() or (s != so).all(), extra[:8]
+        assert close(eng.eval_m(t)[0], orc.evaluate(t.astype(np.int64)))          # M() never reads the diagonal
+        pats.append(orc.top_eigvec()[0].copy())
+        eng.close()
+    assert not np.allclose(np.abs(pats[0]), np.abs(pats[1]))   # the diagonal entry did change the eigenvector
 
 
 # ---------------------------------------------------------------- full-size properties

@@ -133,6 +133,76 @@ def test_island_exchange_world2_gloo():
     assert s0 == -float(np.count_nonzero(np.array(t0) != np.arange(24)))     # reported score belongs to the reported tour
 
 
+class ToyDeviceEngine(ToyEngine):
+    """Stand-in for an engine whose exchange runs on the device (libahx's persistent GA kernel): IslandGA then
+    only wires the islands -- export a 64-byte mailbox handle, all-gather, connect -- and advances them."""
+
+    def ga_begin(self, init, prm):
+        super().ga_begin(init, prm)
+        assert prm.n_islands == dist.get_world_size() and prm.migrate_every == 5 and prm.n_elite == 2
+        self.connected, self.epochs = None, 0
+
+    def ga_island_export(self):
+        h = np.zeros(64, np.uint8)
+        h[:8] = np.frombuffer(np.int64(1000 + self.island).tobytes(), np.uint8)
+        return h
+
+    def ga_island_connect(self, handles):
+        handles = np.asarray(handles)
+        assert handles.shape == (dist.get_world_size(), 64) and handles.dtype == np.uint8
+        self.connected = [int(np.frombuffer(handles[r, :8].tobytes(), np.int64)[0]) for r in range(handles.shape[0])]
+
+    def ga_island_epochs(self):
+        return self.epochs
+
+    def ga_advance(self, n):
+        assert self.connected == [1000 + r for r in range(dist.get_world_size())], "advance before the islands were wired"
+        st = super().ga_advance(n)
+        self.epochs = self.gen // 5
+        return st
+
+
+class _PrmDev(_Prm):
+    n_islands, migrate_every, n_elite = 1, 50, 2
+
+
+def _worker_device(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = 24
+        init = np.random.default_rng(5).permutation(L).astype(np.int32)
+        eng = ToyDeviceEngine(seed=200 + rank)
+        ga = IslandGA(eng, init, _PrmDev(), migrate_every=5, n_elite=2)
+        assert ga.mode == "device" and ga.params.island == rank and ga.params.n_islands == world
+        tour, score, st = ga.run(60)
+        ga.close()
+        q.put((rank, tour.tolist(), score, ga.exchanges, int(st.generations)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_island_device_mode_wiring_world2_gloo():
+    """The product path's host side: every island exports its mailbox handle, the handles are all-gathered in
+    island order and connected before the first advance; one advance call runs the whole period (the exchange
+    is the kernel's business); the global best is replicated on every rank."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_device, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    (r0, t0, s0, x0, g0), (r1, t1, s1, x1, g1) = res
+    assert (r0, r1) == (0, 1) and t0 == t1 and s0 == s1 and sorted(t0) == list(range(24))
+    assert x0 == x1 == 12 and g0 == g1 == 60
+    assert s0 == -float(np.count_nonzero(np.array(t0) != np.arange(24)))
+
+
 def test_farm_groups_partitions_every_group_once():
     w = [n * n for n in (700, 900, 850, 720, 810, 760, 880, 705, 799, 845, 731, 777)]
     for world in (1, 2, 3, 8):

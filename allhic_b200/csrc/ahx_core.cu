@@ -345,7 +345,7 @@ static cudaError_t launch_sparse_t(ahx_ctx *ctx, const IdxT *tours, const int32_
                                    double *out, cudaStream_t s) {
   auto kern = eval_m_sparse_kernel<T, Coo, IdxT, XG>;
   const size_t smem = XG ? sizeof(int) * static_cast<size_t>(L) : eval_m_smem_bytes(T, ctx->N, L);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
+  cudaError_t e = opt_in_smem(kern, ctx->smem_optin);
   if (e != cudaSuccess) return e;
   const typename Coo::Elem *coo;
   if constexpr (sizeof(typename Coo::Elem) == 8) coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo16.p);
@@ -396,7 +396,7 @@ template <int T, typename Coo, typename IdxT>
 static cudaError_t launch_x32_t(ahx_ctx *ctx, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
   auto kern = eval_m_x32_kernel<T, Coo, IdxT>;
   const size_t smem = eval_x32_smem_bytes(T, ctx->coo16, ctx->N, L);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
+  cudaError_t e = opt_in_smem(kern, ctx->smem_optin);
   if (e != cudaSuccess) return e;
   const typename Coo::Elem *coo;
   if constexpr (sizeof(typename Coo::Elem) == 8) coo = reinterpret_cast<const typename Coo::Elem *>(ctx->d_coo16o.p);
@@ -457,7 +457,7 @@ template <int T, bool STREAM, typename IdxT>
 static cudaError_t launch_res_t(ahx_ctx *ctx, bool sizes, const IdxT *tours, const int32_t *rows, int32_t P, int32_t L, double *out, cudaStream_t s) {
   auto kern = L < ctx->N ? eval_m_res_kernel<T, true, STREAM, ResDirect<T, IdxT>> : eval_m_res_kernel<T, false, STREAM, ResDirect<T, IdxT>>;
   const size_t smem = res_smem_bytes(T, ctx->N, ctx->E_res[res_ti(T)], STREAM, sizes);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
+  cudaError_t e = opt_in_smem(kern, ctx->smem_optin);
   if (e != cudaSuccess) return e;
   const bool scaled = static_cast<uint64_t>(ctx->N) * 4u * T <= 65535u;   // the table of byte offsets exists (ahx_load)
   ResArgs g{(STREAM && !scaled ? ctx->d_rraw : ctx->d_rpairs)[res_ti(T)].p, ctx->d_rnl8[res_ti(T)].p, ctx->d_sizes32.p, static_cast<int>(ctx->E_res[res_ti(T)]), ctx->N, L, ctx->d_errflag.p, sizes ? 1 : 0, scaled ? 1 : 0};
@@ -538,7 +538,7 @@ int launch_eval_m_dense(ahx_ctx *ctx, const int32_t *d_tours, int32_t P, int32_t
   if (rc != AHX_OK) return rc;
   const size_t smem = (sizeof(double) + sizeof(int)) * static_cast<size_t>(L);
   if (smem + 1024 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_eval_m_dense: tour too long for the dense kernel's shared memory");
-  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_m_dense_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  AHX_CUDA(ctx, opt_in_smem(eval_m_dense_kernel<int32_t>, ctx->smem_optin));
   eval_m_dense_kernel<int32_t><<<P, kBlock, smem, s>>>(d_tours, P, L, ctx->N, ctx->d_sizes.p, ctx->d_M.p, d_out, ctx->d_errflag.p);
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
@@ -550,7 +550,7 @@ int launch_eval_q(ahx_ctx *ctx, const int32_t *d_tours, int shared_tour, const u
   if (P == 0) return AHX_OK;
   const size_t smem = sizeof(long long) * static_cast<size_t>(L) + sizeof(int) * (static_cast<size_t>(ctx->N) + L) + ctx->N;
   if (smem + 1024 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_eval_q: group too large for shared memory");
-  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  AHX_CUDA(ctx, opt_in_smem(eval_q_kernel, ctx->smem_optin));
   eval_q_kernel<<<P, kBlock, smem, s>>>(d_tours, shared_tour, P, L, ctx->N, ctx->d_sizes.p, d_signs, ctx->d_pa.p, ctx->d_pb.p,
                                         ctx->d_slots.p, ctx->d_hist.p, static_cast<int>(ctx->E), d_out);
   ctx->launches++;

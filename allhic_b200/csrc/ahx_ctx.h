@@ -28,6 +28,18 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Opts a kernel into the device's full shared-memory carve-out: the dynamic limit is the opt-in maximum minus
+// the kernel's own static shared memory (the sum of the two is what the driver checks).  The value is a
+// constant per (kernel, device), so concurrent contexts that launch the same kernel never fight over it.
+template <typename K>
+inline cudaError_t opt_in_smem(K kern, size_t smem_optin) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+  if (e != cudaSuccess) return e;
+  const long long room = static_cast<long long>(smem_optin) - static_cast<long long>(fa.sharedSizeBytes);
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(room > 0 ? room : 0));
+}
+
 // Device-resident GA bookkeeping (one per context), evaluate.go:281-306.
 struct GaState {
   long long gen;        // ga.Generations

@@ -154,7 +154,7 @@ double top_eigenvector(int32_t n, int64_t E, const int32_t *pa, const int32_t *p
   *info = EigInfo{};
   if (n <= 0 || (E <= 0 && !diag)) return 0.0;
   constexpr int kDense = 48, kDenseFallback = 1500;
-  if (n <= kDense) { info->dense = true; return top_eigenvector_dense(n, E, pa, pb, w, diag, v); }
+  if (n <= kDense) { info->dense = true; info->converged = true; return top_eigenvector_dense(n, E, pa, pb, w, diag, v); }
   const int m = std::min<int32_t>(n, 200);
   std::vector<double> Q(static_cast<size_t>(m + 1) * n), alpha(m), beta(m), r(n), S;
   // deterministic start vector with a component along (almost surely) every eigenvector

@@ -279,7 +279,7 @@ int eval_q_shared_tour(ahx_ctx *ctx, int32_t P, int32_t L, const int32_t *tour, 
                                                                  ctx->d_cum.p, ctx->d_S4.p, ctx->d_pairinfo.p);
     ctx->launches++;
   }
-  AHX_CUDA(ctx, cudaFuncSetAttribute(eval_q_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  AHX_CUDA(ctx, opt_in_smem(eval_q_lookup_kernel, ctx->smem_optin));
   eval_q_lookup_kernel<<<P, kBlock, ctx->N, ctx->stream>>>(ctx->N, E, d_signs, ctx->d_pa.p, ctx->d_pb.p, ctx->d_S4.p, ctx->d_pairinfo.p, d_out);
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
@@ -359,14 +359,14 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
                                                                ctx->d_rec_o.p);
       ctx->launches++;
     }
-    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+    AHX_CUDA(ctx, opt_in_smem(flip_one_stream_kernel, ctx->smem_optin));
     flip_one_stream_kernel<<<1, kBlock, smem_stream, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_S4.p,
                                                                 ctx->d_pairinfo.p, ctx->d_step_off.p, ctx->d_rec_d.p, ctx->d_rec_d.p + nrec, ctx->d_rec_o.p,
                                                                 ctx->d_trace.p, ctx->d_stepacc.p, ctx->d_counts.p, d_final);
     AHX_CUDA(ctx, cudaGetLastError());
     AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `off` is stack-owned
   } else {
-    AHX_CUDA(ctx, cudaFuncSetAttribute(flip_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+    AHX_CUDA(ctx, opt_in_smem(flip_one_kernel, ctx->smem_optin));
     flip_one_kernel<<<1, 32, ctx->N, ctx->stream>>>(ctx->d_tours.p, L, ctx->N, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, E, ctx->d_adj_ptr.p,
                                                    ctx->d_adj_e.p, ctx->d_S4.p, ctx->d_pairinfo.p, ctx->d_trace.p, ctx->d_stepacc.p,
                                                    ctx->d_counts.p, d_final);

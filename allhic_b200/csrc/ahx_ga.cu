@@ -644,7 +644,7 @@ template <int T, typename Coo>
 static cudaError_t launch_apply(ahx_ctx *ctx, const GaDev &g, const GaPlan &pl, cudaStream_t s) {
   auto kern = ga_apply_kernel<T, Coo>;
   const size_t smem = eval_x32_smem_bytes(T, ctx->coo16, ctx->N, ctx->ga_L);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
+  cudaError_t e = opt_in_smem(kern, ctx->smem_optin);
   if (e != cudaSuccess) return e;
   const int n_eval = (g.P + T - 1) / T;
   const int n_copy = std::min(g.P, ctx->sm_count * 4);
@@ -741,7 +741,7 @@ static GaRes make_res(ahx_ctx *ctx) {
 template <int T, bool STREAM, bool SUB>
 static cudaError_t launch_persist_ts(ahx_ctx *ctx, long long n_gens, cudaStream_t s) {
   auto kern = ga_persist_kernel<T, STREAM, SUB>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin));
+  cudaError_t e = opt_in_smem(kern, ctx->smem_optin);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(ctx->d_gbar.p, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
   const bool scaled = static_cast<uint64_t>(ctx->N) * 4u * T <= 65535u;   // the table of byte offsets exists (ahx_load)
@@ -969,8 +969,8 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
     AHX_CUDA(ctx, cudaMemsetAsync(ctx->d_plan.p + 5 * static_cast<size_t>(prm->npop), 0, 2 * sizeof(int32_t), ctx->stream));
   }
   if (ctx->ga_x32 || ctx->ga_global) { /* attributes are set per launch */ }
-  else if (ctx->coo16) AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-  else AHX_CUDA(ctx, cudaFuncSetAttribute(ga_generation_kernel<Coo32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  else if (ctx->coo16) AHX_CUDA(ctx, opt_in_smem(ga_generation_kernel<Coo16>, ctx->smem_optin));
+  else AHX_CUDA(ctx, opt_in_smem(ga_generation_kernel<Coo32>, ctx->smem_optin));
   ctx->ga_ms = 0.0;
   const size_t PL = static_cast<size_t>(prm->npop) * L;
   for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_pop[i].reserve(PL)); AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); }

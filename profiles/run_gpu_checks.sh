@@ -32,7 +32,7 @@ echo "== bench config2 (N=500, P=1k)"
 python bench.py --workload config2 > $OUT/${TAG}_bench_config2.json 2> $OUT/${TAG}_bench_config2.err; echo "rc=$?"; cut -c1-300 $OUT/${TAG}_bench_config2.json
 
 if [ -n "$FULL" ]; then
-  CMD="python bench.py --steps 3 --warmup 3 --ga-gens 40 --cpu-seconds 0.3"
+  CMD="python bench.py --steps 3 --warmup 3 --cpu-seconds 0 --no-extras"
   echo "== plain run, then ncu launch list of the same command"
   $CMD > $OUT/${TAG}_plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launch.log 2>&1

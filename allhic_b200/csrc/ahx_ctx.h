@@ -158,9 +158,9 @@ struct ahx_ctx {
   ahx::DevBuf<int32_t> d_rowof[2], d_sel_rows;
   ahx::DevBuf<double> d_row_fit;
   ahx::DevBuf<unsigned int> d_gbar;           // [0] grid barrier counter, [1] hall-of-fame index scratch
-  ahx::DevBuf<unsigned char> d_used;          // 3 byte maps of referenced pool rows
+  ahx::DevBuf<uint32_t> d_used;               // 3 bit maps of referenced pool rows
   ahx::DevBuf<unsigned long long> d_gmin;
-  ahx::DevBuf<uint32_t> d_gmask;              // mutation masks of two generations
+  ahx::DevBuf<uint32_t> d_gmask;              // mutation masks of three generations (published two ahead)
   ahx::DevBuf<uint32_t> d_xpool;              // coordinate row of every pool row
   // islands: own mailbox, the table of peer mailboxes, IPC mappings opened so far (handle bytes -> pointer)
   ahx::DevBuf<unsigned char> d_mbox;

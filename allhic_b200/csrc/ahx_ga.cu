@@ -702,10 +702,9 @@ static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double m
 __global__ void ga_res_init_kernel(GaRes q, const int *__restrict__ init, const double *__restrict__ f0) {
   // MakeTour = r.Tour.Clone(): PopSize copies of one tour (evaluate.go:259-262) = P references to row 0
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.P; i += gridDim.x * blockDim.x) { q.rowof[0][i] = 0; q.fit[0][i] = f0[0]; }
-  const size_t ub = 2 * static_cast<size_t>(q.P), ubp = (ub + 31) / 32 * 32;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < 3 * ubp; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    q.used[i] = (i == 0) ? 1 : 0;   // generation 0 references row 0 only
-  if (blockIdx.x == 0 && threadIdx.x < 3) q.gmin[threadIdx.x] = ~0ULL;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * ga_wr_pad(q.P); i += gridDim.x * blockDim.x)
+    q.used[i] = (i == 0) ? 1u : 0u;   // generation 0 references row 0 only
+  if (blockIdx.x == 0 && threadIdx.x < 3) q.gmin[threadIdx.x] = make_ulonglong2(~0ULL, ~0ULL);
   if (blockIdx.x == 0 && threadIdx.x == 0) *q.gidx = 0x7fffffff;
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < q.L; i += blockDim.x) { q.pool[i] = init[i]; q.hof[i] = init[i]; }
@@ -731,7 +730,7 @@ static GaRes make_res(ahx_ctx *ctx) {
   q.pool = ctx->d_pop[0].p; q.rowof[0] = ctx->d_rowof[0].p; q.rowof[1] = ctx->d_rowof[1].p;
   q.fit[0] = ctx->d_fit[0].p; q.fit[1] = ctx->d_fit[1].p; q.hof = ctx->d_hof.p; q.st = ctx->d_state.p;
   q.gbar = ctx->d_gbar.p;
-  q.used = ctx->d_used.p; q.gmin = ctx->d_gmin.p; q.gmask = ctx->d_gmask.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
+  q.used = ctx->d_used.p; q.gmin = reinterpret_cast<ulonglong2 *>(ctx->d_gmin.p); q.gmask = ctx->d_gmask.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
   const ahx_ga_params &p = ctx->ga_prm;
   q.n_islands = p.n_islands > 1 ? p.n_islands : 1; q.island = p.island; q.migrate_every = p.migrate_every; q.n_elite = p.n_elite;
   q.isl = ctx->d_isl.p;
@@ -936,7 +935,7 @@ int ahx_ga_begin(ahx_ctx *ctx, const ahx_ga_params *prm, int32_t L, const int32_
     AHX_CUDA(ctx, ctx->d_pop[0].reserve(PL2));
     for (int i = 0; i < 2; ++i) { AHX_CUDA(ctx, ctx->d_fit[i].reserve(prm->npop)); AHX_CUDA(ctx, ctx->d_rowof[i].reserve(prm->npop)); }
     AHX_CUDA(ctx, ctx->d_hof.reserve(L)); AHX_CUDA(ctx, ctx->d_state.reserve(1)); AHX_CUDA(ctx, ctx->d_gbar.reserve(2));
-    AHX_CUDA(ctx, ctx->d_used.reserve(3 * ((2 * static_cast<size_t>(prm->npop) + 31) / 32 * 32))); AHX_CUDA(ctx, ctx->d_gmin.reserve(3)); AHX_CUDA(ctx, ctx->d_gmask.reserve(2 * ((static_cast<size_t>(prm->npop) + 31) / 32)));
+    AHX_CUDA(ctx, ctx->d_used.reserve(3 * static_cast<size_t>(ga_wr_pad(prm->npop)))); AHX_CUDA(ctx, ctx->d_gmin.reserve(6)); AHX_CUDA(ctx, ctx->d_gmask.reserve(3 * static_cast<size_t>(ga_wm_pad(prm->npop))));
     AHX_CUDA(ctx, ctx->d_tours.reserve(L)); AHX_CUDA(ctx, ctx->d_scores.reserve(1));
     ctx->ga_ms = 0.0; ctx->ga_x32 = false; ctx->ga_global = false;
     ctx->ga_active_set.assign(init_tour, init_tour + L);
@@ -1218,10 +1217,10 @@ int ahx_ga_put_migrants(ahx_ctx *ctx, int32_t n, const int32_t *tours) {
       AHX_CUDA(ctx, cudaMemcpyAsync(worst.data(), ctx->d_sel_idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
       AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       for (int32_t i = 0; i < n; ++i) rowof[worst[i]] = freerows[i];
-      const size_t ubp = (2 * static_cast<size_t>(P) + 31) / 32 * 32;
-      std::vector<uint8_t> map(ubp, 0);
-      for (int32_t i = 0; i < P; ++i) map[rowof[i]] = 1;
-      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_used.p + static_cast<size_t>(hs.gen % 3) * ubp, map.data(), ubp, cudaMemcpyHostToDevice, ctx->stream));
+      const size_t wrp = static_cast<size_t>(ga_wr_pad(P));
+      std::vector<uint32_t> map(wrp, 0u);
+      for (int32_t i = 0; i < P; ++i) map[rowof[i] >> 5] |= 1u << (rowof[i] & 31);
+      AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_used.p + static_cast<size_t>(hs.gen % 3) * wrp, map.data(), sizeof(uint32_t) * wrp, cudaMemcpyHostToDevice, ctx->stream));
       AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     scatter_rows_kernel<<<n, 256, 0, ctx->stream>>>(ctx->d_pop[0].p, ctx->d_sel_rows.p, L, ctx->d_sel_tours.p);

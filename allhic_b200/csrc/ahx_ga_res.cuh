@@ -50,14 +50,19 @@ struct GaRes {
   int *hof;             // [L]
   GaState *st;
   unsigned int *gbar;   // grid barrier counter, zero at launch
-  unsigned char *used;  // [3][pad32(2P)] byte maps: used[g % 3][r] = 1 iff generation g references pool row r
-  unsigned long long *gmin;   // [3] order-preserving key of the best fitness evaluated while building generation g (index g % 3)
-  int *gidx;            // lowest offspring index holding that fitness (0x7fffffff when idle)
-  uint32_t *gmask;      // [2][ceil(P/32)] mutation masks of generations g (index g & 1), filled one generation ahead
+  uint32_t *used;       // [3][ga_wr_pad(P)] bit maps: bit r of used[g % 3] is set iff generation g references pool row r
+  ulonglong2 *gmin;     // [3] best individual evaluated while building generation g (index g % 3) that beats the hall of fame: .y = order-preserving
+                        // key of its fitness, .x = offspring index << 32 | pool row; 128-bit minimum, so the lowest index wins among equal fitness values
+  int *gidx;            // (legacy paths)
+  uint32_t *gmask;      // [3][ga_wm_pad(P)] mutation masks of generations g (index g % 3), filled two generations ahead
   // islands (include/ahx.h "Islands"); n_islands <= 1: single population
   int n_islands, island, migrate_every, n_elite;
   GaIslands *isl;
 };
+
+// words of a mutation mask / of a row map, padded to 16 bytes (they travel by TMA bulk copy)
+__host__ __device__ inline int ga_wm_pad(int P) { return ((P + 31) / 32 + 3) & ~3; }
+__host__ __device__ inline int ga_wr_pad(int P) { return ((2 * P + 31) / 32 + 3) & ~3; }
 
 // One mutated offspring: where it comes from, where it goes, and its mutation in two
 // branch-free forms (the four operators of Tour.Mutate, evaluate.go:157-218, fit both --
@@ -141,10 +146,16 @@ __device__ __forceinline__ int slot_source(const GaSlot &s, int i, int L) {
   return src;
 }
 
+// first slot of the CTA's slot table that thread `tid` handles (then every kRThreads-th)
+__device__ __forceinline__ int slot_of_thread(int tid) {
+  constexpr int NWARP = kRThreads / 32;
+  return (NWARP - 1 - (tid >> 5)) + NWARP * (tid & 31);
+}
+
 inline size_t ga_res_extra_bytes(int P, int T, int nbmax) {
-  const size_t wm = (static_cast<size_t>(P) + 31) / 32, wr = (2 * static_cast<size_t>(P) + 31) / 32;
-  return res_align16(4 * (2 * wm + 2 * wr)) + res_align16(sizeof(GaSlot) * static_cast<size_t>(nbmax) * T) + res_align16(4 * (kRThreads / 32 + 1)) +
-         res_align16(kIslScratchBytes) + 64;
+  const size_t wm = static_cast<size_t>(ga_wm_pad(P)), wr = static_cast<size_t>(ga_wr_pad(P));
+  return res_align16(4 * (4 * wm + 2 * wr)) + 2 * res_align16(sizeof(GaSlot) * static_cast<size_t>(nbmax) * T) + res_align16(4 * (kRThreads / 32 + 1)) +
+         res_align16(kIslScratchBytes) + 32 + 64;
 }
 
 // order-preserving map double -> uint64 (for atomicMin on fitness values) and back
@@ -156,9 +167,22 @@ __device__ __forceinline__ double key_fit(unsigned long long k) {
   return __longlong_as_double(static_cast<long long>((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k));
 }
 
+// 128-bit minimum of (hi, lo) at addr (.y = hi, .x = lo): atom.cas.b128 (sm_90+).  The first guess is the reset value.
+__device__ __forceinline__ void atomic_min_u128(ulonglong2 *addr, unsigned long long hi, unsigned long long lo) {
+  unsigned long long chi = ~0ULL, clo = ~0ULL;
+  for (;;) {
+    if (hi > chi || (hi == chi && lo >= clo)) return;
+    unsigned long long ohi, olo;
+    asm volatile("{\n\t.reg .b128 cmp, swp, old;\n\tmov.b128 cmp, {%2, %3};\n\tmov.b128 swp, {%4, %5};\n\tatom.relaxed.gpu.global.cas.b128 old, [%6], cmp, swp;\n\tmov.b128 {%0, %1}, old;\n\t}"
+                 : "=l"(olo), "=l"(ohi) : "l"(clo), "l"(chi), "l"(lo), "l"(hi), "l"(addr) : "memory");
+    if (ohi == chi && olo == clo) return;
+    chi = ohi; clo = olo;
+  }
+}
+
 template <int T, bool SUB = false>
 struct GaSrc {
-  const int *pool; int *pool_w; const uint32_t *xpool; uint32_t *xpool_w; const GaSlot *slots; double *fitn; unsigned long long *gmin;
+  const int *pool; int *pool_w; const uint32_t *xpool; uint32_t *xpool_w; const GaSlot *slots; double *fitn; ulonglong2 *gmin; double hof_fit;
   // Lane l works on tour t = l mod T and on contig (then position) base + l / T: 32/T consecutive
   // elements of each tour per warp instruction (one 32-byte sector per tour), and the coordinate
   // store X[c*T + t] of a warp is 32 consecutive words.
@@ -199,8 +223,12 @@ struct GaSrc {
   }
   __device__ __forceinline__ void prefetch(int, int) const {}
   __device__ __forceinline__ void store(int j, int t, double score) const {
-    const int o = slots[j * T + t].o;
-    if (o >= 0) { fitn[o] = score; atomicMin(gmin, fit_key(score)); }
+    const GaSlot &sl = slots[j * T + t];
+    if (sl.o >= 0) {
+      fitn[sl.o] = score;
+      // only an individual that beats the hall of fame matters (evaluate.go:291); rare, so the 128-bit CAS loop is cold
+      if (score < hof_fit) atomic_min_u128(gmin, fit_key(score), (static_cast<unsigned long long>(sl.o) << 32) | static_cast<unsigned int>(sl.child_row));
+    }
   }
 };
 
@@ -254,14 +282,28 @@ __device__ __forceinline__ int mask_select(const uint32_t *mask, const uint32_t 
   return lo * 32 + static_cast<int>(__fns(w, 0, static_cast<int>(m - pref[lo]) + 1));
 }
 
+// Arrival is a release reduction (no return value to wait for; the release is cumulative over the CTA's writes
+// ordered before it by the block barrier), the wait an acquire poll by one thread.
 __device__ __forceinline__ void grid_barrier(unsigned int *gbar, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(gbar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gbar) : "memory");
     unsigned int v;
     do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar) : "memory"); } while (v < target);
-    __threadfence();
+  }
+  __syncthreads();
+}
+
+// The same barrier; the polling thread also fetches 16 bytes that every thread needs right behind it (the
+// generation's 128-bit minimum) into shared memory -- one request per CTA to that one line instead of one per warp.
+template <typename F>
+__device__ __forceinline__ void grid_barrier_fetch(unsigned int *gbar, unsigned int target, const ulonglong2 *src, ulonglong2 *dst_smem, F &&after) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gbar) : "memory");
+    unsigned int v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gbar) : "memory"); } while (v < target);
+    if (!after()) *dst_smem = __ldcg(src);                // after(): starts the bulk copies of what the next generation needs (the 16 bytes included), or returns false
   }
   __syncthreads();
 }
@@ -297,32 +339,76 @@ __device__ __forceinline__ uint32_t ga_load_mask(const GaRes &q, const uint32_t 
   return block_scan_array(mpref, WM, scan_tmp);
 }
 
-// Bit mask of the pool rows a generation references (from its byte map in global memory, filled
-// while that generation was built) and the exclusive word prefix of the FREE rows, for mask_select.
-__device__ __forceinline__ void ga_row_map(const GaRes &q, const unsigned char *used_cur, uint32_t *rused, uint32_t *rpref, uint32_t *scan_tmp) {
+// Row bit map of a generation (from global memory, filled while that generation was built) and the exclusive
+// word prefix of the FREE rows, for mask_select.
+__device__ __forceinline__ void ga_free_prefix(const GaRes &q, const uint32_t *rused, uint32_t *rpref, uint32_t *scan_tmp) {
   const int tid = threadIdx.x, WR = (2 * q.P + 31) / 32;
   for (int wi = tid; wi < WR; wi += kRThreads) {
-    uint32_t w = 0;
-    const uint4 *src = reinterpret_cast<const uint4 *>(used_cur + static_cast<size_t>(wi) * 32);
+    uint32_t w = ~rused[wi];
     const int nvalid = min(32, 2 * q.P - wi * 32);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (nvalid <= h * 16) break;
-      const uint4 v = __ldcg(src + h);                       // the map is padded to a multiple of 32 bytes
-      const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) w |= ((x[i] >> (8 * b)) & 1u) << (h * 16 + i * 4 + b);
-    }
-    rused[wi] = w;
-    w = ~w;
     if (nvalid < 32) w &= (1u << nvalid) - 1u;
     rpref[wi] = __popc(w);
   }
   __syncthreads();
   block_scan_array(rpref, WR, scan_tmp);   // at least P of the 2P rows are free
   __syncthreads();
+}
+__device__ __forceinline__ void ga_row_map(const GaRes &q, const uint32_t *used_cur, uint32_t *rused, uint32_t *rpref, uint32_t *scan_tmp) {
+  const int tid = threadIdx.x, WR = (2 * q.P + 31) / 32;
+  for (int wi = tid; wi < WR; wi += kRThreads) rused[wi] = __ldcg(used_cur + wi);
+  __syncthreads();
+  ga_free_prefix(q, rused, rpref, scan_tmp);
+}
+
+// The mutation mask of the generation after next and the row map of the next generation are both complete in
+// global memory once the grid barrier that ends a generation has been passed.  The thread that polled the barrier
+// then starts two TMA bulk copies (ga_issue_mask_rows) that land them in shared memory -- no registers, nobody
+// waits -- while the dependent loads of the next generation's front half run; ga_finish_mask_rows waits on the
+// mbarrier and turns them into the select structures (popcount + ONE block scan over both when WM + WR <= kRThreads).
+__device__ __forceinline__ void ga_issue_mask_rows(const GaRes &q, const uint32_t *gmask, const uint32_t *used_cur, const ulonglong2 *gmin, uint32_t *mflag, uint32_t *rused,
+                                                   ulonglong2 *gm_smem, uint64_t *bar) {
+  const uint32_t mb = 4u * static_cast<uint32_t>(ga_wm_pad(q.P)), rb = 4u * static_cast<uint32_t>(ga_wr_pad(q.P));
+  asm volatile("fence.proxy.async;" ::: "memory");       // the other CTAs' (generic proxy) stores, acquired at the barrier, before the async-proxy reads
+  mbar_expect_tx(bar, mb + rb + 16u);
+  bulk_copy_g2s(gm_smem, gmin, 16u, bar);
+  bulk_copy_g2s(mflag, gmask, mb, bar);
+  bulk_copy_g2s(rused, used_cur, rb, bar);
+}
+// One thread polls the mbarrier; the others sleep in the block barrier instead of spinning on it (23 polling warps
+// took the issue slots the front half's warps needed).
+__device__ __forceinline__ void ga_wait_pending(uint64_t *bar, uint32_t parity) {
+  if (threadIdx.x == 0) mbar_wait(bar, parity);
+  __syncthreads();
+}
+// returns the number of mutated offspring of the mask; ends with a block barrier
+__device__ __forceinline__ uint32_t ga_finish_mask_rows(const GaRes &q, uint64_t *bar, uint32_t parity, const uint32_t *mflag, uint32_t *mpref, const uint32_t *rused,
+                                                        uint32_t *rpref, uint32_t *scan_tmp) {
+  const int tid = threadIdx.x, WM = (q.P + 31) / 32, WR = (2 * q.P + 31) / 32, wi = tid - WM;
+  (void)bar; (void)parity;                                // the caller has waited for the copies (ga_wait_pending)
+  if (WM + WR > kRThreads) {
+    for (int w = tid; w < WM; w += kRThreads) mpref[w] = __popc(mflag[w]);
+    __syncthreads();
+    const uint32_t M = block_scan_array(mpref, WM, scan_tmp);
+    ga_free_prefix(q, rused, rpref, scan_tmp);
+    return M;
+  }
+  uint32_t cnt = 0;
+  if (tid < WM) cnt = __popc(mflag[tid]);
+  else if (wi < WR) {
+    uint32_t w = ~rused[wi];
+    const int nvalid = min(32, 2 * q.P - wi * 32);
+    if (nvalid < 32) w &= (1u << nvalid) - 1u;
+    cnt = __popc(w);
+  }
+  uint32_t total = 0;
+  const uint32_t excl = block_scan_u32(cnt, scan_tmp, &total);
+  if (tid < WM) mpref[tid] = excl;
+  if (tid == WM) scan_tmp[0] = excl;                      // = number of mutated offspring (sum of the mask segment)
+  __syncthreads();
+  const uint32_t M = scan_tmp[0];
+  if (tid >= WM && wi < WR) rpref[wi] = excl - M;
+  __syncthreads();
+  return M;
 }
 
 // ---- islands: the exchange step, inside the kernel ------------------------------------
@@ -445,7 +531,7 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
     int win = -1;                                                                 // thread 0: the migrant that beats the hall of fame
     if (!timed_out) {
       isl_select_k(fitc, q.P, m, true, sc.sel + kIslMaxMigrants, sc);             // worst first
-      ga_row_map(q, q.used + static_cast<size_t>(gen % 3) * ((2 * static_cast<size_t>(q.P) + 31) / 32 * 32), rused, rpref, scan_tmp);
+      ga_row_map(q, q.used + static_cast<size_t>(gen % 3) * ga_wr_pad(q.P), rused, rpref, scan_tmp);
       const int WR = (2 * q.P + 31) / 32;
       if (tid < m) sc.rows[tid] = mask_select(rused, rpref, WR, static_cast<uint32_t>(tid), true, 2 * q.P);
       __syncthreads();
@@ -487,11 +573,10 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
         for (int i = tid; i < L; i += kRThreads) q.hof[i] = best_row[i];
       }
       // exact row map of the edited generation (fresh rows are allocated from its complement)
-      unsigned char *used_cur = q.used + static_cast<size_t>(gen % 3) * ((2 * static_cast<size_t>(q.P) + 31) / 32 * 32);
-      uint32_t *z = reinterpret_cast<uint32_t *>(used_cur);
-      for (size_t i = tid; i < (2 * static_cast<size_t>(q.P) + 31) / 32 * 8; i += kRThreads) z[i] = 0u;
+      uint32_t *used_cur = q.used + static_cast<size_t>(gen % 3) * ga_wr_pad(q.P);
+      for (int i = tid; i < ga_wr_pad(q.P); i += kRThreads) used_cur[i] = 0u;
       __syncthreads();
-      for (int i = tid; i < q.P; i += kRThreads) used_cur[__ldcg(rowc + i)] = 1;
+      for (int i = tid; i < q.P; i += kRThreads) { const int r = __ldcg(rowc + i); atomicOr(used_cur + (r >> 5), 1u << (r & 31)); }
     }
     if (tid == 0) { isl->x_hof_fit = hof_fit; isl->x_updated = updated; }
   }
@@ -508,9 +593,12 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
   const ResSmem m = res_carve<T, STREAM>(smem_res, g);
   const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
   const int WM = (q.P + 31) / 32, WR = (2 * q.P + 31) / 32;
-  uint32_t *mflag = reinterpret_cast<uint32_t *>(m.extra), *mpref = mflag + WM, *rused = mpref + WM, *rpref = rused + WR;
-  GaSlot *slots = reinterpret_cast<GaSlot *>(m.extra + res_align16(4ull * (2 * WM + 2 * WR)));
-  uint32_t *scan_tmp = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(slots) + res_align16(sizeof(GaSlot) * static_cast<size_t>(q.nbmax) * T));   // kRThreads/32 + 1 words
+  // mutation mask + exclusive word prefix of generations g (buffer g & 1) and g + 1, row bit map + prefix of the free rows
+  const int WMp = ga_wm_pad(q.P), WRp = ga_wr_pad(q.P);                 // padded to 16 bytes: the words arrive by TMA bulk copy
+  uint32_t *mbase = reinterpret_cast<uint32_t *>(m.extra), *rused = mbase + 4 * WMp, *rpref = rused + WRp;
+  const size_t slot_bytes = res_align16(sizeof(GaSlot) * static_cast<size_t>(q.nbmax) * T);
+  unsigned char *slot_base = m.extra + res_align16(4ull * (4 * WMp + 2 * WRp));   // two slot tables (generation g & 1)
+  uint32_t *scan_tmp = reinterpret_cast<uint32_t *>(slot_base + 2 * slot_bytes);   // kRThreads/32 + 1 words
   unsigned char *isl_smem = reinterpret_cast<unsigned char *>(scan_tmp) + res_align16(4 * (kRThreads / 32 + 1));
   res_init<STREAM>(m, g, true);
   int kdone = 0;
@@ -521,113 +609,209 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
   double hof_fit = q.st->hof_fit;
   int stop = q.st->stop;
   unsigned int nsync = 0;
-  const size_t ub = (2 * static_cast<size_t>(q.P) + 31) / 32 * 32;   // bytes per row-reference map (padded)
-  // the first generation of this launch: every CTA publishes its share of the mask, one extra barrier
-  if (n_gens > 0 && !stop) ga_publish_mask(q, ph, gen, q.gmask + static_cast<size_t>(gen & 1) * WM, cta, G);
+  uint32_t Mb[2] = {0u, 0u};                                           // mutated offspring of the masks in the two buffers
+  auto mflag_of = [&](long long gg) { return mbase + static_cast<size_t>(gg & 1) * 2 * WMp; };
+  auto gmask_of = [&](long long gg) { return q.gmask + static_cast<size_t>(gg % 3) * WMp; };   // three in rotation: a launch's first CTAs publish generation g + 2 while the last still read g
+  auto used_of = [&](long long gg) { return q.used + static_cast<size_t>(gg % 3) * WRp; };
+  // Masks are published TWO generations ahead (they do not depend on fitness), so that the mask of generation g + 1
+  // is already scanned in shared memory when generation g's barrier falls.  The first two of this launch: here.
+  if (n_gens > 0 && !stop) {
+    ga_publish_mask(q, ph, gen, gmask_of(gen), cta, G);
+    ga_publish_mask(q, ph, gen + 1, gmask_of(gen + 1), cta, G);
+  }
   ++nsync;
   grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
-  uint32_t M = (n_gens > 0 && !stop) ? ga_load_mask(q, q.gmask + static_cast<size_t>(gen & 1) * WM, mflag, mpref, scan_tmp) : 0u;
+  if (n_gens > 0 && !stop) {
+    Mb[gen & 1] = ga_load_mask(q, gmask_of(gen), mflag_of(gen), mflag_of(gen) + WMp, scan_tmp);
+    Mb[(gen + 1) & 1] = ga_load_mask(q, gmask_of(gen + 1), mflag_of(gen + 1), mflag_of(gen + 1) + WMp, scan_tmp);
+    ga_row_map(q, used_of(gen), rused, rpref, scan_tmp);
+  }
 #ifdef AHX_GA_TIMING   // make EXTRA_NVFLAGS=-DAHX_GA_TIMING: per-phase clock64 totals of the first and last CTA, printed at exit
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
 #define AHX_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); tph[i] += now_ - tprev; tprev = now_; } } while (0)
+  long long tq[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tqprev = clock64();   // the same for the first slot thread
+#define AHX_TICKQ(i) do { if (tid == kRThreads - 32) { const long long now_ = clock64(); tq[i] += now_ - tqprev; tqprev = now_; } } while (0)
 #else
 #define AHX_TICK(i) do { } while (0)
+#define AHX_TICKQ(i) do { } while (0)
 #endif
-  for (long long it = 0; it < n_gens && !stop; ++it) {
-    const int cur = static_cast<int>(gen & 1);
-    const int *rowc = q.rowof[cur]; int *rown = q.rowof[cur ^ 1];
-    const double *fitc = q.fit[cur]; double *fitn = q.fit[cur ^ 1];
-    const uint32_t glo = static_cast<uint32_t>(gen), ghi = static_cast<uint32_t>(gen >> 32);
-    const unsigned char *used_cur = q.used + static_cast<size_t>(gen % 3) * ub;          // rows generation `gen` references
-    unsigned char *used_new = q.used + static_cast<size_t>((gen + 1) % 3) * ub;        // marked while generation gen+1 is built
-    unsigned char *used_old = q.used + static_cast<size_t>((gen + 2) % 3) * ub;        // generation gen-1's map: nobody reads it any more
-    unsigned long long *gmin_new = q.gmin + (gen + 1) % 3;
-    // ---- rows the current generation references -> free-row select structure
-    ga_row_map(q, used_cur, rused, rpref, scan_tmp);
-    AHX_TICK(0);   // row map -> free-row select
-    // ---- slot table of the mutated offspring this CTA scores
-    const uint32_t Mcur = M;
-    const int nb_total = (static_cast<int>(Mcur) + T - 1) / T;
-    const int nb_local = cta < nb_total ? (nb_total - cta + G - 1) / G : 0;
-    for (int s = kRThreads - 1 - tid; s < nb_local * T; s += kRThreads) {   // threads from the top of the block; the clones below start at thread 0
+  ulonglong2 *bcast = reinterpret_cast<ulonglong2 *>(isl_smem + res_align16(kIslScratchBytes));
+  uint64_t *pbar = reinterpret_cast<uint64_t *>(bcast + 1);               // mbarrier of the bulk copies issued behind each grid barrier
+  if (tid == 0) { mbar_init(pbar, 1); mbar_init_fence(); }                 // visible to the block by the barriers below
+  // Selection of offspring o of generation gg + 1 (parents: generation gg): the winner, its pool row and fitness.
+  // (Fetching both rounds' candidates and their row ids in one round trip -- 18 loads instead of 3 + 3 + 1 + 1 --
+  // measured slower: 44.3 against 42.8 us per generation at config3.)
+  auto select_parent = [&](long long gg, int o, int *row, double *fit) {
+    const int c = static_cast<int>(gg & 1);
+    const uint32_t glo = static_cast<uint32_t>(gg), ghi = static_cast<uint32_t>(gg >> 32);
+    const int parent = tournament_pair(q.fit[c], q.P, q.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
+    *row = __ldcg(q.rowof[c] + parent); *fit = __ldcg(q.fit[c] + parent);
+    return parent;
+  };
+  // Front half of building generation gg + 1: (1) for the mutated offspring this CTA scores (batch b -> CTA b mod G)
+  // the offspring index, mutation plan, tournament parent and the operator's two maps -- a chain of dependent loads
+  // (fitness + row id -> tour row -> coordinate row); (2) this CTA's share of the un-mutated offspring, which inherit
+  // row and fitness (eaopt keeps Evaluated = true on clones).  The two run in different threads, and nothing here
+  // reads what the rest of the set-up (free rows, next mask) produces, so the front half starts right behind the
+  // previous generation's barrier, while those loads are in flight and before that generation's bookkeeping.  It
+  // writes only generation gg + 1's buffers: if the run turns out to stop at gg they are never read.
+  auto front_half = [&](long long gg) {
+    const int c = static_cast<int>(gg & 1);
+    int *rown = q.rowof[c ^ 1]; double *fitn = q.fit[c ^ 1];
+    const uint32_t glo = static_cast<uint32_t>(gg), ghi = static_cast<uint32_t>(gg >> 32);
+    const uint32_t *mf = mflag_of(gg), *mp_ = mf + WMp;
+    const uint32_t Mg = Mb[gg & 1];
+    const int nbt = (static_cast<int>(Mg) + T - 1) / T, nbl = cta < nbt ? (nbt - cta + G - 1) / G : 0;
+    GaSlot *sl_tab = reinterpret_cast<GaSlot *>(slot_base + static_cast<size_t>(gg & 1) * slot_bytes);
+    uint32_t *used_nx = used_of(gg + 1);
+    // slot s -> lane s / 24 of warp 23 - s % 24: one slot per WARP while there are at most 24 (their code paths differ:
+    // operator, tournament round, so slots sharing a warp would run one after the other); the clones start at thread 0
+    for (int s = slot_of_thread(tid); s < nbl * T; s += kRThreads) {
       const int j = s / T, t = s % T;
       const uint32_t mi = static_cast<uint32_t>((cta + j * G) * T + t);
       GaSlot sl{};
       sl.o = -1;
-      if (mi < Mcur) {
-        const int o = mask_select(mflag, mpref, WM, mi, false, q.P);
+      if (mi < Mg) {
+        AHX_TICKQ(0);
+        const int o = mask_select(mf, mp_, WM, mi, false, q.P);
         const MutPlan mp = plan_mutation(ph, glo, ghi, static_cast<uint32_t>(o), q.mut_prob, q.L);
-        const int parent = tournament_pair(fitc, q.P, q.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
-        sl.parent_row = __ldcg(rowc + parent);
+        AHX_TICKQ(1);   // select + plan
+        double pf;
+        select_parent(gg, o, &sl.parent_row, &pf);
+        AHX_TICKQ(2);   // tournament + row
         remap_of(mp, q.L, q.pool + static_cast<size_t>(sl.parent_row) * q.L, q.xpool + static_cast<size_t>(sl.parent_row) * g.N, q.sizes32, q.total2, &sl);
+        AHX_TICKQ(3);   // remap_of
         sl.o = o;
-        sl.child_row = mask_select(rused, rpref, WR, mi, true, 2 * q.P);
-        rown[o] = sl.child_row;
-        used_new[sl.child_row] = 1;
       }
-      slots[s] = sl;
+      sl_tab[s] = sl;
     }
-    // ---- un-mutated offspring: inherit row and fitness (eaopt keeps Evaluated = true on clones)
     for (int o = cta + tid * G; o < q.P; o += kRThreads * G) {
-      if ((mflag[o >> 5] >> (o & 31)) & 1u) continue;
-      const int parent = tournament_pair(fitc, q.P, q.k, ph, glo, ghi, static_cast<uint32_t>(o >> 1), o & 1);
-      const int row = __ldcg(rowc + parent);
+      if ((mf[o >> 5] >> (o & 31)) & 1u) continue;
+      int row; double pf;
+      select_parent(gg, o, &row, &pf);
       rown[o] = row;
-      used_new[row] = 1;
-      fitn[o] = __ldcg(fitc + parent);
+      atomicOr(used_nx + (row >> 5), 1u << (row & 31));
+      fitn[o] = pf;
     }
-    // ---- housekeeping for later generations: this CTA's words of the next generation's mutation mask,
-    // clear generation gen-1's row map (this CTA's slice), reset its minimum
-    ga_publish_mask(q, ph, gen + 1, q.gmask + static_cast<size_t>((gen + 1) & 1) * WM, cta, G);
-    {
-      const size_t words = ub / 4;
-      uint32_t *z = reinterpret_cast<uint32_t *>(used_old);
-      for (size_t i = static_cast<size_t>(cta) * kRThreads + tid; i < words; i += static_cast<size_t>(G) * kRThreads) z[i] = 0u;
-      if (cta == 0 && tid == 0) q.gmin[(gen + 2) % 3] = ~0ULL;
-    }
-    __syncthreads();
-    AHX_TICK(1);   // slots + clones
-    // ---- score this CTA's batches; the generation's best new fitness goes to gmin_new
-    GaSrc<T, SUB> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new};
-    res_run_batches<T, SUB, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
-    const long long ngen_now = gen + 1;
-    __syncthreads();
-    AHX_TICK(2);   // build + score
-    ++nsync;
-    grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
-    AHX_TICK(3);   // grid barrier
-    const unsigned long long kmin = __ldcg(gmin_new);   // in flight together with the mask words (one L2 round trip, not two)
-    M = ga_load_mask(q, q.gmask + static_cast<size_t>(ngen_now & 1) * WM, mflag, mpref, scan_tmp);
-    // ---- bookkeeping (evaluate.go:287-306).  Clones are copies of individuals that already exist, so
-    // only a mutated offspring can beat the hall of fame: compare the minimum over this generation's
-    // evaluations; on a (rare) improvement the owners of that fitness agree on the lowest offspring index.
-    if (kmin < fit_key(hof_fit)) {          // updateHallOfFame keeps the best ever; currentBest > *best
-      hof_fit = key_fit(kmin); updated = ngen_now;
-      for (int s = tid; s < nb_local * T; s += kRThreads) {
-        const int o = slots[s].o;
-        if (o >= 0 && fit_key(__ldcg(fitn + o)) == kmin) atomicMin(q.gidx, o);
-      }
-      ++nsync;
-      grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
-      if (cta == 0) {
-        const int bi = __ldcg(q.gidx);
-        const int *best_row = q.pool + static_cast<size_t>(__ldcg(rown + bi)) * q.L;
+  };
+  // Bookkeeping of a finished generation `gnow` (evaluate.go:287-306) from the 128-bit minimum of its evaluations.
+  // Clones are copies of individuals that already exist, so only a mutated offspring can beat the hall of fame;
+  // the minimum carries the winner's offspring index and pool row, so there is nothing to agree on: the last CTA
+  // copies the row (it stays referenced by generation gnow while gnow + 1 is built) and nobody waits for it.
+  ulonglong2 gm = make_ulonglong2(0ULL, ~0ULL);
+  uint32_t Mlast = 0;
+  auto bookkeeping = [&](long long gnow) {
+    const bool improved = gm.y < fit_key(hof_fit);          // updateHallOfFame keeps the best ever; currentBest > *best
+    if (improved) {
+      hof_fit = key_fit(gm.y); updated = gnow;
+      if (cta == G - 1) {
+        const int *best_row = q.pool + static_cast<size_t>(gm.x & 0xffffffffULL) * q.L;
         for (int i = tid; i < q.L; i += kRThreads) q.hof[i] = __ldcg(best_row + i);
-        __syncthreads();
-        if (tid == 0) { q.st->best_idx = bi; *q.gidx = 0x7fffffff; }   // next use is at least one grid barrier away
+        if (tid == 0) q.st->best_idx = static_cast<int>(gm.x >> 32);
       }
     }
-    evals += Mcur;
+    evals += Mlast;
     // EarlyStop (evaluate.go:304-306); with islands it is a collective decision taken at the exchange points
-    if ((q.n_islands <= 1 && ngen_now - updated > q.ngen) || ngen_now >= q.max_gens) stop = 1;
-    gen = ngen_now;
-    AHX_TICK(4);   // mask load + hall of fame
-    if (q.n_islands > 1 && gen % q.migrate_every == 0) {
+    if ((q.n_islands <= 1 && gnow - updated > q.ngen) || gnow >= q.max_gens) stop = 1;
+    return improved;
+  };
+  bool book = false;                                   // generation `gen` exists, its bookkeeping is still to be done
+  bool pend = false;                                   // bulk copies of the next mask / this generation's row map are in flight
+  uint32_t pphase = 0;
+  long long it = 0;
+  while (it < n_gens && !stop) {
+    // ---- an exchange is due at this generation: it changes the population, so bookkeeping and exchange come first
+    if (book && q.n_islands > 1 && gen % q.migrate_every == 0) {
+      const bool improved = bookkeeping(gen);
+      book = false;
+      if (improved) { ++nsync; grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G)); }   // CTA 0 may replace the hall-of-fame tour by a migrant's
       ga_island_exchange(q, g.N, gen, hof_fit, updated, stop, nsync, rused, rpref, scan_tmp, isl_smem);
       AHX_TICK(5);   // island exchange
+      if (stop) break;
+      // mask of gen + 1 and the (edited) row map of gen, plainly
+      Mb[(gen + 1) & 1] = ga_load_mask(q, gmask_of(gen + 1), mflag_of(gen + 1), mflag_of(gen + 1) + WMp, scan_tmp);
+      ga_row_map(q, used_of(gen), rused, rpref, scan_tmp);
+    }
+    front_half(gen);
+    if (pend) { ga_wait_pending(pbar, pphase); pphase ^= 1u; gm = *bcast; }
+    if (book) {
+      bookkeeping(gen);
+      book = false;
+      if (stop) break;
+    }
+    AHX_TICK(4);   // front half + bookkeeping
+    const int cur = static_cast<int>(gen & 1);
+    int *rown = q.rowof[cur ^ 1];
+    double *fitn = q.fit[cur ^ 1];
+    uint32_t *used_new = used_of(gen + 1);        // marked while generation gen+1 is built
+    uint32_t *used_old = used_of(gen + 2);        // generation gen-1's map: nobody reads it any more
+    ulonglong2 *gmin_new = q.gmin + (gen + 1) % 3;
+    GaSlot *slots = reinterpret_cast<GaSlot *>(slot_base + static_cast<size_t>(gen & 1) * slot_bytes);
+    const uint32_t Mcur = Mb[gen & 1];
+    const int nb_total = (static_cast<int>(Mcur) + T - 1) / T;
+    const int nb_local = cta < nb_total ? (nb_total - cta + G - 1) / G : 0;
+    // ---- the loads issued behind the previous barrier have landed: free-row select structure of this generation,
+    // mask of the next one
+    if (pend) {
+      Mb[(gen + 1) & 1] = ga_finish_mask_rows(q, pbar, pphase, mflag_of(gen + 1), mflag_of(gen + 1) + WMp, rused, rpref, scan_tmp);
+      pend = false;
+    }
+    AHX_TICKQ(4);   // finish (scan)
+    // ---- slot table, back half: the k-th mutated offspring takes the k-th free row (a thread finishes the slots it began)
+    for (int s = slot_of_thread(tid); s < nb_local * T; s += kRThreads) {
+      const int o = slots[s].o;
+      if (o >= 0) {
+        const int j = s / T, t = s % T;
+        const int child = mask_select(rused, rpref, WR, static_cast<uint32_t>((cta + j * G) * T + t), true, 2 * q.P);
+        slots[s].child_row = child;
+        rown[o] = child;
+        atomicOr(used_new + (child >> 5), 1u << (child & 31));
+      }
+    }
+    AHX_TICKQ(5);   // back half
+    // ---- housekeeping for later generations: this CTA's words of the mutation mask of generation gen + 2,
+    // clear generation gen-1's row map (this CTA's slice), reset its minimum
+    ga_publish_mask(q, ph, gen + 2, gmask_of(gen + 2), cta, G);
+    {
+      for (int i = cta * kRThreads + tid; i < WRp; i += G * kRThreads) used_old[i] = 0u;
+      if (cta == 0 && tid == 0) q.gmin[(gen + 2) % 3] = make_ulonglong2(~0ULL, ~0ULL);
+    }
+    AHX_TICKQ(6);   // publish + clear
+    __syncthreads();
+    AHX_TICKQ(7);   // sync
+    AHX_TICK(1);   // rest of the set-up
+    // ---- score this CTA's batches; an individual that beats the hall of fame goes to gmin_new
+    GaSrc<T, SUB> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new, hof_fit};
+    res_run_batches<T, SUB, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
+    AHX_TICK(2);   // build + score
+    ++nsync;
+    // what the next generation needs from global memory starts to move the moment the barrier opens
+    const bool more = it + 1 < n_gens && gen + 1 < q.max_gens;
+    const bool issue = more && !(q.n_islands > 1 && (gen + 1) % q.migrate_every == 0);
+    grid_barrier_fetch(q.gbar, nsync * static_cast<unsigned int>(G), gmin_new, bcast, [&]() {
+      if (issue) ga_issue_mask_rows(q, gmask_of(gen + 2), used_new, gmin_new, mflag_of(gen + 2), rused, bcast, pbar);
+      return issue;
+    });
+    AHX_TICK(3);   // grid barrier
+    AHX_TICKQ(8);   // batches + barrier
+    if (!issue) gm = *bcast;                              // else: read once the copies have landed
+    Mlast = Mcur;
+    ++it; ++gen;
+    book = true;
+    pend = issue;
+  }
+  if (book) {
+    // the launch ends on a freshly built generation: its bookkeeping, and the exchange if one is due at it
+    const bool improved = bookkeeping(gen);
+    if (q.n_islands > 1 && gen % q.migrate_every == 0) {
+      if (improved) { ++nsync; grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G)); }
+      ga_island_exchange(q, g.N, gen, hof_fit, updated, stop, nsync, rused, rpref, scan_tmp, isl_smem);
     }
   }
 #ifdef AHX_GA_TIMING
+  if (tid == kRThreads - 32 && cta == 0)
+    printf("cta 0 slot thread: to-slot %lld  select+plan %lld  tournament+row %lld  remap_of %lld  finish %lld  back %lld  publish+clear %lld  sync %lld  batches+barrier %lld\n",
+           tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7], tq[8]);
   if (tid == 0 && (cta == 0 || cta == G - 1))
     printf("cta %d (%d batches/gen at the end): rowmap %lld  slots %lld  build+score %lld  barrier %lld  mask+hof %lld  exchange %lld cycles over %lld generations\n",
            cta, 0, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], n_gens);

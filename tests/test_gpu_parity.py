@@ -556,15 +556,25 @@ def test_flip_all_sign_pattern_vs_jacobi_oracle(built_lib, tmp_path, n):
     s, acc, a, b = eng.flip_all(t, plus)
     info = eng.flip_all_info()
     assert info["converged"] and info["dense"] == (n <= 48) and info["residual"] <= 1e-9
-    assert close(a, a_o) and acc == acc_o
-    so = orc.signs()
-    assert (s == so).all() or (s != so).all()              # the eigenvector's global sign is arbitrary (flipWhole settles it)
-    orc.set_signs(s)
-    assert close(b, orc.evaluate_q())
-    # the recovered pattern separates the flipped contigs from the others
-    truth = np.array([ord('-') if i in flipped else ord('+') for i in range(n)], np.uint8)
-    agree = (s == truth).mean()
-    assert agree > 0.95 or agree < 0.05
+    assert close(a, a_o)
+    # The eigenvector's global sign is implementation defined (gonum's EigenSym, the oracle's Jacobi and the
+    # product's Lanczos may each return v or -v), so the candidate sign vector is the oracle's pattern or its
+    # complement; the new score, and with it ACCEPT / REJECT (orientation.go:56-62), belongs to the candidate.
+    v = orc.top_eigvec()[0]
+    cand = np.where(v < 0, ord('-'), ord('+')).astype(np.uint8)
+    comp = np.where(v < 0, ord('+'), ord('-')).astype(np.uint8)
+    orc.set_signs(cand); q_cand = orc.evaluate_q()
+    orc.set_signs(comp); q_comp = orc.evaluate_q()
+    assert close(b_o, q_cand)
+    assert close(b, q_cand) or close(b, q_comp)
+    ours = cand if close(b, q_cand) else comp
+    assert acc == (not b < a)                               # REJECT only when newScore < score (orientation.go:58)
+    # contigs without any contact have a zero component: '+' on both sides whatever the global sign (`v < 0`)
+    live = np.abs(v) > 1e-9 * np.abs(v).max()
+    assert live.sum() >= 0.9 * n
+    assert (s[live] == (ours if acc else plus)[live]).all()
+    if close(b, q_cand):
+        assert acc == acc_o
     eng.close()
 
 

@@ -26,6 +26,24 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 BINARY = os.path.join(_HERE, "bin", "allhic-b200")
 
 
+def partition_refiles(contigsfile, k):
+    """The per-group REfiles `allhic partition <counts_RE.txt> <pairs.txt> k` leaves behind (Partitioner.splitRE,
+    partition.go:205-215): RemoveExt(contigsfile) + ".<k>g<j>.txt", j = 1..k."""
+    root, _ = os.path.splitext(contigsfile)
+    return ["%s.%dg%d.txt" % (root, k, j + 1) for j in range(k)]
+
+
+def pipeline_groups(contigsfile, k, clmfile):
+    """The (REfile, clmfile) list `allhic pipeline` optimizes one after the other (allhic.go:285-293): every group of
+    the k-way partition against the same genome-wide CLM (the host binary parses that file once for all of them).
+    Feed it to optimize_groups()."""
+    refiles = partition_refiles(contigsfile, k)
+    missing = [r for r in refiles if not os.path.exists(r)]
+    if missing:
+        raise FileNotFoundError("partition output not found: %s" % ", ".join(missing))
+    return [(r, clmfile) for r in refiles]
+
+
 def _count_contigs(refile):
     with open(refile) as f:
         return sum(1 for line in f if line.strip() and not line.startswith("#"))

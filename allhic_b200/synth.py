@@ -32,9 +32,11 @@ def config4_groups():
     return [dict(n=int(n), seed=4204 + g, npop=1000) for g, n in enumerate(ns)]
 
 
-def generate(n, seed, pairs_per_contig=300, mean_size=100_000):
-    """Returns dict(names, sizes, pa, pb, dists) where dists[e] is a (4, nlinks)
-    int64 array in file orientation order ++, +-, -+, -- for pair (pa[e] < pb[e])."""
+def simulate_read_pairs(n, seed, pairs_per_contig=300, mean_size=100_000):
+    """One chromosome of n contigs laid end to end in true order and R = pairs_per_contig * n read pairs with a
+    1/d separation spectrum on [MinLinkDist, MaxLinkDist]: what the BAM that `extract` reads would hold.
+    Returns dict(sizes, G, ai, apos, bi, bpos): the inter-contig pairs as (contig, 0-based position) of read and
+    mate, read on the left."""
     rng = np.random.Generator(np.random.PCG64(seed))
     sizes = np.clip(rng.exponential(mean_size, n), 1_000, 2_000_000).astype(np.int64)
     starts = np.concatenate([[0], np.cumsum(sizes)])
@@ -49,8 +51,18 @@ def generate(n, seed, pairs_per_contig=300, mean_size=100_000):
     bi = np.searchsorted(starts, y, side="right") - 1
     inter = ai != bi
     x, y, ai, bi = x[inter], y[inter], ai[inter], bi[inter]
-    apos = x - starts[ai]
-    bpos = y - starts[bi]
+    return dict(sizes=sizes, G=G, ai=ai, apos=x - starts[ai], bi=bi, bpos=y - starts[bi])
+
+
+def generate(n, seed, pairs_per_contig=300, mean_size=100_000):
+    """Returns dict(names, sizes, pa, pb, dists) where dists[e] is a (4, nlinks)
+    int64 array in file orientation order ++, +-, -+, -- for pair (pa[e] < pb[e]).
+    The CLM lines are what `extract` writes for the simulated read pairs (extract.go:476-531; checked against a
+    restatement of that loop by tests/test_extract_semantics.py), except that a pair's distances are written in
+    ascending order (Go: BAM record order -- GoldenArray is a histogram, so the order only moves SumLog's rounding)
+    and a zero distance (read and mate both at position 0 of abutting contigs) is written as 1 (ln 0 = -Inf)."""
+    sim = simulate_read_pairs(n, seed, pairs_per_contig, mean_size)
+    sizes, G, ai, bi, apos, bpos = sim["sizes"], sim["G"], sim["ai"], sim["bi"], sim["apos"], sim["bpos"]
     L1 = sizes[ai]
     L2 = sizes[bi]
     four = np.stack([(L1 - apos) + bpos, (L1 - apos) + (L2 - bpos), apos + bpos, apos + (L2 - bpos)], axis=0)

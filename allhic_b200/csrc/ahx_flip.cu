@@ -333,7 +333,7 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   if ((rc = upload_tour_index(ctx, L, tour)) != AHX_OK) return rc;
   const int E = static_cast<int>(ctx->E), Lm = std::max<int32_t>(L, 1);
   AHX_CUDA(ctx, ctx->d_S4.reserve(static_cast<size_t>(std::max(E, 1)) * 4)); AHX_CUDA(ctx, ctx->d_pairinfo.reserve(std::max(E, 1)));
-  AHX_CUDA(ctx, ctx->d_trace.reserve(static_cast<size_t>(Lm) * 2 + 1)); AHX_CUDA(ctx, ctx->d_stepacc.reserve(Lm));
+  AHX_CUDA(ctx, ctx->d_trace.reserve(static_cast<size_t>(Lm) * 2 + 2)); AHX_CUDA(ctx, ctx->d_stepacc.reserve(Lm));
   AHX_CUDA(ctx, ctx->d_counts.reserve(2)); AHX_CUDA(ctx, ctx->d_signs.reserve(ctx->N)); AHX_CUDA(ctx, ctx->d_tours.reserve(Lm));
   AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_signs.p, signs, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
   if (L) AHX_CUDA(ctx, cudaMemcpyAsync(ctx->d_tours.p, tour, sizeof(int32_t) * L, cudaMemcpyHostToDevice, ctx->stream));
@@ -373,12 +373,23 @@ int ahx_flip_one(ahx_ctx *ctx, int32_t L, const int32_t *tour, uint8_t *signs, d
   }
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
+  // The pass keeps a running score (score - delta per accepted step); the reference's final `score` is a full
+  // EvaluateQ sum (orientation.go:96-99).  Re-synchronise: one full sum over the final signs, returned as the
+  // final score, so rounding never accumulates from one pass into the next.
+  if (static_cast<size_t>(ctx->N) + 1024 <= ctx->smem_optin) {
+    AHX_CUDA(ctx, opt_in_smem(eval_q_lookup_kernel, ctx->smem_optin));
+    eval_q_lookup_kernel<<<1, kBlock, ctx->N, ctx->stream>>>(ctx->N, E, ctx->d_signs.p, ctx->d_pa.p, ctx->d_pb.p, ctx->d_S4.p, ctx->d_pairinfo.p, d_final + 1);
+    ctx->launches++;
+    AHX_CUDA(ctx, cudaGetLastError());
+  } else {
+    AHX_CUDA(ctx, cudaMemcpyAsync(d_final + 1, d_final, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   AHX_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
   long long counts[2] = {0, 0};
   double fs = 0.0;
   AHX_CUDA(ctx, cudaMemcpyAsync(signs, ctx->d_signs.p, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaMemcpyAsync(counts, ctx->d_counts.p, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
-  AHX_CUDA(ctx, cudaMemcpyAsync(&fs, d_final, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  AHX_CUDA(ctx, cudaMemcpyAsync(&fs, d_final + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (trace && L) AHX_CUDA(ctx, cudaMemcpyAsync(trace, ctx->d_trace.p, sizeof(double) * 2 * L, cudaMemcpyDeviceToHost, ctx->stream));
   if (step_accepted && L) AHX_CUDA(ctx, cudaMemcpyAsync(step_accepted, ctx->d_stepacc.p, L, cudaMemcpyDeviceToHost, ctx->stream));
   AHX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

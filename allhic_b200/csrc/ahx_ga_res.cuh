@@ -451,14 +451,38 @@ __device__ __forceinline__ IslScratch isl_scratch(unsigned char *p) {
 // (best first, lowest index on ties) or its complement (worst first, lowest index on ties).  Whole block.
 __device__ __forceinline__ void isl_select_k(const double *fit, int P, int k, bool worst, int *out, const IslScratch &sc) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // populations up to kSelReg * kRThreads: every thread reads its share of the fitness array ONCE and the k rounds
+  // run on registers (k sweeps of the array from L2 were most of the import's time at 8 islands)
+  constexpr int kSelReg = 12;
+  const bool in_regs = P <= kSelReg * kRThreads;
+  unsigned long long keys[kSelReg];
+  if (in_regs) {
+#pragma unroll
+    for (int r = 0; r < kSelReg; ++r) {
+      const int i = tid + r * kRThreads;
+      unsigned long long key = i < P ? fit_key(__ldcg(fit + i)) : 0ULL;
+      if (worst) key = ~key;
+      keys[r] = key;
+    }
+  }
   unsigned long long lk = 0; int li = -1;                       // previous winner: candidates must be strictly greater
   for (int r = 0; r < k; ++r) {
     unsigned long long bk = ~0ULL; int bi = 0x7fffffff;
-    for (int i = tid; i < P; i += kRThreads) {
-      unsigned long long key = fit_key(__ldcg(fit + i));
-      if (worst) key = ~key;
-      const bool after = r == 0 || key > lk || (key == lk && i > li);
-      if (after && (key < bk || (key == bk && i < bi))) { bk = key; bi = i; }
+    if (in_regs) {
+#pragma unroll
+      for (int j = 0; j < kSelReg; ++j) {
+        const int i = tid + j * kRThreads;
+        const unsigned long long key = keys[j];
+        const bool after = r == 0 || key > lk || (key == lk && i > li);
+        if (i < P && after && (key < bk || (key == bk && i < bi))) { bk = key; bi = i; }
+      }
+    } else {
+      for (int i = tid; i < P; i += kRThreads) {
+        unsigned long long key = fit_key(__ldcg(fit + i));
+        if (worst) key = ~key;
+        const bool after = r == 0 || key > lk || (key == lk && i > li);
+        if (after && (key < bk || (key == bk && i < bi))) { bk = key; bi = i; }
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -537,17 +561,22 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
       const int WR = (2 * q.P + 31) / 32;
       if (tid < m) sc.rows[tid] = mask_select(rused, rpref, WR, static_cast<uint32_t>(tid), true, 2 * q.P);
       __syncthreads();
-      // migrant j: elite j % ne of the (j / ne)-th OTHER island, in island order
-      for (int j = 0; j < m; ++j) {
-        const int s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1, e = j % ne;
+      // migrant j: elite j % ne of the (j / ne)-th OTHER island, in island order; one warp copies one migrant's
+      // two rows, all migrants at once, then thread 0 walks them in order (first of equals wins the hall of fame)
+      for (int j = tid >> 5; j < m; j += kRThreads / 32) {
+        const int lane = tid & 31, s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1, e = j % ne;
         const unsigned char *slot = mine + flags_b + (static_cast<size_t>(src) * 2 + par) * slot_b;
         const int *st = reinterpret_cast<const int *>(slot + head_b);
         const uint32_t *sx = reinterpret_cast<const uint32_t *>(st + static_cast<size_t>(ne) * L);
         int *pt = q.pool + static_cast<size_t>(sc.rows[j]) * L;
         uint32_t *px = q.xpool + static_cast<size_t>(sc.rows[j]) * N;
-        for (int i = tid; i < L; i += kRThreads) pt[i] = __ldcg(st + static_cast<size_t>(e) * L + i);
-        for (int i = tid; i < N; i += kRThreads) px[i] = __ldcg(sx + static_cast<size_t>(e) * N + i);
-        if (tid == 0) {
+        for (int i = lane; i < L; i += 32) pt[i] = __ldcg(st + static_cast<size_t>(e) * L + i);
+        for (int i = lane; i < N; i += 32) px[i] = __ldcg(sx + static_cast<size_t>(e) * N + i);
+      }
+      if (tid == 0) {
+        for (int j = 0; j < m; ++j) {
+          const int s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1, e = j % ne;
+          const unsigned char *slot = mine + flags_b + (static_cast<size_t>(src) * 2 + par) * slot_b;
           const double f = __ldcg(reinterpret_cast<const double *>(slot) + 1 + e);
           const int ind = sc.sel[kIslMaxMigrants + j];
           rowc[ind] = sc.rows[j]; fitc[ind] = f;

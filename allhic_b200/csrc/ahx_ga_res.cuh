@@ -124,7 +124,7 @@ __device__ __forceinline__ void remap_of(const MutPlan &mp, int L, const int *pt
 constexpr int kIslMaxMigrants = 64;          // n_elite * (n_islands - 1) at most
 // island scratch in shared memory: per-warp (key, index) pairs of the block-wide selection, the last
 // winner, the selected individuals (elites, then worst) and the migrants' pool rows
-constexpr size_t kIslScratchBytes = 16 * (kRThreads / 32) + 32 + 4 * (3 * kIslMaxMigrants) + 16;
+constexpr size_t kIslScratchBytes = 2 * 16 * (kRThreads / 32) + 32 + 4 * (3 * kIslMaxMigrants) + 16 + 8 * kIslMaxMigrants;
 // The two elementwise maps of a slot (the operator code the persistent kernel runs; ahx_mutate_remap
 // applies exactly these to one tour for the bit-exact operator tests).
 // coordinate of contig c in the child, from its coordinate x in the parent:
@@ -429,18 +429,20 @@ __device__ __forceinline__ long long global_timer_ns() {
 }
 
 struct IslScratch {
-  unsigned long long *wkey;   // [warps]
-  int *widx;                  // [warps]
-  unsigned long long *last;   // [1] key of the previous winner
+  unsigned long long *wkey;   // [2][warps] (double buffered by selection round: one block barrier per round)
+  int *widx;                  // [2][warps]
+  unsigned long long *last;   // [1] key of the previous winner (large populations' path)
   int *last_idx;              // [1] (and [2]: time-out flag)
   int *sel;                   // [2 * kIslMaxMigrants] selected individuals
   int *rows;                  // [kIslMaxMigrants] pool rows of the migrants
+  double *mfit;               // [kIslMaxMigrants] fitness of the migrants
 };
 __device__ __forceinline__ IslScratch isl_scratch(unsigned char *p) {
   IslScratch s;
-  s.wkey = reinterpret_cast<unsigned long long *>(p); p += 8 * (kRThreads / 32);
+  s.wkey = reinterpret_cast<unsigned long long *>(p); p += 2 * 8 * (kRThreads / 32);
   s.last = reinterpret_cast<unsigned long long *>(p); p += 8;
-  s.widx = reinterpret_cast<int *>(p); p += 4 * (kRThreads / 32);
+  s.mfit = reinterpret_cast<double *>(p); p += 8 * kIslMaxMigrants;
+  s.widx = reinterpret_cast<int *>(p); p += 2 * 4 * (kRThreads / 32);
   s.last_idx = reinterpret_cast<int *>(p); p += 16;
   s.sel = reinterpret_cast<int *>(p); p += 4 * 2 * kIslMaxMigrants;
   s.rows = reinterpret_cast<int *>(p);
@@ -449,52 +451,84 @@ __device__ __forceinline__ IslScratch isl_scratch(unsigned char *p) {
 
 // The k individuals with the smallest (key, index), ascending, into out[0..k): key = fit_key(fitness)
 // (best first, lowest index on ties) or its complement (worst first, lowest index on ties).  Whole block.
+// Populations up to kSelReg * kRThreads: every thread reads its share of the fitness array ONCE; a round is a
+// warp arg-min by shuffles, one block barrier, and the same arg-min over the warps' results done by every warp
+// for itself; the winner's owner retires it.  (r1: k sweeps of the array from L2, two barriers and a serial
+// merge per round -- 45 us for the 14 migrants of 8 islands, measured with AHX_GA_TIMING.)
 __device__ __forceinline__ void isl_select_k(const double *fit, int P, int k, bool worst, int *out, const IslScratch &sc) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // populations up to kSelReg * kRThreads: every thread reads its share of the fitness array ONCE and the k rounds
-  // run on registers (k sweeps of the array from L2 were most of the import's time at 8 islands)
-  constexpr int kSelReg = 12;
-  const bool in_regs = P <= kSelReg * kRThreads;
-  unsigned long long keys[kSelReg];
-  if (in_regs) {
-#pragma unroll
-    for (int r = 0; r < kSelReg; ++r) {
-      const int i = tid + r * kRThreads;
-      unsigned long long key = i < P ? fit_key(__ldcg(fit + i)) : 0ULL;
-      if (worst) key = ~key;
-      keys[r] = key;
-    }
-  }
-  unsigned long long lk = 0; int li = -1;                       // previous winner: candidates must be strictly greater
-  for (int r = 0; r < k; ++r) {
-    unsigned long long bk = ~0ULL; int bi = 0x7fffffff;
-    if (in_regs) {
-#pragma unroll
-      for (int j = 0; j < kSelReg; ++j) {
-        const int i = tid + j * kRThreads;
-        const unsigned long long key = keys[j];
-        const bool after = r == 0 || key > lk || (key == lk && i > li);
-        if (i < P && after && (key < bk || (key == bk && i < bi))) { bk = key; bi = i; }
-      }
-    } else {
-      for (int i = tid; i < P; i += kRThreads) {
-        unsigned long long key = fit_key(__ldcg(fit + i));
-        if (worst) key = ~key;
-        const bool after = r == 0 || key > lk || (key == lk && i > li);
-        if (after && (key < bk || (key == bk && i < bi))) { bk = key; bi = i; }
-      }
-    }
+  constexpr int kSelReg = 12, NW = kRThreads / 32;
+  constexpr unsigned long long kNoKey = ~0ULL; constexpr int kNoIdx = 0x7fffffff;
+  auto better = [](unsigned long long ka, int ia, unsigned long long kb, int ib) { return ka < kb || (ka == kb && ia < ib); };
+  auto warp_argmin = [&](unsigned long long &bk, int &bi) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
       const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, d);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
-      if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+      if (better(ok, oi, bk, bi)) { bk = ok; bi = oi; }
     }
+  };
+  if (P <= kSelReg * kRThreads) {
+    unsigned long long keys[kSelReg];
+#pragma unroll
+    for (int j = 0; j < kSelReg; ++j) {
+      const int i = tid + j * kRThreads;
+      unsigned long long key = i < P ? fit_key(__ldcg(fit + i)) : 0ULL;
+      if (worst) key = ~key;
+      keys[j] = i < P ? key : kNoKey;
+    }
+    // lane-local and warp-local minima are cached: a round only recomputes them in the thread / warp that owned
+    // the previous winner, every other warp just redoes the 24-entry arg-min over the warps' results
+    auto local_min = [&](unsigned long long &bk, int &bi) {
+      bk = kNoKey; bi = kNoIdx;
+#pragma unroll
+      for (int j = 0; j < kSelReg; ++j) {
+        const int i = keys[j] == kNoKey ? kNoIdx : tid + j * kRThreads;      // retired / beyond the end
+        if (better(keys[j], i, bk, bi)) { bk = keys[j]; bi = i; }
+      }
+    };
+    unsigned long long mk; int mi;                                           // this thread's best candidate
+    local_min(mk, mi);
+    bool dirty = true;                                                       // this warp's entry needs recomputing
+    for (int r = 0; r < k; ++r) {
+      unsigned long long *wk = sc.wkey + (r & 1) * NW; int *wi = sc.widx + (r & 1) * NW;
+      const unsigned long long *wk_prev = sc.wkey + ((r & 1) ^ 1) * NW; const int *wi_prev = sc.widx + ((r & 1) ^ 1) * NW;
+      unsigned long long bk = mk; int bi = mi;
+      if (dirty) warp_argmin(bk, bi);                                        // warp-uniform condition
+      if (lane == 0) {
+        if (dirty) { wk[wid] = bk; wi[wid] = bi; }
+        else { wk[wid] = wk_prev[wid]; wi[wid] = wi_prev[wid]; }
+      }
+      __syncthreads();
+      bk = lane < NW ? wk[lane] : kNoKey; bi = lane < NW ? wi[lane] : kNoIdx;
+      warp_argmin(bk, bi);                                                   // every warp: the block's winner
+      if (tid == 0) out[r] = bi;
+      dirty = bi != kNoIdx && ((bi % kRThreads) >> 5) == wid;                // the winner lives in this warp
+      if (bi != kNoIdx && bi % kRThreads == tid) {                           // its owner retires it
+#pragma unroll
+        for (int j = 0; j < kSelReg; ++j)
+          if (tid + j * kRThreads == bi) keys[j] = kNoKey;
+        local_min(mk, mi);
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  unsigned long long lk = 0; int li = -1;                       // previous winner: candidates must be strictly greater
+  for (int r = 0; r < k; ++r) {
+    unsigned long long bk = kNoKey; int bi = kNoIdx;
+    for (int i = tid; i < P; i += kRThreads) {
+      unsigned long long key = fit_key(__ldcg(fit + i));
+      if (worst) key = ~key;
+      const bool after = r == 0 || key > lk || (key == lk && i > li);
+      if (after && better(key, i, bk, bi)) { bk = key; bi = i; }
+    }
+    warp_argmin(bk, bi);
     if (lane == 0) { sc.wkey[wid] = bk; sc.widx[wid] = bi; }
     __syncthreads();
     if (tid == 0) {
-      for (int w = 1; w < kRThreads / 32; ++w)
-        if (sc.wkey[w] < bk || (sc.wkey[w] == bk && sc.widx[w] < bi)) { bk = sc.wkey[w]; bi = sc.widx[w]; }
+      for (int w = 1; w < NW; ++w)
+        if (better(sc.wkey[w], sc.widx[w], bk, bi)) { bk = sc.wkey[w]; bi = sc.widx[w]; }
       out[r] = bi; *sc.last = bk; *sc.last_idx = bi;
     }
     __syncthreads();
@@ -502,6 +536,29 @@ __device__ __forceinline__ void isl_select_k(const double *fit, int P, int k, bo
   }
 }
 
+// n 4-byte words from src to dst by one warp: 16-byte vectors when both are aligned, four in flight per lane
+__device__ __forceinline__ void warp_copy_words(void *dst, const void *src, int n, int lane) {
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+    const int nv = n >> 2;
+    const int4 *s4 = reinterpret_cast<const int4 *>(src); int4 *d4 = reinterpret_cast<int4 *>(dst);
+    int i = lane;
+    for (; i + 96 < nv; i += 128) {
+      const int4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + 32), c = __ldcg(s4 + i + 64), d = __ldcg(s4 + i + 96);
+      d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = d;
+    }
+    for (; i < nv; i += 32) d4[i] = __ldcg(s4 + i);
+    for (int j = (nv << 2) + lane; j < n; j += 32) reinterpret_cast<int *>(dst)[j] = __ldcg(reinterpret_cast<const int *>(src) + j);
+  } else {
+    for (int i = lane; i < n; i += 32) reinterpret_cast<int *>(dst)[i] = __ldcg(reinterpret_cast<const int *>(src) + i);
+  }
+}
+
+#ifdef AHX_GA_TIMING
+__device__ long long g_isl_ticks[8];   // CTA 0, thread 0: clock64 totals of the exchange's phases
+#define AHX_ISL_TICK(i) do { if (cta == 0 && tid == 0) { const long long n_ = clock64(); g_isl_ticks[i] += n_ - tisl; tisl = n_; } } while (0)
+#else
+#define AHX_ISL_TICK(i) do { } while (0)
+#endif
 // One exchange at generation `gen` (a multiple of migrate_every; `cur` = gen & 1 is the population just
 // built).  Called by every thread of every CTA after the generation's bookkeeping.  Export: CTA c writes
 // this island's elites into the mailbox of island (island + 1 + c) mod W.  Import: CTA 0 waits for the
@@ -518,7 +575,11 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
   const size_t flags_b = isl_flags_bytes(W), head_b = isl_head_bytes(ne), slot_b = isl_slot_bytes(ne, L, N);
   const IslScratch sc = isl_scratch(isl_smem);
   const bool exporter = cta < W - 1;
+#ifdef AHX_GA_TIMING
+  long long tisl = clock64();
+#endif
   if (exporter || cta == 0) isl_select_k(fitc, q.P, ne, false, sc.sel, sc);          // elites: the same list in every CTA that needs it
+  AHX_ISL_TICK(0);   // elite selection
   for (int c = cta; c < W - 1; c += G) {
     const int dst = (q.island + 1 + c) % W;
     unsigned char *slot = isl->mbox[dst] + flags_b + (static_cast<size_t>(q.island) * 2 + par) * slot_b;
@@ -527,17 +588,16 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
     if (tid < ne) head[1 + tid] = __ldcg(fitc + sc.sel[tid]);
     int *dt = reinterpret_cast<int *>(slot + head_b);
     uint32_t *dx = reinterpret_cast<uint32_t *>(dt + static_cast<size_t>(ne) * L);
-    for (int e = 0; e < ne; ++e) {
-      const int row = __ldcg(rowc + sc.sel[e]);
-      const int *pt = q.pool + static_cast<size_t>(row) * L;
-      const uint32_t *px = q.xpool + static_cast<size_t>(row) * N;
-      for (int i = tid; i < L; i += kRThreads) dt[static_cast<size_t>(e) * L + i] = __ldcg(pt + i);
-      for (int i = tid; i < N; i += kRThreads) dx[static_cast<size_t>(e) * N + i] = __ldcg(px + i);
+    for (int w = tid >> 5; w < 2 * ne; w += kRThreads / 32) {          // one warp per (elite, tour row | coordinate row)
+      const int e = w >> 1, row = __ldcg(rowc + sc.sel[e]);
+      if (w & 1) warp_copy_words(dx + static_cast<size_t>(e) * N, q.xpool + static_cast<size_t>(row) * N, N, tid & 31);
+      else warp_copy_words(dt + static_cast<size_t>(e) * L, q.pool + static_cast<size_t>(row) * L, L, tid & 31);
     }
     __threadfence_system();
     __syncthreads();
     if (tid == 0) st_release_sys_u64(reinterpret_cast<unsigned long long *>(isl->mbox[dst] + 32 * static_cast<size_t>(q.island)), epoch);
   }
+  AHX_ISL_TICK(1);   // export
   if (cta == 0) {
     const unsigned char *mine = isl->mbox[q.island];
     if (tid == 0) sc.last_idx[2] = 0;
@@ -552,6 +612,7 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
     }
     __syncthreads();
     const bool timed_out = sc.last_idx[2] != 0;
+    AHX_ISL_TICK(2);   // wait for the peers' flags
     const int m = ne * (W - 1);
     double g_best = isl->g_best; long long g_updated = isl->g_updated;
     int win = -1;                                                                 // thread 0: the migrant that beats the hall of fame
@@ -561,28 +622,31 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
       const int WR = (2 * q.P + 31) / 32;
       if (tid < m) sc.rows[tid] = mask_select(rused, rpref, WR, static_cast<uint32_t>(tid), true, 2 * q.P);
       __syncthreads();
-      // migrant j: elite j % ne of the (j / ne)-th OTHER island, in island order; one warp copies one migrant's
-      // two rows, all migrants at once, then thread 0 walks them in order (first of equals wins the hall of fame)
-      for (int j = tid >> 5; j < m; j += kRThreads / 32) {
-        const int lane = tid & 31, s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1, e = j % ne;
-        const unsigned char *slot = mine + flags_b + (static_cast<size_t>(src) * 2 + par) * slot_b;
-        const int *st = reinterpret_cast<const int *>(slot + head_b);
+      AHX_ISL_TICK(3);   // worst selection + free rows
+      // migrant j: elite j % ne of the (j / ne)-th OTHER island, in island order.  One warp per (migrant, row) copies,
+      // thread j adopts migrant j (row id + fitness of the individual it replaces), then thread 0 walks the m
+      // fitness values in order (first of equals wins the hall of fame).
+      auto slot_of = [&](int j) {
+        const int s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1;
+        return mine + flags_b + (static_cast<size_t>(src) * 2 + par) * slot_b;
+      };
+      for (int w = tid >> 5; w < 2 * m; w += kRThreads / 32) {
+        const int j = w >> 1, e = j % ne;
+        const int *st = reinterpret_cast<const int *>(slot_of(j) + head_b);
         const uint32_t *sx = reinterpret_cast<const uint32_t *>(st + static_cast<size_t>(ne) * L);
-        int *pt = q.pool + static_cast<size_t>(sc.rows[j]) * L;
-        uint32_t *px = q.xpool + static_cast<size_t>(sc.rows[j]) * N;
-        for (int i = lane; i < L; i += 32) pt[i] = __ldcg(st + static_cast<size_t>(e) * L + i);
-        for (int i = lane; i < N; i += 32) px[i] = __ldcg(sx + static_cast<size_t>(e) * N + i);
+        if (w & 1) warp_copy_words(q.xpool + static_cast<size_t>(sc.rows[j]) * N, sx + static_cast<size_t>(e) * N, N, tid & 31);
+        else warp_copy_words(q.pool + static_cast<size_t>(sc.rows[j]) * L, st + static_cast<size_t>(e) * L, L, tid & 31);
       }
-      if (tid == 0) {
-        for (int j = 0; j < m; ++j) {
-          const int s0 = j / ne, src = s0 < q.island ? s0 : s0 + 1, e = j % ne;
-          const unsigned char *slot = mine + flags_b + (static_cast<size_t>(src) * 2 + par) * slot_b;
-          const double f = __ldcg(reinterpret_cast<const double *>(slot) + 1 + e);
-          const int ind = sc.sel[kIslMaxMigrants + j];
-          rowc[ind] = sc.rows[j]; fitc[ind] = f;
-          if (f < hof_fit) { hof_fit = f; updated = gen; win = j; }                 // a migrant beats the hall of fame (first of equals)
-        }
+      if (tid < m) {
+        const double f = __ldcg(reinterpret_cast<const double *>(slot_of(tid)) + 1 + tid % ne);
+        const int ind = sc.sel[kIslMaxMigrants + tid];
+        rowc[ind] = sc.rows[tid]; fitc[ind] = f;
+        sc.mfit[tid] = f;
       }
+      __syncthreads();
+      if (tid == 0)
+        for (int j = 0; j < m; ++j)
+          if (sc.mfit[j] < hof_fit) { hof_fit = sc.mfit[j]; updated = gen; win = j; }   // a migrant beats the hall of fame (first of equals)
       if (tid == 0) {
         double nb = hof_fit;
         for (int s = 0; s < W; ++s)
@@ -607,13 +671,21 @@ __device__ __forceinline__ void ga_island_exchange(const GaRes &q, int N, long l
       uint32_t *used_cur = q.used + static_cast<size_t>(gen % 3) * ga_wr_pad(q.P);
       for (int i = tid; i < ga_wr_pad(q.P); i += kRThreads) used_cur[i] = 0u;
       __syncthreads();
-      for (int i = tid; i < q.P; i += kRThreads) { const int r = __ldcg(rowc + i); atomicOr(used_cur + (r >> 5), 1u << (r & 31)); }
+      for (int i0 = tid; i0 < q.P; i0 += 8 * kRThreads) {                           // loads first, then the (fire-and-forget) atomics
+        int rr[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rr[u] = i0 + u * kRThreads < q.P ? __ldcg(rowc + i0 + u * kRThreads) : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (rr[u] >= 0) atomicOr(used_cur + (rr[u] >> 5), 1u << (rr[u] & 31));
+      }
     }
     if (tid == 0) { isl->x_hof_fit = hof_fit; isl->x_updated = updated; }
+    AHX_ISL_TICK(4);   // copies + bookkeeping + row map
   }
   ++nsync;
   grid_barrier(q.gbar, nsync * static_cast<unsigned int>(G));
   hof_fit = __ldcg(&isl->x_hof_fit); updated = __ldcg(&isl->x_updated); stop = __ldcg(&isl->x_stop);
+  AHX_ISL_TICK(5);   // closing barrier
 }
 
 // SUB: the tours cover a subset of the group's contigs (L < N: a resumed run whose tour file lists fewer
@@ -843,6 +915,9 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
   if (tid == kRThreads - 32 && cta == 0)
     printf("cta 0 slot thread: to-slot %lld  select+plan %lld  tournament+row %lld  remap_of %lld  finish %lld  back %lld  publish+clear %lld  sync %lld  batches+barrier %lld\n",
            tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7], tq[8]);
+  if (tid == 0 && cta == 0 && q.n_islands > 1)
+    printf("island %d exchange phases (cycles, totals): elites %lld  export %lld  wait-flags %lld  worst+rows %lld  import %lld  barrier %lld\n",
+           q.island, g_isl_ticks[0], g_isl_ticks[1], g_isl_ticks[2], g_isl_ticks[3], g_isl_ticks[4], g_isl_ticks[5]);
   if (tid == 0 && (cta == 0 || cta == G - 1))
     printf("cta %d (%d batches/gen at the end): rowmap %lld  slots %lld  build+score %lld  barrier %lld  mask+hof %lld  exchange %lld cycles over %lld generations\n",
            cta, 0, tph[0], tph[1], tph[2], tph[3], tph[4], tph[5], n_gens);

@@ -680,7 +680,7 @@ static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double m
   const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
   const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
   auto try_T = [&](int t) {
-    const int G = static_cast<int>(std::min<double>(ctx->sm_count, std::max(1.0, std::ceil(1.25 * expect / t))));
+    const int G = static_cast<int>(std::min<double>(ctx->sm_count, std::max(1.0, std::ceil(1.2 * expect / t))));
     const int nbmax = ((P + t - 1) / t + G - 1) / G;
     for (int stream = 0; stream < 2; ++stream) {   // table resident in shared memory if it fits, streamed otherwise
       if (stream ? no_stream : only_stream) continue;

@@ -233,15 +233,20 @@ __global__ void build_dense_kernel(const int *__restrict__ pa, const int *__rest
 __global__ void __launch_bounds__(kBlock)
 eval_q_kernel(const int *__restrict__ tours, int shared_tour, int P, int L, int N, const long long *__restrict__ sizes,
               const unsigned char *__restrict__ signs, const int *__restrict__ pa, const int *__restrict__ pb,
-              const int *__restrict__ slots, const int *__restrict__ hist, int E, double *__restrict__ out) {
+              const int *__restrict__ slots, const int *__restrict__ hist, int E, double *__restrict__ out,
+              unsigned char *gscratch, size_t gstride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ long long scan_scratch[kWarps];
   __shared__ double red_scratch[kWarps];
-  long long *cum = reinterpret_cast<long long *>(smem_raw);
-  int *pos = reinterpret_cast<int *>(smem_raw + sizeof(long long) * static_cast<size_t>(L));
+  // the per-individual arrays live in shared memory, or -- groups beyond ~13 000 contigs -- in this CTA's slice of a
+  // global scratch buffer (L2-resident; the CTA then walks its individuals p = blockIdx.x, + gridDim.x, ...)
+  unsigned char *base = gscratch ? gscratch + static_cast<size_t>(blockIdx.x) * gstride : smem_raw;
+  long long *cum = reinterpret_cast<long long *>(base);
+  int *pos = reinterpret_cast<int *>(base + sizeof(long long) * static_cast<size_t>(L));
   int *tig = pos + N;
   unsigned char *sg = reinterpret_cast<unsigned char *>(tig + L);
-  const int tid = threadIdx.x, p = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int p = blockIdx.x; p < P; p += gridDim.x) {
   const int *src = tours + (shared_tour ? 0 : static_cast<size_t>(p) * L);
   const unsigned char *sgsrc = signs + static_cast<size_t>(p) * N;
   for (int i = tid; i < N; i += kBlock) { pos[i] = -1; sg[i] = sgsrc[i]; }
@@ -282,6 +287,8 @@ eval_q_kernel(const int *__restrict__ tours, int shared_tour, int P, int L, int 
   }
   const double s = block_sum(acc, red_scratch, tid);
   if (tid == 0) out[p] = 0.0 - s;
+  __syncthreads();   // the arrays are reused by the CTA's next individual
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -549,10 +556,19 @@ int launch_eval_q(ahx_ctx *ctx, const int32_t *d_tours, int shared_tour, const u
                   double *d_out, cudaStream_t s) {
   if (P == 0) return AHX_OK;
   const size_t smem = sizeof(long long) * static_cast<size_t>(L) + sizeof(int) * (static_cast<size_t>(ctx->N) + L) + ctx->N;
-  if (smem + 1024 > ctx->smem_optin) return fail(ctx, AHX_ERR_ARG, "ahx_eval_q: group too large for shared memory");
   AHX_CUDA(ctx, opt_in_smem(eval_q_kernel, ctx->smem_optin));
-  eval_q_kernel<<<P, kBlock, smem, s>>>(d_tours, shared_tour, P, L, ctx->N, ctx->d_sizes.p, d_signs, ctx->d_pa.p, ctx->d_pb.p,
-                                        ctx->d_slots.p, ctx->d_hist.p, static_cast<int>(ctx->E), d_out);
+  const bool force_global = getenv("AHX_EVALQ_GLOBAL") && atoi(getenv("AHX_EVALQ_GLOBAL"));   // test knob
+  if (smem + 1024 > ctx->smem_optin || force_global) {
+    // 17 N bytes per individual do not fit an SM's shared memory: one slice of a global scratch buffer per CTA
+    const size_t stride = (smem + 255) & ~static_cast<size_t>(255);
+    const int grid = std::min<int>(P, 4 * ctx->sm_count);
+    AHX_CUDA(ctx, ctx->d_qscratch.reserve(stride * grid));
+    eval_q_kernel<<<grid, kBlock, 0, s>>>(d_tours, shared_tour, P, L, ctx->N, ctx->d_sizes.p, d_signs, ctx->d_pa.p, ctx->d_pb.p,
+                                           ctx->d_slots.p, ctx->d_hist.p, static_cast<int>(ctx->E), d_out, ctx->d_qscratch.p, stride);
+  } else {
+    eval_q_kernel<<<P, kBlock, smem, s>>>(d_tours, shared_tour, P, L, ctx->N, ctx->d_sizes.p, d_signs, ctx->d_pa.p, ctx->d_pb.p,
+                                          ctx->d_slots.p, ctx->d_hist.p, static_cast<int>(ctx->E), d_out, nullptr, 0);
+  }
   ctx->launches++;
   AHX_CUDA(ctx, cudaGetLastError());
   return AHX_OK;
@@ -760,7 +776,7 @@ void ahx_destroy(ahx_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);          // this context's work only: other contexts of the process keep running
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   for (auto &kv : ctx->isl_opened) cudaIpcCloseMemHandle(kv.second);
-  ctx->d_mbox.release(); ctx->d_isl.release();
+  ctx->d_mbox.release(); ctx->d_isl.release(); ctx->d_qscratch.release();
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   ctx->d_sizes.release(); ctx->d_sizes32.release(); ctx->d_coo16.release(); ctx->d_coo32.release(); ctx->d_coo16o.release(); ctx->d_coo32o.release(); for (auto &b : ctx->d_rpairs) b.release(); for (auto &b : ctx->d_rraw) b.release(); for (auto &b : ctx->d_rnl8) b.release(); ctx->d_pa.release(); ctx->d_pb.release();
   ctx->d_slots.release(); ctx->d_hist.release(); ctx->d_M.release(); ctx->d_adj_ptr.release(); ctx->d_adj_e.release();

@@ -163,6 +163,7 @@ struct ahx_ctx {
   ahx::DevBuf<uint32_t> d_gmask;              // mutation masks of three generations (published two ahead)
   ahx::DevBuf<uint32_t> d_xpool;              // coordinate row of every pool row
   // islands: own mailbox, the table of peer mailboxes, IPC mappings opened so far (handle bytes -> pointer)
+  ahx::DevBuf<unsigned char> d_qscratch;      // eval_q_kernel's per-CTA arrays for groups too large for shared memory
   ahx::DevBuf<unsigned char> d_mbox;
   ahx::DevBuf<ahx::GaIslands> d_isl;
   bool isl_connected = false;

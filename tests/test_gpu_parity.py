@@ -195,6 +195,26 @@ def test_eval_q_fixture_and_synth(fix, syn):
             assert close(got[k], orc.evaluate_q())
 
 
+def test_eval_q_global_scratch_path_is_bit_identical(syn, monkeypatch):
+    """Groups whose 17 N bytes of per-individual arrays exceed an SM's shared memory (N > ~13 000) keep them in a
+    per-CTA slice of a global buffer and walk the individuals grid-stride: same arithmetic, same bits."""
+    eng, clm, orc = syn
+    rng = np.random.default_rng(33)
+    n = clm.N
+    tours = np.stack([rng.permutation(n) for _ in range(700)]).astype(np.int32)     # more individuals than CTAs
+    signs = rand_signs(rng, n, 700)
+    want = eng.eval_q(tours, signs)
+    monkeypatch.setenv("AHX_EVALQ_GLOBAL", "1")
+    got = eng.eval_q(tours, signs)
+    assert (got == want).all()
+    sub = np.ascontiguousarray(tours[:5, : n // 2])
+    got_sub = eng.eval_q(sub, signs[:5])
+    monkeypatch.delenv("AHX_EVALQ_GLOBAL")
+    assert (got_sub == eng.eval_q(sub, signs[:5])).all()
+    orc.set_tour(tours[3]); orc.set_signs(signs[3])
+    assert close(got[3], orc.evaluate_q())
+
+
 def test_eval_q_general_slot_table(engine, tmp_path):
     """CLM written in both directions with missing orientations: the 8-slot table
     must reproduce the map lookups of Q() (orientation.go:145-150)."""

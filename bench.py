@@ -44,7 +44,9 @@ try:
 except Exception:
     pass
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
-NCU_DRAM_BYTES_PER_LAUNCH = {("eval_m_res_kernel", "config3", 8000): 64223232 + 508160}
+NCU_DRAM_BYTES_PER_LAUNCH = {("eval_m_res_kernel", "config3", 8000): 64222976 + 442880}      # profiles/r2_ncu_full_summary.txt
+# ga_persist_kernel: one 30-generation launch at config3 read 27 317 760 B and wrote 571 921 408 B (profiles/r2_ncu_ga_persist_summary.txt)
+NCU_DRAM_BYTES_PER_GENERATION = {("ga_persist_kernel", "config3", 8000): (27317760 + 571921408) / 30.0}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 GA_GENS_PER_STEP = 500          # evaluate.go:294: the reference logs every 500 generations; one step = one such period
@@ -599,7 +601,9 @@ def main():
     bound = max(legs, key=lambda k: legs[k][0] / legs[k][1])
     kname = {3: "ga_persist_kernel (pair table streamed)", 2: "ga_persist_kernel", 1: "ga_plan_kernel + ga_apply_kernel", 0: "ga_generation_kernel"}[ga_kernel]
     roof = {"kernel": kname, "bound": bound, "achieved": legs[bound][0], "peak": legs[bound][1], "unit": legs[bound][2], "frac": legs[bound][0] / legs[bound][1],
-            "traffic": None,
+            "traffic": (NCU_DRAM_BYTES_PER_GENERATION[("ga_persist_kernel", args.workload, P)] * gens_done / max(1, ga_launches))
+            if ga_kernel == 2 and ("ga_persist_kernel", args.workload, P) in NCU_DRAM_BYTES_PER_GENERATION else None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of a 30-generation launch of this kernel at this size (profiles/r2_ncu_ga_persist_summary.txt), scaled to the generations of one launch here; null = no capture at this size",
             "peak_source": {"fp64": "DFMA microbenchmark measured live by this run (ahx_probe_fp64; MEASURED_PEAKS.json has no fp64 figure)",
                             "smem": "128 B/clk/SM x %d SMs x %.0f MHz" % (eng.sm_count(), sm_mhz), "hbm": HBM_PEAK_SRC}[bound],
             "algorithmic_per_eval": {"stored_pairs_E": E, "fp64_flop": 10.0 * E, "smem_gather_bytes": 8 * E, "hbm_bytes": 16 * L},

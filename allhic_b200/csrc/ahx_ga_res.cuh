@@ -146,6 +146,15 @@ __device__ __forceinline__ int slot_source(const GaSlot &s, int i, int L) {
   return src;
 }
 
+// The M mutated offspring of a generation are dealt out evenly: CTA c scores the mutants first .. first + n - 1
+// (n = M / G or M / G + 1), T at a time; its last batch is then usually ragged and only pays for its live tours
+// (res_run_batches).  Batch-granular dealing (batch b -> CTA b mod G) left a third of the CTAs one whole batch short.
+__device__ __forceinline__ void ga_deal(uint32_t M, int cta, int G, uint32_t *first, int *n) {
+  const uint32_t qn = M / static_cast<uint32_t>(G), r = M % static_cast<uint32_t>(G), c = static_cast<uint32_t>(cta);
+  *first = c * qn + min(c, r);
+  *n = static_cast<int>(qn + (c < r ? 1u : 0u));
+}
+
 // first slot of the CTA's slot table that thread `tid` handles (then every kRThreads-th)
 __device__ __forceinline__ int slot_of_thread(int tid) {
   constexpr int NWARP = kRThreads / 32;
@@ -182,7 +191,7 @@ __device__ __forceinline__ void atomic_min_u128(ulonglong2 *addr, unsigned long 
 
 template <int T, bool SUB = false>
 struct GaSrc {
-  const int *pool; int *pool_w; const uint32_t *xpool; uint32_t *xpool_w; const GaSlot *slots; double *fitn; ulonglong2 *gmin; double hof_fit;
+  const int *pool; int *pool_w; const uint32_t *xpool; uint32_t *xpool_w; const GaSlot *slots; double *fitn; ulonglong2 *gmin; double hof_fit; int nlive;   // nlive: this CTA's mutated offspring (slots 0 .. nlive-1)
   // Lane l works on tour t = l mod T and on contig (then position) base + l / T: 32/T consecutive
   // elements of each tour per warp instruction (one 32-byte sector per tour), and the coordinate
   // store X[c*T + t] of a warp is 32 consecutive words.
@@ -222,6 +231,8 @@ struct GaSrc {
     named_bar_sync(BAR, NW * 32);   // X[buf] is complete
   }
   __device__ __forceinline__ void prefetch(int, int) const {}
+  static constexpr bool kRaggedBatches = true;    // every CTA's last batch of every generation
+  __device__ __forceinline__ int live(int j) const { return min(T, max(0, nlive - j * T)); }
   __device__ __forceinline__ void store(int j, int t, double score) const {
     const GaSlot &sl = slots[j * T + t];
     if (sl.o >= 0) {
@@ -764,17 +775,18 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     const uint32_t glo = static_cast<uint32_t>(gg), ghi = static_cast<uint32_t>(gg >> 32);
     const uint32_t *mf = mflag_of(gg), *mp_ = mf + WMp;
     const uint32_t Mg = Mb[gg & 1];
-    const int nbt = (static_cast<int>(Mg) + T - 1) / T, nbl = cta < nbt ? (nbt - cta + G - 1) / G : 0;
+    uint32_t first; int nmine;
+    ga_deal(Mg, cta, G, &first, &nmine);
+    const int nbl = (nmine + T - 1) / T;
     GaSlot *sl_tab = reinterpret_cast<GaSlot *>(slot_base + static_cast<size_t>(gg & 1) * slot_bytes);
     uint32_t *used_nx = used_of(gg + 1);
     // slot s -> lane s / 24 of warp 23 - s % 24: one slot per WARP while there are at most 24 (their code paths differ:
     // operator, tournament round, so slots sharing a warp would run one after the other); the clones start at thread 0
     for (int s = slot_of_thread(tid); s < nbl * T; s += kRThreads) {
-      const int j = s / T, t = s % T;
-      const uint32_t mi = static_cast<uint32_t>((cta + j * G) * T + t);
+      const uint32_t mi = first + static_cast<uint32_t>(s);
       GaSlot sl{};
       sl.o = -1;
-      if (mi < Mg) {
+      if (s < nmine) {
         AHX_TICKQ(0);
         const int o = mask_select(mf, mp_, WM, mi, false, q.P);
         const MutPlan mp = plan_mutation(ph, glo, ghi, static_cast<uint32_t>(o), q.mut_prob, q.L);
@@ -851,8 +863,9 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     ulonglong2 *gmin_new = q.gmin + (gen + 1) % 3;
     GaSlot *slots = reinterpret_cast<GaSlot *>(slot_base + static_cast<size_t>(gen & 1) * slot_bytes);
     const uint32_t Mcur = Mb[gen & 1];
-    const int nb_total = (static_cast<int>(Mcur) + T - 1) / T;
-    const int nb_local = cta < nb_total ? (nb_total - cta + G - 1) / G : 0;
+    uint32_t first_mi; int n_mine;
+    ga_deal(Mcur, cta, G, &first_mi, &n_mine);
+    const int nb_local = (n_mine + T - 1) / T;
     // ---- the loads issued behind the previous barrier have landed: free-row select structure of this generation,
     // mask of the next one
     if (pend) {
@@ -864,8 +877,7 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     for (int s = slot_of_thread(tid); s < nb_local * T; s += kRThreads) {
       const int o = slots[s].o;
       if (o >= 0) {
-        const int j = s / T, t = s % T;
-        const int child = mask_select(rused, rpref, WR, static_cast<uint32_t>((cta + j * G) * T + t), true, 2 * q.P);
+        const int child = mask_select(rused, rpref, WR, first_mi + static_cast<uint32_t>(s), true, 2 * q.P);
         slots[s].child_row = child;
         rown[o] = child;
         atomicOr(used_new + (child >> 5), 1u << (child & 31));
@@ -884,7 +896,7 @@ __global__ void __launch_bounds__(kRThreads, 1) ga_persist_kernel(ResArgs g, GaR
     AHX_TICKQ(7);   // sync
     AHX_TICK(1);   // rest of the set-up
     // ---- score this CTA's batches; an individual that beats the hall of fame goes to gmin_new
-    GaSrc<T, SUB> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new, hof_fit};
+    GaSrc<T, SUB> src{q.pool, q.pool, q.xpool, q.xpool, slots, fitn, gmin_new, hof_fit, n_mine};
     res_run_batches<T, SUB, STREAM>(g, m, src, 0, 1, nb_local, kdone, table_ready);
     AHX_TICK(2);   // build + score
     ++nsync;

@@ -124,6 +124,8 @@ struct ResDirect {
     }
   };
   __device__ __forceinline__ int n_batches() const { return (P + T - 1) / T; }
+  static constexpr bool kRaggedBatches = false;   // at most the last batch of a call is ragged: not worth a specialised loop
+  __device__ __forceinline__ int live(int batch) const { return min(T, P - batch * T); }   // live tours: the first slots of the batch
   __device__ __forceinline__ int out_row(int batch, int t) const {
     const int p = batch * T + t;
     return p < P ? (rows ? rows[p] : p) : -1;
@@ -311,7 +313,8 @@ __device__ __forceinline__ double res_n(uint32_t n8x4) {
 
 // SCALED: p holds byte offsets (resident tables); otherwise contig indices a | b << 16 (the
 // streamed table of large groups, where N * 4T can exceed 16 bits).
-template <int T, bool SUB, bool SCALED>
+// TL: tours of the batch that are live (the first TL slots; a ragged last batch): the others cost nothing.
+template <int T, bool SUB, bool SCALED, int TL = T>
 __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, double n, double (&acc)[T]) {
   using V = typename XVec<T>::type;
   uint32_t xa[T], xb[T];
@@ -324,7 +327,7 @@ __device__ __forceinline__ void res_pair_terms(const uint32_t *X, uint32_t p, do
     x_unpack(*reinterpret_cast<const V *>(X + static_cast<size_t>(p >> 16) * T), xb);
   }
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
+  for (int t = 0; t < TL; ++t) {
     const uint32_t d = __usad(xa[t], xb[t], 0u);
     const bool in = SUB ? (d - 1u < kLimit2) : (d <= kLimit2);
     // exact uint32 -> double is (2^52 + d) - 2^52 with the high word 0x43300000; outside the window the
@@ -492,19 +495,34 @@ __device__ __forceinline__ void res_run_batches(const ResArgs &g, const ResSmem 
             pn[u] = table4[iu]; nn[u] = i + u * kRCT < nvec ? nl8x4[iu] : 0u;   // beyond the end: zero link counts
           }
         };
-        fetch(tid);
-        for (int i = tid; i < nvec; i += UI * kRCT) {
-          uint4 p[UI]; uint32_t n[UI];
+        // a batch with fewer live tours than slots (the last batch of a population; in the GA every CTA's last
+        // batch, since the mutants are dealt out evenly) skips the dead tours' arithmetic: T = 4 only
+        auto sweep_table = [&](auto live_tours) {
+          constexpr int TL = decltype(live_tours)::value;
+          fetch(tid);
+          for (int i = tid; i < nvec; i += UI * kRCT) {
+            uint4 p[UI]; uint32_t n[UI];
 #pragma unroll
-          for (int u = 0; u < UI; ++u) { p[u] = pn[u]; n[u] = nn[u]; }
-          if (i + UI * kRCT < nvec) fetch(i + UI * kRCT);
+            for (int u = 0; u < UI; ++u) { p[u] = pn[u]; n[u] = nn[u]; }
+            if (i + UI * kRCT < nvec) fetch(i + UI * kRCT);
 #pragma unroll
-          for (int u = 0; u < UI; ++u) {
-            res_pair_terms<T, SUB, true>(X, p[u].x, res_n<0>(n[u]), acc);
-            res_pair_terms<T, SUB, true>(X, p[u].y, res_n<1>(n[u]), acc);
-            res_pair_terms<T, SUB, true>(X, p[u].z, res_n<2>(n[u]), acc);
-            res_pair_terms<T, SUB, true>(X, p[u].w, res_n<3>(n[u]), acc);
+            for (int u = 0; u < UI; ++u) {
+              res_pair_terms<T, SUB, true, TL>(X, p[u].x, res_n<0>(n[u]), acc);
+              res_pair_terms<T, SUB, true, TL>(X, p[u].y, res_n<1>(n[u]), acc);
+              res_pair_terms<T, SUB, true, TL>(X, p[u].z, res_n<2>(n[u]), acc);
+              res_pair_terms<T, SUB, true, TL>(X, p[u].w, res_n<3>(n[u]), acc);
+            }
           }
+        };
+        if constexpr (T == 4 && Src::kRaggedBatches) {
+          switch (src.live(b)) {
+            case 1: sweep_table(std::integral_constant<int, 1>{}); break;
+            case 2: sweep_table(std::integral_constant<int, 2>{}); break;
+            case 3: sweep_table(std::integral_constant<int, 3>{}); break;
+            default: sweep_table(std::integral_constant<int, 4>{}); break;
+          }
+        } else {
+          sweep_table(std::integral_constant<int, T>{});
         }
       } else {
         constexpr int US = UI > 2 ? 2 : UI;   // at most half of the ring's stages in use, the other half loading

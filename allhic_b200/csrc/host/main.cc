@@ -171,6 +171,10 @@ int main(int argc, char **argv) {
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].ntigs > groups[b].ntigs; });   // ~N^2 work: longest first
   std::atomic<size_t> next{0};
   std::atomic<int> failed{0};
+  // AHX_FARM_TIMING=1: wall-clock offsets of every worker's milestones on stderr
+  const bool farm_timing = getenv("AHX_FARM_TIMING") && atoi(getenv("AHX_FARM_TIMING"));
+  const auto farm_t0 = std::chrono::steady_clock::now();
+  auto farm_now = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - farm_t0).count(); };
   std::mutex out_mu;
   std::vector<std::thread> workers;
   for (int w = 0; w < nworkers; ++w)
@@ -178,6 +182,7 @@ int main(int argc, char **argv) {
       const int dev = p.Device + w % ngpus;
       ahx_ctx *ctx = nullptr;
       if (ahx_create(dev, &ctx) != AHX_OK) { fprintf(stderr, "%s\n", ahx_last_error(nullptr)); return; }
+      if (farm_timing) fprintf(stderr, "farm: worker %d (device %d) has its context at %.3f s\n", w, dev, farm_now());
       for (size_t k = next++; k < order.size(); k = next++) {
         Group &g = groups[order[k]];
         allhic::logSetTag("[group " + std::to_string(g.idx) + "] ");
@@ -187,6 +192,7 @@ int main(int argc, char **argv) {
         const auto t0 = std::chrono::steady_clock::now();
         const bool ok = run_group(q, g, {ctx}, &text);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (farm_timing) fprintf(stderr, "farm: worker %d group %d from %.3f to %.3f s\n", w, g.idx, farm_now() - dt, farm_now());
         std::lock_guard<std::mutex> lk(out_mu);
         fwrite(text.data(), 1, text.size(), stdout);
         printf("%s %d %s device=%d seconds=%.3f\n", ok ? "AHX_GROUP_DONE" : "AHX_GROUP_FAILED", g.idx, g.re.c_str(), dev, dt);
@@ -196,6 +202,7 @@ int main(int argc, char **argv) {
       ahx_destroy(ctx);
     });
   for (auto &t : workers) t.join();
+  if (farm_timing) fprintf(stderr, "farm: all workers joined at %.3f s\n", farm_now());   // what follows (1.3 s on an 8-GPU box) is the driver tearing the process's CUDA contexts down; ending the process with _exit instead did not shorten it
   for (auto &g : groups) if (g.parsed) ahx_clm_free(g.parsed);   // groups no worker reached (every worker failed to start)
   return failed ? 1 : (next.load() >= order.size() ? 0 : 1);
 }

@@ -705,7 +705,6 @@ __global__ void ga_res_init_kernel(GaRes q, const int *__restrict__ init, const 
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * ga_wr_pad(q.P); i += gridDim.x * blockDim.x)
     q.used[i] = (i == 0) ? 1u : 0u;   // generation 0 references row 0 only
   if (blockIdx.x == 0 && threadIdx.x < 3) q.gmin[threadIdx.x] = make_ulonglong2(~0ULL, ~0ULL);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *q.gidx = 0x7fffffff;
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < q.L; i += blockDim.x) { q.pool[i] = init[i]; q.hof[i] = init[i]; }
     if (threadIdx.x == 0) {
@@ -730,7 +729,7 @@ static GaRes make_res(ahx_ctx *ctx) {
   q.pool = ctx->d_pop[0].p; q.rowof[0] = ctx->d_rowof[0].p; q.rowof[1] = ctx->d_rowof[1].p;
   q.fit[0] = ctx->d_fit[0].p; q.fit[1] = ctx->d_fit[1].p; q.hof = ctx->d_hof.p; q.st = ctx->d_state.p;
   q.gbar = ctx->d_gbar.p;
-  q.used = ctx->d_used.p; q.gmin = reinterpret_cast<ulonglong2 *>(ctx->d_gmin.p); q.gmask = ctx->d_gmask.p; q.gidx = reinterpret_cast<int *>(ctx->d_gbar.p + 1);
+  q.used = ctx->d_used.p; q.gmin = reinterpret_cast<ulonglong2 *>(ctx->d_gmin.p); q.gmask = ctx->d_gmask.p;
   const ahx_ga_params &p = ctx->ga_prm;
   q.n_islands = p.n_islands > 1 ? p.n_islands : 1; q.island = p.island; q.migrate_every = p.migrate_every; q.n_elite = p.n_elite;
   q.isl = ctx->d_isl.p;

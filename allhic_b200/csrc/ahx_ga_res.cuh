@@ -8,26 +8,31 @@
 // of its parent, so individuals are stored by reference: rowof[g & 1][i] is the
 // physical row of individual i of generation g in a pool of 2P rows.  An un-mutated
 // offspring inherits its parent's row id and fitness (no copy); a mutated offspring
-// gets a fresh row from the rows generation g does not reference (at least P of the 2P).
+// gets a fresh row from the rows generation g does not reference (at least P of the 2P;
+// bit maps in global memory, set with atomicOr while a generation is built).
 // The k-th mutated offspring (ascending index) takes the k-th free row, so the layout
 // is a pure function of the seed.
 //
-// One generation, every CTA (G = gridDim.x, 24 warps):
-//   1. bit mask of the pool rows the current generation references (from a byte map in
-//      global memory that the CTAs filled while they built that generation) + word prefix
-//   2. slot table: for the mutated offspring this CTA scores (batch b -> CTA b mod G):
-//      offspring index (select on the mutation mask), tournament parents, mutation plan,
-//      fresh row (select on the free rows)
-//   3. the CTA's share of un-mutated offspring (o = c, c + G, ...): tournament, inherit
-//   4. res_run_batches: the coordinates of T offspring at a time are built straight from
-//      the parent rows through the mutation's index remap (the child rows are written on the
-//      way), consumers score them (ahx_resident.cuh); atomicMin of the new fitness values
-//   5. (during 2-3) this CTA's words of the NEXT generation's mutation mask (first Philox draw
-//      of each offspring; independent of fitness) to global memory
-//   6. grid barrier; load the whole mask, word prefix
-//   7. bookkeeping (evaluate.go:287-306): only a mutated offspring can beat the hall of fame,
-//      so one load of the generation's minimum decides; an improvement (rare) costs a second
-//      barrier to agree on the lowest offspring index and copy its row
+// One generation g -> g + 1, every CTA (G = gridDim.x, 24 warps).  State that is ready in shared memory when it
+// starts: the mutation mask of g (+ word prefix), the bit map of the pool rows g references (+ prefix of the free ones).
+//   1. front half (started right behind the previous grid barrier, before that generation's bookkeeping):
+//      for the mutated offspring this CTA scores -- the M mutants are dealt out evenly, CTA c gets a contiguous
+//      run of them -- offspring index (select on the mask), mutation plan, tournament parent, the operator's two
+//      maps (remap_of: needs the parent's tour and coordinate rows); in other threads this CTA's share of the
+//      un-mutated offspring (o = c, c + G, ...): tournament, inherit row and fitness
+//   2. bookkeeping of generation g (evaluate.go:287-306) from its 128-bit minimum; the last CTA copies the
+//      winner's row to the hall of fame, nobody waits
+//   3. the TMA bulk copies issued when the barrier opened have landed: mask of g + 1 and row map of g, one block
+//      scan over both; back half: the k-th mutant takes the k-th free row
+//   4. housekeeping: this CTA's words of the mask of g + 2 (first Philox draw of each offspring; independent of
+//      fitness), clear the row map of g - 1, reset the minimum of g + 2
+//   5. res_run_batches: the coordinates of T offspring at a time are built straight from the parent rows through
+//      the mutation's maps (the child rows are written on the way), consumers score them (ahx_resident.cuh; a
+//      ragged last batch only pays for its live tours); an individual that beats the hall of fame enters the
+//      128-bit atomic minimum (fitness key, offspring index, pool row)
+//   6. grid barrier; the polling thread starts the bulk copies of step 3 for the next generation
+// Islands: at exchange generations bookkeeping + ga_island_exchange come first and the next generation starts
+// plainly (no speculation, maps reloaded).
 // Scores do not depend on which tours share a batch (each tour has its own accumulators
 // and a fixed summation order), tournaments and plans are functions of (seed, generation,
 // offspring): the run is bit-identical for any grid size and any T.
@@ -53,7 +58,6 @@ struct GaRes {
   uint32_t *used;       // [3][ga_wr_pad(P)] bit maps: bit r of used[g % 3] is set iff generation g references pool row r
   ulonglong2 *gmin;     // [3] best individual evaluated while building generation g (index g % 3) that beats the hall of fame: .y = order-preserving
                         // key of its fitness, .x = offspring index << 32 | pool row; 128-bit minimum, so the lowest index wins among equal fitness values
-  int *gidx;            // (legacy paths)
   uint32_t *gmask;      // [3][ga_wm_pad(P)] mutation masks of generations g (index g % 3), filled two generations ahead
   // islands (include/ahx.h "Islands"); n_islands <= 1: single population
   int n_islands, island, migrate_every, n_elite;

@@ -110,6 +110,30 @@ def test_abi_exports_every_declared_symbol(built_lib):
     assert built_lib.ahx_version() == 100
 
 
+def test_cgo_stub_binds_only_declared_entry_points():
+    """INTEGRATION.md's cgo stub is the reference-side binding a maintainer would add (it cannot be compiled here:
+    no Go toolchain).  Every C.ahx_* it calls must be declared in include/ahx.h or defined in the stub's own C
+    preamble, every struct field it touches must exist, and every reference call site the header cites must be bound."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```go\n(.*?)```", doc, re.S)
+    assert blocks, "no Go block in INTEGRATION.md"
+    go = "\n".join(blocks)
+    hdr = open(os.path.join(ROOT, "include", "ahx.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ahx_[a-z0-9_]+)\s*\(", hdr_nc))
+    types = set(re.findall(r"typedef struct (ahx_[a-z0-9_]+)", hdr_nc)) | set(re.findall(r"\}\s*(ahx_[a-z0-9_]+);", hdr_nc))
+    preamble = set(re.findall(r"static int (ahx_[a-z0-9_]+)\(", go))
+    used = set(re.findall(r"C\.(ahx_[a-z0-9_]+)", go))
+    assert used - declared - types - preamble == set(), used - declared - types - preamble
+    for must in ("ahx_clm_add_line", "ahx_clm_finalize", "ahx_create", "ahx_load_clm", "ahx_ga_run", "ahx_ga_run_islands", "ahx_eval_q",
+                 "ahx_flip_all", "ahx_flip_whole", "ahx_flip_one", "ahx_destroy"):
+        assert must in go, must
+    fields = set(re.findall(r"\bp\.([a-z_]+)", go))
+    params = hdr_nc[hdr_nc.index("typedef struct ahx_ga_params"):hdr_nc.index("} ahx_ga_params;")]
+    for f in fields:
+        assert re.search(r"\b%s;" % f, params), "ahx_ga_params has no field %s" % f
+
+
 def test_no_cpu_fallback(built_lib):
     """Without a device the product path must fail loudly, not compute on the CPU."""
     import allhic_b200 as A

@@ -45,8 +45,8 @@ except Exception:
     pass
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/)
 NCU_DRAM_BYTES_PER_LAUNCH = {("eval_m_res_kernel", "config3", 8000): 64222976 + 442880}      # profiles/r2_ncu_full_summary.txt
-# ga_persist_kernel: one 30-generation launch at config3 read 27 317 760 B and wrote 571 921 408 B (profiles/r2_ncu_ga_persist_summary.txt)
-NCU_DRAM_BYTES_PER_GENERATION = {("ga_persist_kernel", "config3", 8000): (27317760 + 571921408) / 30.0}
+# ga_persist_kernel: one 30-generation launch at config3 read 15 527 936 B and wrote 398 512 384 B (profiles/r2_ncu_ga_persist_summary.txt)
+NCU_DRAM_BYTES_PER_GENERATION = {("ga_persist_kernel", "config3", 8000): (15527936 + 398512384) / 30.0}
 METRIC = "tour fitness evals/sec"
 UNIT = "evals/s"
 GA_GENS_PER_STEP = 500          # evaluate.go:294: the reference logs every 500 generations; one step = one such period

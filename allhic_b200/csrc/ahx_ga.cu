@@ -680,17 +680,21 @@ static GaResCfg ga_res_config(const ahx_ctx *ctx, int32_t P, int32_t L, double m
   const bool no_stream = getenv("AHX_EVAL_STREAM") && !atoi(getenv("AHX_EVAL_STREAM"));
   const bool only_stream = getenv("AHX_EVAL_STREAM") && atoi(getenv("AHX_EVAL_STREAM")) == 1;
   auto try_T = [&](int t) {
-    const int G = static_cast<int>(std::min<double>(ctx->sm_count, std::max(1.0, std::ceil(1.2 * expect / t))));
-    const int nbmax = ((P + t - 1) / t + G - 1) / G;
-    for (int stream = 0; stream < 2; ++stream) {   // table resident in shared memory if it fits, streamed otherwise
-      if (stream ? no_stream : only_stream) continue;
-      if (!stream && static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) continue;
-      const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res[res_ti(t)], stream != 0) + ga_res_extra_bytes(P, t, nbmax);
-      if (smem + 1024 > ctx->smem_optin) continue;
-      c.T = t; c.G = G; c.nbmax = nbmax; c.smem = smem; c.stream = stream != 0;
-      return true;
+    // CTAs: enough for the expected mutants; the slot tables must hold the worst case (every offspring mutated) of a
+    // CTA's share, so a large population with a tiny mutation rate takes more CTAs than its mutants need
+    int G = static_cast<int>(std::min<double>(ctx->sm_count, std::max(1.0, std::ceil(1.2 * expect / t))));
+    for (;; G = std::min(ctx->sm_count, 2 * G)) {
+      const int nbmax = ((P + t - 1) / t + G - 1) / G;
+      for (int stream = 0; stream < 2; ++stream) {   // table resident in shared memory if it fits, streamed otherwise
+        if (stream ? no_stream : only_stream) continue;
+        if (!stream && static_cast<uint64_t>(ctx->N) * 4u * t > 65535u) continue;
+        const size_t smem = res_smem_bytes(t, ctx->N, ctx->E_res[res_ti(t)], stream != 0) + ga_res_extra_bytes(P, t, nbmax);
+        if (smem + 1024 > ctx->smem_optin) continue;
+        c.T = t; c.G = G; c.nbmax = nbmax; c.smem = smem; c.stream = stream != 0;
+        return true;
+      }
+      if (G >= ctx->sm_count) return false;
     }
-    return false;
   };
   int want = expect >= 4.0 * ctx->sm_count ? 4 : (expect >= 2.0 * ctx->sm_count ? 2 : 1);
   if (const char *env = getenv("AHX_GA_T")) { const int t = atoi(env); if (t == 1 || t == 2 || t == 4) want = t; }

@@ -9,6 +9,8 @@ size, island) combinations, each checked three ways:
   * the hall of fame is the best individual ever evaluated: its score equals the oracle's score of its tour and the
     best-ever trace never decreases.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -45,7 +47,7 @@ def _run(eng, init, prm_kw, chunks):
     return best, score, st, trace, bad, kernel
 
 
-@pytest.mark.parametrize("case", range(24))
+@pytest.mark.parametrize("case", range(int(os.environ.get("AHX_STRESS_CASES", "24"))))   # AHX_STRESS_CASES=200 for a long soak
 def test_generation_loop_random_configurations(syn, case):
     eng, clm, orc = syn
     rng = np.random.default_rng(9000 + case)

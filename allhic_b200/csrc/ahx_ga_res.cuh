@@ -402,6 +402,29 @@ __device__ __forceinline__ uint32_t ga_finish_mask_rows(const GaRes &q, uint64_t
                                                         uint32_t *rpref, uint32_t *scan_tmp) {
   const int tid = threadIdx.x, WM = (q.P + 31) / 32, WR = (2 * q.P + 31) / 32, wi = tid - WM;
   (void)bar; (void)parity;                                // the caller has waited for the copies (ga_wait_pending)
+  if (WM + WR <= 32) {
+    // small populations (the CLI's default 100: 4 + 7 words): one warp scans both maps with shuffles, one block
+    // barrier instead of five -- at 10 us per generation every barrier of 24 warps shows
+    if (tid < 32) {
+      uint32_t cnt = 0;
+      if (tid < WM) cnt = __popc(mflag[tid]);
+      else if (wi < WR) {
+        uint32_t w = ~rused[wi];
+        const int nvalid = min(32, 2 * q.P - wi * 32);
+        if (nvalid < 32) w &= (1u << nvalid) - 1u;
+        cnt = __popc(w);
+      }
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += n; }
+      const uint32_t excl = incl - cnt, M = __shfl_sync(0xffffffffu, excl, WM);   // lane WM's exclusive prefix = mutants of the mask
+      if (tid < WM) mpref[tid] = excl;
+      else if (wi < WR) rpref[wi] = excl - M;
+      if (tid == 0) scan_tmp[0] = M;
+    }
+    __syncthreads();
+    return scan_tmp[0];
+  }
   if (WM + WR > kRThreads) {
     for (int w = tid; w < WM; w += kRThreads) mpref[w] = __popc(mflag[w]);
     __syncthreads();

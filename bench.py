@@ -436,7 +436,16 @@ def small_leg(A, name, args, dfma):
     ga_s = (st.device_ms - st0.device_ms) * 1e-3
     ga_ev = st.evaluations - st0.evaluations
     eng.ga_end()
+    # orientation phase at this size: flipAll (sparse Lanczos on the host + two EvaluateQ sums) and one flipOne pass
+    rng = np.random.default_rng(7)
+    sg = np.where(rng.random(n) < 0.5, ord('+'), ord('-')).astype(np.uint8)
+    eng.flip_one(tours[0], sg)
+    t0 = time.perf_counter(); eng.flip_one(tours[0], sg); fo_wall = time.perf_counter() - t0; fo_dev = eng.last_device_ms()
+    t0 = time.perf_counter(); eng.flip_all(tours[0], np.full(n, ord('+'), np.uint8)); fa_wall = time.perf_counter() - t0
+    info = eng.flip_all_info()
     out = {"workload": desc, "n_contigs": n, "population": P, "contig_pairs_E": E,
+           "orientation": {"flip_one_pass_ms_device": fo_dev, "flip_one_pass_ms_e2e": fo_wall * 1e3, "flip_all_ms_e2e": fa_wall * 1e3,
+                           "flip_all_lanczos": {"converged": bool(info["converged"]), "dense": bool(info["dense"]), "residual": info["residual"], "matvecs": info["matvecs"]}},
            "evaluate_only": {"evals_per_s": P / ks, "ms_per_launch": ks * 1e3, "kernel": {3: "eval_m_res_kernel (table streamed)", 2: "eval_m_res_kernel", 1: "eval_m_x32_kernel", 0: "eval_m_sparse_kernel"}[kind],
                              "tours_per_batch": tpb,
                              "roofline": {"bound": "fp64", "achieved": P * E * 10.0 / ks / 1e12, "peak": dfma, "unit": "TFLOP/s", "frac": P * E * 10.0 / ks / 1e12 / dfma}},

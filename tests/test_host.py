@@ -134,6 +134,12 @@ def test_cgo_stub_binds_only_declared_entry_points():
         assert re.search(r"\b%s;" % f, params), "ahx_ga_params has no field %s" % f
 
 
+def test_cgo_stub_file_matches_integration_md():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.findall(r"```go\n(.*?)```", doc, re.S)[0]
+    assert open(os.path.join(ROOT, "go", "ahx_cgo.go")).read() == block
+
+
 def test_no_cpu_fallback(built_lib):
     """Without a device the product path must fail loudly, not compute on the CPU."""
     import allhic_b200 as A

@@ -116,48 +116,66 @@ struct FlatMap {
   }
 };
 
+// std::allocator whose default construction leaves the element uninitialised (vector::resize without the zero fill)
+template <typename T>
+struct NoInit : std::allocator<T> {
+  template <typename U> struct rebind { using other = NoInit<U>; };
+  using std::allocator<T>::allocator;
+  template <typename U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <typename U, typename... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+
 struct ahx_clm {
   int32_t n = 0;
   std::vector<std::string> names;
   std::vector<int64_t> sizes;
   std::unordered_map<std::string, int32_t> tig2idx;
-  struct Contact { int32_t ai, bi; int32_t strand; int64_t nlinks; double mean_dist; };
+  struct Contact { int32_t ai, bi; int32_t strand; int64_t nlinks; double mean_dist; int64_t order; };   // order: stamp of the line that created the key
   struct Oriented { int32_t ai, bi; uint8_t ao, bo; std::array<int32_t, AHX_BB> g; };
-  std::vector<Contact> contacts;                       // insertion order
-  FlatMap cmap;
-  // orientedContacts, sharded by key hash so that ahx_clm_parse can fill the shards from several
-  // threads; within a shard entries keep the file's order ("later line wins" is a per-key rule)
+  // contacts and orientedContacts, both sharded by key hash so that ahx_clm_parse can fill the shards from several
+  // threads; within a shard entries keep the file's order ("smallest SumLog wins, the first of equals" and
+  // "later line wins" are per-key rules); a contact remembers the stamp of the line that created its key, which
+  // restores the one cross-key rule there is (finalize: of the keys (a,b) and (b,a) the later-created wins)
+  struct CShard { FlatMap map; std::vector<Contact> v; };
   struct OShard { FlatMap map; std::vector<Oriented> v; };
+  std::vector<CShard> csh = std::vector<CShard>(1);
   std::vector<OShard> osh = std::vector<OShard>(1);
-  size_t shard_of(uint64_t key) const { return osh.size() == 1 ? 0 : static_cast<size_t>((FlatMap::mix(key) >> 40) % osh.size()); }
+  int64_t next_order = 0;                                // builder API: lines arrive one by one
+  // every key of a CLM line -- contacts[(a,b)], orientedContacts[(a,b,ao,bo)] and its mirror -- lives in the shard of the
+  // unordered contig pair, so the parser can bucket whole lines by shard while it tokenises
+  static size_t pair_shard(int32_t a, int32_t b, size_t S) {
+    return S <= 1 ? 0 : static_cast<size_t>((FlatMap::mix(pair_key(std::min(a, b), std::max(a, b))) >> 40) % S);
+  }
   bool finalized = false;
-  std::vector<int32_t> pa, pb, nl, slots, hist;
+  std::vector<int32_t> pa, pb, nl, slots;
+  std::vector<int32_t, NoInit<int32_t>> hist;   // 48 bytes per oriented contact: sized without a zero fill, first touched by the threads that pack it
   std::vector<int8_t> strand;
   std::vector<double> diag;   // O[a][a] from self-pair lines (empty when there are none: `extract` never writes them)
 
-  void apply_contact(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, double mean_dist, int64_t nlinks) {
-    finalized = false;
+  // sh: pair_shard(ai, bi, number of shards) (one thread per shard; csh and osh have the same size)
+  void apply_contact(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, double mean_dist, int64_t nlinks, int64_t order, size_t sh) {
+    const uint64_t key = pair_key(ai, bi);
+    CShard &cs = csh[sh];
     const int32_t st = (ao != bo) ? -1 : 1;                                 // clm.go:224-227
     bool fresh;
-    const int64_t at = *cmap.insert(pair_key(ai, bi), static_cast<int64_t>(contacts.size()), &fresh);
+    const int64_t at = *cs.map.insert(key, static_cast<int64_t>(cs.v.size()), &fresh);
     if (fresh) {
-      contacts.push_back({ai, bi, st, nlinks, mean_dist});
+      cs.v.push_back({ai, bi, st, nlinks, mean_dist, order});
     } else {
-      Contact &c = contacts[at];
+      Contact &c = cs.v[at];
       if (mean_dist < c.mean_dist) { c.strand = st; c.nlinks = nlinks; c.mean_dist = mean_dist; }   // clm.go:229-236
     }
   }
   void apply_line(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g,
                   double mean_dist, int64_t nlinks) {
-    apply_contact(ai, bi, ao, bo, mean_dist, nlinks);
-    put_oriented(ai, bi, ao, bo, g, -1);
-    put_oriented(bi, ai, rr(bo), rr(ao), g, -1);                            // clm.go:238
+    finalized = false;
+    const size_t sh = pair_shard(ai, bi, csh.size());
+    apply_contact(ai, bi, ao, bo, mean_dist, nlinks, next_order++, sh);
+    put_oriented(ai, bi, ao, bo, g, sh);
+    put_oriented(bi, ai, rr(bo), rr(ao), g, sh);                            // clm.go:238
   }
-  // only < 0: whatever the key's shard; else only when the key belongs to shard `only` (one thread per shard)
-  void put_oriented(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g, int only) {
+  void put_oriented(int32_t ai, int32_t bi, uint8_t ao, uint8_t bo, const std::array<int32_t, AHX_BB> &g, size_t sh) {
     const uint64_t key = okey(ai, bi, ao, bo);
-    const size_t sh = shard_of(key);
-    if (only >= 0 && sh != static_cast<size_t>(only)) return;
     OShard &o = osh[sh];
     bool fresh;
     const int64_t at = *o.map.insert(key, static_cast<int64_t>(o.v.size()), &fresh);
@@ -205,8 +223,8 @@ struct ParsedLine { int32_t ai, bi; uint8_t ao, bo; std::array<int32_t, AHX_BB> 
 // tokenised and histogrammed once, whatever the number of groups.
 struct Hit { int32_t group, ai, bi; };
 template <typename Resolve>
-bool parse_chunk(const Resolve &resolve, const char *buf, size_t beg, size_t end, size_t total,
-                 std::vector<std::vector<ParsedLine>> *out, std::string *err) {
+bool parse_chunk(const Resolve &resolve, const char *buf, size_t beg, size_t end, size_t total, size_t S,
+                 std::vector<std::vector<ParsedLine>> *out /* [group * S + shard] */, std::string *err) {
   std::vector<Hit> hits;
   std::vector<int64_t> dists;
   size_t p = beg;
@@ -245,7 +263,7 @@ bool parse_chunk(const Resolve &resolve, const char *buf, size_t beg, size_t end
       }
       pl.nlinks = static_cast<int64_t>(dists.size());                      // len(line.links), clm.go:228
       golden_and_sumlog(dists.data(), pl.nlinks, pl.g.data(), &pl.sumlog);
-      for (const Hit &h : hits) { pl.ai = h.ai; pl.bi = h.bi; (*out)[h.group].push_back(pl); }
+      for (const Hit &h : hits) { pl.ai = h.ai; pl.bi = h.bi; (*out)[h.group * S + ahx_clm::pair_shard(h.ai, h.bi, S)].push_back(pl); }
     }
     p = next;
   }
@@ -287,6 +305,7 @@ extern "C" {
 // resolved against every group's REfile, GoldenArray / SumLog once per kept line), then every group's
 // two maps are filled in file order -- "smallest SumLog wins" / "last line wins" exactly like the
 // single-threaded Go loop (clm.go:221-238) run on that group alone.
+static int finalize_impl(ahx_clm *clm, int nthreads);
 static int parse_groups(const char *clmfile, const char *const *refiles, int32_t n_groups, int nthreads, ahx_clm **out) {
   std::vector<ahx_clm *> clms(n_groups, nullptr);
   auto drop = [&] { for (auto *c : clms) delete c; };
@@ -328,58 +347,63 @@ static int parse_groups(const char *clmfile, const char *const *refiles, int32_t
     for (auto &x : ia->second)
       for (auto &y : ib->second) if (x.first == y.first) hits->push_back({x.first, x.second, y.second});
   };
-  std::vector<std::vector<std::vector<ParsedLine>>> parts(nthreads, std::vector<std::vector<ParsedLine>>(n_groups));   // [chunk][group]
+  // shards per group: one group is applied by up to 8 threads, several groups by one thread each
+  const size_t S = n_groups == 1 ? static_cast<size_t>(std::max(1, std::min(napply, 8))) : 1;
+  std::vector<std::vector<std::vector<ParsedLine>>> parts(nthreads, std::vector<std::vector<ParsedLine>>(n_groups * S));   // [chunk][group * S + shard]
   std::vector<std::string> errs(nthreads);
   std::vector<char> ok(nthreads, 1);
   {
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t)
       th.emplace_back([&, t] {
-        ok[t] = n_groups == 1 ? parse_chunk(resolve1, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t])
-                              : parse_chunk(resolveN, m.p, cut[t], cut[t + 1], m.n, &parts[t], &errs[t]);
+        ok[t] = n_groups == 1 ? parse_chunk(resolve1, m.p, cut[t], cut[t + 1], m.n, S, &parts[t], &errs[t])
+                              : parse_chunk(resolveN, m.p, cut[t], cut[t + 1], m.n, S, &parts[t], &errs[t]);
       });
     for (auto &x : th) x.join();
   }
   const auto t_parse = std::chrono::steady_clock::now();
   for (int t = 0; t < nthreads; ++t)
     if (!ok[t]) { set_global_error(errs[t]); drop(); return AHX_ERR_IO; }
-  // the two maps of a group are independent: one thread applies `contacts`, S threads one shard of
-  // `orientedContacts` each (every thread walks the group's lines in file order and keeps its shard's keys);
+  // both maps of a group are sharded by key hash: S threads each walk the group's lines in file order and keep
+  // the keys of their shard (`contacts`: smallest SumLog wins, `orientedContacts`: last line wins -- per-key rules);
   // several groups: the groups are spread over the threads instead, one shard each
   std::vector<int> rcs(n_groups, AHX_OK);
   std::vector<std::string> ferr(n_groups);
-  auto apply_group = [&](int32_t g, int S) {
+  auto apply_group = [&](int32_t g) {
     ahx_clm *clm = clms[g];
     size_t nlines = 0;
-    for (auto &part : parts) nlines += part[g].size();
-    clm->osh.assign(static_cast<size_t>(S), ahx_clm::OShard{});
+    for (auto &part : parts) for (size_t sh = 0; sh < S; ++sh) nlines += part[g * S + sh].size();
+    clm->osh.assign(S, ahx_clm::OShard{});
+    clm->csh.assign(S, ahx_clm::CShard{});
     std::vector<std::thread> ap;
-    auto contacts = [&, clm, nlines] {
-      clm->cmap.reserve(nlines / 2 + 16); clm->contacts.reserve(nlines / 2 + 16);
-      for (auto &part : parts)
-        for (auto &pl : part[g]) clm->apply_contact(pl.ai, pl.bi, pl.ao, pl.bo, pl.sumlog, pl.nlinks);
-    };
-    auto shard = [&, clm, nlines, S](int sh) {
+    // thread sh applies the lines the tokenisers bucketed into shard sh, in file order: contacts and oriented contacts
+    auto shard = [&, clm, g](size_t sh) {
+      size_t mine = 0;
+      for (auto &part : parts) mine += part[g * S + sh].size();
       ahx_clm::OShard &o = clm->osh[sh];
-      o.map.reserve(2 * nlines / S + nlines / (4 * S) + 16); o.v.reserve(2 * nlines / S + nlines / (4 * S) + 16);
+      ahx_clm::CShard &c = clm->csh[sh];
+      o.map.reserve(2 * mine + mine / 4 + 16); o.v.reserve(2 * mine + mine / 4 + 16);
+      c.map.reserve(mine / 2 + mine / 8 + 16); c.v.reserve(mine / 2 + mine / 8 + 16);
+      int64_t order = 0;   // stamps are only compared between the keys (a,b) and (b,a), which share a shard
       for (auto &part : parts)
-        for (auto &pl : part[g]) {
+        for (auto &pl : part[g * S + sh]) {
+          clm->apply_contact(pl.ai, pl.bi, pl.ao, pl.bo, pl.sumlog, pl.nlinks, order++, sh);
           clm->put_oriented(pl.ai, pl.bi, pl.ao, pl.bo, pl.g, sh);
           clm->put_oriented(pl.bi, pl.ai, rr(pl.bo), rr(pl.ao), pl.g, sh);
         }
     };
-    if (S == 1) { contacts(); shard(0); }
+    if (S == 1) shard(0);
     else {
-      ap.emplace_back(contacts);
-      for (int sh = 0; sh < S; ++sh) ap.emplace_back(shard, sh);
+      for (size_t sh = 0; sh < S; ++sh) ap.emplace_back(shard, sh);
       for (auto &x : ap) x.join();
     }
+    clm->next_order = static_cast<int64_t>(nlines);
   };
   std::chrono::steady_clock::time_point t_apply;
   if (n_groups == 1) {
-    apply_group(0, std::max(1, std::min(napply - 1, 8)));
+    apply_group(0);
     t_apply = std::chrono::steady_clock::now();
-    rcs[0] = ahx_clm_finalize(clms[0]);
+    rcs[0] = finalize_impl(clms[0], napply);
     if (rcs[0] != AHX_OK) ferr[0] = global_error();
   } else {
     std::vector<std::thread> gt;
@@ -387,7 +411,7 @@ static int parse_groups(const char *clmfile, const char *const *refiles, int32_t
     for (int t = 0; t < std::min<int>(napply, n_groups); ++t)
       gt.emplace_back([&] {
         for (int32_t g = next++; g < n_groups; g = next++) {
-          apply_group(g, 1);
+          apply_group(g);
           for (auto &part : parts) std::vector<ParsedLine>().swap(part[g]);
           rcs[g] = ahx_clm_finalize(clms[g]);
           if (rcs[g] != AHX_OK) ferr[g] = global_error();
@@ -439,13 +463,18 @@ int ahx_clm_add_line(ahx_clm *clm, int32_t ai, int32_t bi, uint8_t ao, uint8_t b
   return AHX_OK;
 }
 
-int ahx_clm_finalize(ahx_clm *clm) {
+// nthreads > 1: the oriented entries are looked up and the histograms packed by several threads (the result is the
+// same table: rows and slots are positions, not insertion orders)
+static int finalize_impl(ahx_clm *clm, int nthreads) {
   if (!clm) { set_global_error("ahx_clm_finalize: null"); return AHX_ERR_ARG; }
   if (clm->finalized) return AHX_OK;
+  const auto tf0 = std::chrono::steady_clock::now();
+  auto tf = [&](const char *what) { if (getenv("AHX_CLM_TIMING2")) fprintf(stderr, "  finalize %s at %.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count()); };
   // rows = unordered pairs {a<b}, sorted by (a,b) so that consecutive rows share `a`
   std::vector<uint64_t> keys;
-  keys.reserve(clm->contacts.size());
-  for (auto &c : clm->contacts) if (c.ai != c.bi) keys.push_back(pair_key(std::min(c.ai, c.bi), std::max(c.ai, c.bi)));
+  { size_t nc = 0; for (auto &cs : clm->csh) nc += cs.v.size(); keys.reserve(nc); }
+  for (auto &cs : clm->csh)
+    for (auto &c : cs.v) if (c.ai != c.bi) keys.push_back(pair_key(std::min(c.ai, c.bi), std::max(c.ai, c.bi)));
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
   const size_t E = keys.size();
@@ -463,37 +492,76 @@ int ahx_clm_finalize(ahx_clm *clm) {
   // order is random; when both (a,b) and (b,a) keys exist (never written by
   // `extract`, extract.go:477-481) the later-inserted key wins here.
   clm->diag.clear();
-  for (auto &c : clm->contacts) {
-    if (c.ai == c.bi) {   // a self-pair line: never read by M() / Q() (i < j are distinct contigs), but O() puts it on the diagonal (SetSym(a, a, ...))
-      if (clm->diag.empty()) clm->diag.assign(clm->n, 0.0);
-      clm->diag[c.ai] = static_cast<double>(c.strand) * static_cast<double>(c.nlinks);
-      continue;
+  std::vector<int64_t> won(E, -1);                       // stamp of the key that currently owns the row
+  for (auto &cs : clm->csh)
+    for (auto &c : cs.v) {
+      if (c.ai == c.bi) {   // a self-pair line: never read by M() / Q() (i < j are distinct contigs), but O() puts it on the diagonal (SetSym(a, a, ...))
+        if (clm->diag.empty()) clm->diag.assign(clm->n, 0.0);
+        clm->diag[c.ai] = static_cast<double>(c.strand) * static_cast<double>(c.nlinks);
+        continue;
+      }
+      const int64_t e = row_of(c.ai, c.bi);
+      if (c.nlinks > INT32_MAX) { set_global_error("nlinks exceeds int32"); return AHX_ERR_ARG; }
+      if (c.order < won[e]) continue;                    // the key created later wins the row
+      won[e] = c.order;
+      clm->nl[e] = static_cast<int32_t>(c.nlinks);
+      clm->strand[e] = static_cast<int8_t>(c.strand);
     }
-    const int64_t e = row_of(c.ai, c.bi);
-    if (c.nlinks > INT32_MAX) { set_global_error("nlinks exceeds int32"); return AHX_ERR_ARG; }
-    clm->nl[e] = static_cast<int32_t>(c.nlinks);
-    clm->strand[e] = static_cast<int8_t>(c.strand);
-  }
+  tf("rows+contacts");
   // histograms in (row, slot) order, whatever the insertion order (and the sharding) was
   std::vector<const ahx_clm::Oriented *> ref(E * 8, nullptr);
-  for (auto &sh : clm->osh)
-    for (auto &o : sh.v) {
-      if (o.ai == o.bi) continue;                       // Q[a][a] is never read (i<j are distinct contigs)
-      const bool sa = o.ao == '-', sb = o.bo == '-';
-      if ((!sa && o.ao != '+') || (!sb && o.bo != '+')) continue;  // can never equal a Signs byte
-      const int64_t e = row_of(o.ai, o.bi);
-      if (e < 0) continue;
-      const int dir = o.ai < o.bi ? 0 : 1;
-      ref[e * 8 + dir * 4 + 2 * (sa ? 1 : 0) + (sb ? 1 : 0)] = &o;
+  auto fill_refs = [&](size_t sh0, size_t step) {       // a key lives in exactly one shard: no two threads write one slot
+    for (size_t si = sh0; si < clm->osh.size(); si += step)
+      for (auto &o : clm->osh[si].v) {
+        if (o.ai == o.bi) continue;                       // Q[a][a] is never read (i<j are distinct contigs)
+        const bool sa = o.ao == '-', sb = o.bo == '-';
+        if ((!sa && o.ao != '+') || (!sb && o.bo != '+')) continue;  // can never equal a Signs byte
+        const int64_t e = row_of(o.ai, o.bi);
+        if (e < 0) continue;
+        const int dir = o.ai < o.bi ? 0 : 1;
+        ref[e * 8 + dir * 4 + 2 * (sa ? 1 : 0) + (sb ? 1 : 0)] = &o;
+      }
+  };
+  const size_t nt = static_cast<size_t>(std::max(1, std::min<int>(nthreads, 16)));
+  if (nt == 1 || ref.size() < (1u << 16)) {
+    fill_refs(0, 1);
+    for (size_t i = 0; i < ref.size(); ++i) {
+      if (!ref[i]) continue;
+      clm->slots[i] = static_cast<int32_t>(clm->hist.size() / AHX_BB);
+      clm->hist.insert(clm->hist.end(), ref[i]->g.begin(), ref[i]->g.end());
     }
-  for (size_t i = 0; i < ref.size(); ++i) {
-    if (!ref[i]) continue;
-    clm->slots[i] = static_cast<int32_t>(clm->hist.size() / AHX_BB);
-    clm->hist.insert(clm->hist.end(), ref[i]->g.begin(), ref[i]->g.end());
+  } else {
+    {
+      std::vector<std::thread> th;
+      const size_t step = std::min(nt, std::max<size_t>(1, clm->osh.size()));
+      for (size_t t = 0; t < step; ++t) th.emplace_back(fill_refs, t, step);
+      for (auto &x : th) x.join();
+    }
+    tf("refs");
+    // pack the histograms in slot order: count per chunk, prefix, copy
+    std::vector<size_t> cnt(nt + 1, 0);
+    const size_t chunk = (ref.size() + nt - 1) / nt;
+    auto count = [&](size_t t) { size_t c = 0; for (size_t i = t * chunk; i < std::min(ref.size(), (t + 1) * chunk); ++i) c += ref[i] != nullptr; cnt[t + 1] = c; };
+    { std::vector<std::thread> th; for (size_t t = 0; t < nt; ++t) th.emplace_back(count, t); for (auto &x : th) x.join(); }
+    for (size_t t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
+    clm->hist.resize(cnt[nt] * AHX_BB);
+    auto pack = [&](size_t t) {
+      size_t h = cnt[t];
+      for (size_t i = t * chunk; i < std::min(ref.size(), (t + 1) * chunk); ++i) {
+        if (!ref[i]) continue;
+        clm->slots[i] = static_cast<int32_t>(h);
+        std::copy(ref[i]->g.begin(), ref[i]->g.end(), clm->hist.begin() + static_cast<std::ptrdiff_t>(h * AHX_BB));
+        ++h;
+      }
+    };
+    { std::vector<std::thread> th; for (size_t t = 0; t < nt; ++t) th.emplace_back(pack, t); for (auto &x : th) x.join(); }
   }
+  tf("packed");
   clm->finalized = true;
   return AHX_OK;
 }
+
+int ahx_clm_finalize(ahx_clm *clm) { return finalize_impl(clm, 1); }
 
 void ahx_clm_free(ahx_clm *clm) { delete clm; }
 int32_t ahx_clm_ntigs(const ahx_clm *clm) { return clm ? clm->n : 0; }

@@ -82,6 +82,38 @@ def test_parser_edge_cases(built_lib, tmp_path):
         O.OracleCLM(str(bad), str(ids))
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_parser_random_files_any_thread_count(built_lib, tmp_path, seed):
+    """Random CLM text with everything the map semantics can trip over -- pairs written in both contig orders
+    ((a,b) and (b,a) are different keys of `contacts`: the later-created one owns the row of M), repeated
+    (pair, orientation) lines (last GArray wins, smallest SumLog wins), contigs missing from the REfile, self pairs
+    -- parsed with 1, 2, 5 and all threads (the lines are bucketed by contig-pair shard and applied by one thread per
+    shard): the same tables as the oracle's single-threaded loop (clm.go:221-238), whatever the thread count."""
+    import allhic_b200 as A
+    rng = np.random.default_rng(seed)
+    n = 40
+    ids = tmp_path / "r.ids"; clmf = tmp_path / "r.clm"
+    ids.write_text("#Contig\tRECounts\tLength\n" + "".join("c%d\t1\t%d\n" % (i, rng.integers(1000, 900000)) for i in range(n)))
+    lines = []
+    for _ in range(6000):                                                   # ~ 400 KB: several tokeniser chunks
+        a, b = rng.integers(0, n + 2, 2)                                   # n, n + 1: not in the REfile
+        if rng.random() < 0.02:
+            b = a
+        d = rng.integers(1, 3_000_000, rng.integers(1, 14))
+        lines.append("c%d%s c%d%s\t%d\t%s\n" % (a, "+-"[rng.integers(2)], b, "+-"[rng.integers(2)], len(d), " ".join(map(str, d))))
+    clmf.write_text("".join(lines))
+    orc = O.OracleCLM(str(clmf), str(ids))
+    first = None
+    for nt in (1, 2, 5, 0):
+        c = A.CLM(str(clmf), str(ids), nthreads=nt)
+        _check_clm_against_oracle(c, orc)
+        t = c.tables()
+        if first is None:
+            first = t
+        else:
+            assert all((t[k] == first[k]).all() for k in ("pa", "pb", "nlinks", "strand", "slots", "hist"))
+
+
 def test_builder_equals_parser(built_lib, oracle_fixture):
     """ahx_clm_new + ahx_clm_add_line (what the Go readClm loop would call) == ahx_clm_parse."""
     import allhic_b200 as A
